@@ -1,0 +1,53 @@
+"""Builds libfdts_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so
+travels to the GPU box with the repository snapshot)."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SOURCES = ["fdts_api.cu", "pattern.cu", "inst_heat.cu", "inst_bbm.cu", "inst_burgers.cu", "inst_ch.cu",
+           "kernels_heat.cu", "microbench.cu"]
+HEADERS = ["fdts_common.cuh", "kernels_generic.cuh", "kargs.cuh", "../../include/fdts.h"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
+         "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+LIB = os.path.join(HERE, "libfdts_b200.so")
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _compile(src):
+    obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+    deps = [os.path.join(HERE, src)] + [os.path.join(HERE, h) for h in HEADERS]
+    if _stale(obj, deps):
+        log = obj + ".log"
+        with open(log, "w") as f:
+            subprocess.check_call([NVCC, *FLAGS, "-c", os.path.join(HERE, src), "-o", obj], stdout=f, stderr=f)
+    return obj
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    if force:
+        for f in os.listdir(os.path.join(HERE, "build")):
+            os.remove(os.path.join(HERE, "build", f))
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(_compile, SOURCES))
+    if _stale(LIB, objs):
+        subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+                               "-lcudart"])
+        if verbose:
+            print("linked", LIB)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)

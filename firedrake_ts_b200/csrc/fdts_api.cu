@@ -1,0 +1,428 @@
+// fdts_api.cu -- the C ABI of libfdts_b200.so (see include/fdts.h for the
+// reference interfaces each entry point replaces).
+#include <string.h>
+
+#include <mutex>
+
+#include "kargs.cuh"
+
+static thread_local std::string g_err;
+void fdts_set_error(const std::string &msg) { g_err = msg; }
+extern "C" const char *fdts_last_error(void) { return g_err.c_str(); }
+extern "C" const char *fdts_version(void) { return "fdts_b200 0.1 (sm_100a)"; }
+
+namespace {
+
+__global__ void transpose_i32(const int32_t *__restrict__ in, int64_t rows, int cols, int32_t *__restrict__ out) {
+  // in: rows x cols (AoS), out: cols x rows (SoA)
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * cols) return;
+  const int c = (int)(t / rows);
+  const int64_t r = t - (int64_t)c * rows;
+  out[t] = in[r * cols + c];
+}
+
+__global__ void set_values(double *__restrict__ v, const int64_t *__restrict__ slots, int64_t n, double val) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n && slots[t] >= 0) v[slots[t]] = val;
+}
+
+__global__ void expand_rowptr(const int64_t *__restrict__ nrp, int64_t nown, int nc, int layout, int64_t node_nnz,
+                              int64_t *__restrict__ rowptr) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > nown * nc) return;
+  if (t == nown * nc) {
+    rowptr[t] = node_nnz * nc * nc;
+    return;
+  }
+  int64_t n;
+  int m;
+  if (layout == FDTS_INTERLEAVED) {
+    n = t / nc;
+    m = (int)(t - n * nc);
+    const int64_t len = nrp[n + 1] - nrp[n];
+    rowptr[t] = nrp[n] * nc * nc + (int64_t)m * len * nc;
+  } else {
+    m = (int)(t / nown);
+    n = t - (int64_t)m * nown;
+    rowptr[t] = (int64_t)m * nc * node_nnz + (int64_t)nc * nrp[n];
+  }
+}
+
+__global__ void expand_colidx(const int64_t *__restrict__ nrp, const int32_t *__restrict__ nci, int64_t nown, int nc,
+                              int layout, int64_t node_nnz, int64_t nnodes, int32_t *__restrict__ colidx) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (n >= nown) return;
+  const int64_t b = nrp[n];
+  const int64_t len = nrp[n + 1] - b;
+  for (int64_t k = lane; k < len; k += 32) {
+    const int64_t col = nci[b + k];
+    for (int m = 0; m < nc; ++m)
+      for (int g = 0; g < nc; ++g) {
+        if (layout == FDTS_INTERLEAVED)
+          colidx[b * nc * nc + (int64_t)m * len * nc + k * nc + g] = (int32_t)(col * nc + g);
+        else
+          colidx[(int64_t)m * nc * node_nnz + (int64_t)nc * b + (int64_t)g * len + k] =
+              (int32_t)((int64_t)g * nnodes + col);
+      }
+  }
+}
+
+__global__ void pack_nodes(const double *__restrict__ x, const int32_t *__restrict__ nodes, int64_t count, int nc,
+                           int layout, int64_t nnodes, double *__restrict__ buf) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count * nc) return;
+  const int m = (int)(t / count);
+  const int64_t k = t - (int64_t)m * count;
+  const int64_t n = nodes[k];
+  buf[t] = x[layout == FDTS_INTERLEAVED ? n * nc + m : (int64_t)m * nnodes + n];
+}
+
+__global__ void unpack_nodes(double *__restrict__ x, int64_t first, int64_t count, int nc, int layout, int64_t nnodes,
+                             const double *__restrict__ buf) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count * nc) return;
+  const int m = (int)(t / count);
+  const int64_t n = first + (t - (int64_t)m * count);
+  x[layout == FDTS_INTERLEAVED ? n * nc + m : (int64_t)m * nnodes + n] = buf[t];
+}
+
+template <typename T>
+int upload(T **dst, const T *src, size_t n, int memspace) {
+  FDTS_CHECK(cudaMalloc((void **)dst, sizeof(T) * (n > 0 ? n : 1)));
+  if (n == 0) return 0;
+  FDTS_CHECK(cudaMemcpy(*dst, src, sizeof(T) * n,
+                        memspace == FDTS_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice));
+  return 0;
+}
+
+}  // namespace
+
+#define GRID(n, b) (unsigned)(((n) + (b)-1) / (b))
+#define RET_IF(x)          \
+  do {                     \
+    int rc_ = (x);         \
+    if (rc_) return rc_;   \
+  } while (0)
+
+KArgs fdts_make_kargs(fdts_engine *e, const double *x, const double *xdot, double shift, double *out, int64_t c0,
+                      int64_t c1) {
+  KArgs a;
+  a.coords = e->coords;
+  a.cell_coord_t = e->cell_coord;
+  a.cell_node_t = e->cell_node;
+  a.B = e->B;
+  a.w = e->w;
+  a.x = x;
+  a.xdot = xdot;
+  a.out = out;
+  a.isbc = e->isbc;
+  a.nrowptr = e->nrowptr;
+  a.pos8_t = e->pos8;
+  a.ncells_total = e->cfg.num_cells;
+  a.c0 = c0;
+  a.c1 = c1;
+  a.nown = e->cfg.num_owned_nodes;
+  a.nnodes = e->cfg.num_nodes;
+  a.node_nnz = e->node_nnz;
+  a.nq = e->cfg.nq;
+  a.shift = shift;
+  a.p0 = e->cfg.params[0];
+  a.p1 = e->cfg.params[1];
+  return a;
+}
+
+int fdts_launch_residual(fdts_engine *e, const double *x, const double *xdot, double *f, int64_t c0, int64_t c1,
+                         cudaStream_t s) {
+  KArgs a = fdts_make_kargs(e, x, xdot, 0.0, f, c0, c1);
+  int rc = 3;
+  switch (e->cfg.family) {
+    case FDTS_HEAT: rc = fdts_generic_heat(false, e, a, s); break;
+    case FDTS_BBM: rc = fdts_generic_bbm(false, e, a, s); break;
+    case FDTS_BURGERS: rc = fdts_generic_burgers(false, e, a, s); break;
+    case FDTS_CAHN_HILLIARD: rc = fdts_generic_ch(false, e, a, s); break;
+  }
+  if (rc == 3) fdts_set_error("no residual kernel for this family/dimension/degree");
+  if (rc == 2) fdts_set_error(std::string("residual kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+  if (rc == 0 && c1 > c0) e->launches++;
+  return rc;
+}
+
+int fdts_launch_jacobian(fdts_engine *e, const double *x, const double *xdot, double shift, double *vals, int64_t c0,
+                         int64_t c1, cudaStream_t s) {
+  KArgs a = fdts_make_kargs(e, x, xdot, shift, vals, c0, c1);
+  int rc = 3;
+  switch (e->cfg.family) {
+    case FDTS_HEAT: rc = fdts_generic_heat(true, e, a, s); break;
+    case FDTS_BBM: rc = fdts_generic_bbm(true, e, a, s); break;
+    case FDTS_BURGERS: rc = fdts_generic_burgers(true, e, a, s); break;
+    case FDTS_CAHN_HILLIARD: rc = fdts_generic_ch(true, e, a, s); break;
+  }
+  if (rc == 3) fdts_set_error("no Jacobian kernel for this family/dimension/degree");
+  if (rc == 2) fdts_set_error(std::string("Jacobian kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+  if (rc == 0 && c1 > c0) e->launches++;
+  return rc;
+}
+
+extern "C" int fdts_create(const fdts_config *cfg, fdts_handle *out) {
+  if (!cfg || !out) {
+    fdts_set_error("null argument");
+    return 1;
+  }
+  if (cfg->dim < 1 || cfg->dim > 3 || cfg->nd < 2 || cfg->nd > 20 || cfg->ncomp < 1 || cfg->ncomp > 3) {
+    fdts_set_error("unsupported dim/nd/ncomp");
+    return 1;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    fdts_set_error("no CUDA device available: this engine has no CPU fallback");
+    return 2;
+  }
+  FDTS_CHECK(cudaSetDevice(cfg->device));
+  fdts_engine *e = new fdts_engine();
+  e->cfg = *cfg;
+  e->device = cfg->device;
+  const int d = cfg->dim, nd = cfg->nd, ms = cfg->memspace;
+  const int64_t nc = cfg->num_cells;
+  int rc = 0;
+  int32_t *tmp_cc = nullptr, *tmp_cn = nullptr;
+  do {
+    if ((rc = upload(&e->coords, cfg->coords, (size_t)cfg->num_coord_nodes * d, ms))) break;
+    if ((rc = upload(&tmp_cc, cfg->cell_coord, (size_t)nc * (d + 1), ms))) break;
+    if ((rc = upload(&tmp_cn, cfg->cell_node, (size_t)nc * nd, ms))) break;
+    if (cudaMalloc(&e->cell_coord, sizeof(int32_t) * (size_t)(nc * (d + 1) + 1)) != cudaSuccess ||
+        cudaMalloc(&e->cell_node, sizeof(int32_t) * (size_t)(nc * nd + 1)) != cudaSuccess) {
+      fdts_set_error("out of device memory for the cell maps");
+      rc = 2;
+      break;
+    }
+    if (nc > 0) {
+      transpose_i32<<<GRID(nc * (d + 1), 256), 256>>>(tmp_cc, nc, d + 1, e->cell_coord);
+      transpose_i32<<<GRID(nc * nd, 256), 256>>>(tmp_cn, nc, nd, e->cell_node);
+    }
+    if ((rc = upload(&e->B, cfg->B, (size_t)cfg->nq * (d + 1) * nd, ms))) break;
+    if ((rc = upload(&e->w, cfg->w, (size_t)cfg->nq, ms))) break;
+    if ((rc = upload(&e->R, cfg->R, (size_t)(d + 1) * (d + 1) * nd * nd, ms))) break;
+    if ((rc = upload(&e->M0, cfg->M0, (size_t)nd, ms))) break;
+    if ((rc = upload(&e->bc_nodes, cfg->bc_nodes, (size_t)cfg->num_bc_nodes, ms))) break;
+    if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      fdts_set_error("stream creation failed");
+      rc = 2;
+      break;
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+      fdts_set_error("upload failed");
+      rc = 2;
+      break;
+    }
+    rc = fdts_build_pattern(e, e->own_stream);
+  } while (0);
+  cudaFree(tmp_cc);
+  cudaFree(tmp_cn);
+  // host pointers are not retained
+  e->cfg.coords = nullptr; e->cfg.cell_coord = nullptr; e->cfg.cell_node = nullptr;
+  e->cfg.B = nullptr; e->cfg.w = nullptr; e->cfg.R = nullptr; e->cfg.M0 = nullptr; e->cfg.bc_nodes = nullptr;
+  if (rc) {
+    fdts_destroy(e);
+    return rc;
+  }
+  *out = e;
+  return 0;
+}
+
+extern "C" int fdts_destroy(fdts_handle e) {
+  if (!e) return 0;
+  cudaSetDevice(e->device);
+  void *ptrs[] = {e->coords, e->cell_coord, e->cell_node, e->B, e->w, e->R, e->M0, e->isbc, e->bc_nodes,
+                  e->bc_diag_slot, e->nrowptr, e->ncolidx, e->pos8, e->adj_ptr, e->adj_cell, e->h2d_x, e->h2d_xdot,
+                  e->d_f, e->d_vals};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  delete e;
+  return 0;
+}
+
+extern "C" int fdts_sizes(fdts_handle e, fdts_sizes_t *out) {
+  if (!e || !out) return 1;
+  const int nc = e->cfg.ncomp;
+  out->num_rows = e->cfg.num_owned_nodes * nc;
+  out->num_cols = e->cfg.num_nodes * nc;
+  out->nnz = e->node_nnz * nc * nc;
+  out->node_nnz = e->node_nnz;
+  out->max_row_nodes = e->max_row_nodes;
+  out->reserved = e->max_degree;
+  return 0;
+}
+
+extern "C" int fdts_get_node_csr(fdts_handle e, int64_t *rowptr, int32_t *colidx, void *stream) {
+  if (!e) return 1;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (rowptr)
+    FDTS_CHECK(cudaMemcpyAsync(rowptr, e->nrowptr, sizeof(int64_t) * (e->cfg.num_owned_nodes + 1),
+                               cudaMemcpyDeviceToDevice, s));
+  if (colidx && e->node_nnz)
+    FDTS_CHECK(cudaMemcpyAsync(colidx, e->ncolidx, sizeof(int32_t) * e->node_nnz, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+extern "C" int fdts_get_csr(fdts_handle e, int64_t *rowptr, int32_t *colidx, void *stream) {
+  if (!e) return 1;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t nown = e->cfg.num_owned_nodes;
+  const int nc = e->cfg.ncomp;
+  if (rowptr) {
+    expand_rowptr<<<GRID(nown * nc + 1, 256), 256, 0, s>>>(e->nrowptr, nown, nc, e->cfg.layout, e->node_nnz, rowptr);
+    e->launches++;
+  }
+  if (colidx && nown > 0) {
+    expand_colidx<<<GRID(nown, 4), 128, 0, s>>>(e->nrowptr, e->ncolidx, nown, nc, e->cfg.layout, e->node_nnz,
+                                               e->cfg.num_nodes, colidx);
+    e->launches++;
+  }
+  FDTS_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fdts_set_param(fdts_handle e, int32_t index, double value) {
+  if (!e || index < 0 || index > 3) return 1;
+  e->cfg.params[index] = value;
+  return 0;
+}
+
+extern "C" int fdts_set_option(fdts_handle e, const char *key, int64_t value) {
+  if (!e || !key) return 1;
+  if (!strcmp(key, "scatter")) {
+    e->opt_scatter = value;
+    return 0;
+  }
+  fdts_set_error(std::string("unknown option ") + key);
+  return 1;
+}
+
+extern "C" int fdts_get_option(fdts_handle e, const char *key, int64_t *value) {
+  if (!e || !key || !value) return 1;
+  if (!strcmp(key, "scatter")) {
+    *value = e->opt_scatter;
+    return 0;
+  }
+  fdts_set_error(std::string("unknown option ") + key);
+  return 1;
+}
+
+static bool use_fast_heat(fdts_engine *e) {
+  return e->opt_scatter == 1 && e->cfg.family == FDTS_HEAT && e->cfg.ncomp == 1;
+}
+
+extern "C" int fdts_ifunction_range(fdts_handle e, double t, const double *x, const double *xdot, double *f,
+                                    int64_t c0, int64_t c1, int32_t flags, void *stream) {
+  (void)t;
+  if (!e || !x || !xdot || !f) {
+    fdts_set_error("null argument");
+    return 1;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (flags & 1) FDTS_CHECK(cudaMemsetAsync(f, 0, sizeof(double) * e->cfg.num_owned_nodes * e->cfg.ncomp, s));
+  RET_IF(fdts_launch_residual(e, x, xdot, f, c0, c1, s));
+  return 0;
+}
+
+extern "C" int fdts_ijacobian_range(fdts_handle e, double t, const double *x, const double *xdot, double shift,
+                                    double *vals, int64_t c0, int64_t c1, int32_t flags, void *stream) {
+  (void)t;
+  if (!e || !x || !xdot || !vals) {
+    fdts_set_error("null argument");
+    return 1;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nc = e->cfg.ncomp;
+  if (flags & 1) FDTS_CHECK(cudaMemsetAsync(vals, 0, sizeof(double) * e->node_nnz * nc * nc, s));
+  RET_IF(fdts_launch_jacobian(e, x, xdot, shift, vals, c0, c1, s));
+  if ((flags & 2) && e->cfg.num_bc_nodes > 0) {
+    const int64_t n = e->cfg.num_bc_nodes * nc;
+    set_values<<<GRID(n, 256), 256, 0, s>>>(vals, e->bc_diag_slot, n, 1.0);
+    e->launches++;
+  }
+  FDTS_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fdts_ifunction(fdts_handle e, double t, const double *x, const double *xdot, double *f, void *stream) {
+  if (!e) return 1;
+  if (use_fast_heat(e)) return fdts_launch_heat(e, 0, x, xdot, 0.0, f, 0, e->cfg.num_cells, (cudaStream_t)stream);
+  return fdts_ifunction_range(e, t, x, xdot, f, 0, e->cfg.num_cells, 1, stream);
+}
+
+extern "C" int fdts_ijacobian(fdts_handle e, double t, const double *x, const double *xdot, double shift, double *vals,
+                              void *stream) {
+  if (!e) return 1;
+  if (use_fast_heat(e)) return fdts_launch_heat(e, 1, x, xdot, shift, vals, 0, e->cfg.num_cells, (cudaStream_t)stream);
+  return fdts_ijacobian_range(e, t, x, xdot, shift, vals, 0, e->cfg.num_cells, 3, stream);
+}
+
+static int ensure_staging(fdts_engine *e) {
+  const int64_t nloc = e->cfg.num_nodes * e->cfg.ncomp;
+  if (!e->h2d_x) {
+    FDTS_CHECK(cudaMalloc(&e->h2d_x, sizeof(double) * (nloc + 1)));
+    FDTS_CHECK(cudaMalloc(&e->h2d_xdot, sizeof(double) * (nloc + 1)));
+    FDTS_CHECK(cudaMalloc(&e->d_f, sizeof(double) * (e->cfg.num_owned_nodes * e->cfg.ncomp + 1)));
+  }
+  return 0;
+}
+
+extern "C" int fdts_ifunction_host(fdts_handle e, double t, const double *x, const double *xdot, double *f) {
+  if (!e) return 1;
+  RET_IF(ensure_staging(e));
+  cudaStream_t s = e->own_stream;
+  const int64_t nloc = e->cfg.num_nodes * e->cfg.ncomp, nown = e->cfg.num_owned_nodes * e->cfg.ncomp;
+  FDTS_CHECK(cudaMemcpyAsync(e->h2d_x, x, sizeof(double) * nloc, cudaMemcpyHostToDevice, s));
+  FDTS_CHECK(cudaMemcpyAsync(e->h2d_xdot, xdot, sizeof(double) * nloc, cudaMemcpyHostToDevice, s));
+  RET_IF(fdts_ifunction(e, t, e->h2d_x, e->h2d_xdot, e->d_f, s));
+  FDTS_CHECK(cudaMemcpyAsync(f, e->d_f, sizeof(double) * nown, cudaMemcpyDeviceToHost, s));
+  FDTS_CHECK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int fdts_ijacobian_host(fdts_handle e, double t, const double *x, const double *xdot, double shift,
+                                   double *vals) {
+  if (!e) return 1;
+  RET_IF(ensure_staging(e));
+  const int nc = e->cfg.ncomp;
+  const int64_t nnz = e->node_nnz * nc * nc;
+  if (!e->d_vals) FDTS_CHECK(cudaMalloc(&e->d_vals, sizeof(double) * (nnz + 1)));
+  cudaStream_t s = e->own_stream;
+  const int64_t nloc = e->cfg.num_nodes * nc;
+  FDTS_CHECK(cudaMemcpyAsync(e->h2d_x, x, sizeof(double) * nloc, cudaMemcpyHostToDevice, s));
+  FDTS_CHECK(cudaMemcpyAsync(e->h2d_xdot, xdot, sizeof(double) * nloc, cudaMemcpyHostToDevice, s));
+  RET_IF(fdts_ijacobian(e, t, e->h2d_x, e->h2d_xdot, shift, e->d_vals, s));
+  FDTS_CHECK(cudaMemcpyAsync(vals, e->d_vals, sizeof(double) * nnz, cudaMemcpyDeviceToHost, s));
+  FDTS_CHECK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int fdts_halo_pack(fdts_handle e, const double *x, const int32_t *nodes, int64_t count, double *buf,
+                              void *stream) {
+  if (!e) return 1;
+  if (count <= 0) return 0;
+  const int nc = e->cfg.ncomp;
+  pack_nodes<<<GRID(count * nc, 256), 256, 0, (cudaStream_t)stream>>>(x, nodes, count, nc, e->cfg.layout,
+                                                                      e->cfg.num_nodes, buf);
+  e->launches++;
+  FDTS_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fdts_halo_unpack(fdts_handle e, double *x, int64_t first, int64_t count, const double *buf,
+                                void *stream) {
+  if (!e) return 1;
+  if (count <= 0) return 0;
+  const int nc = e->cfg.ncomp;
+  unpack_nodes<<<GRID(count * nc, 256), 256, 0, (cudaStream_t)stream>>>(x, first, count, nc, e->cfg.layout,
+                                                                        e->cfg.num_nodes, buf);
+  e->launches++;
+  FDTS_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int64_t fdts_launch_count(fdts_handle e) { return e ? e->launches : 0; }

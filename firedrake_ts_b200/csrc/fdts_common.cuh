@@ -1,0 +1,130 @@
+// fdts_common.cuh -- engine state and device helpers shared by all translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/fdts.h"
+
+#define FDTS_MAXD 3
+
+struct fdts_engine {
+  fdts_config cfg;  // scalars only are meaningful after create; pointers below are device copies
+  int device = 0;
+  // mesh / maps (device)
+  double *coords = nullptr;
+  int32_t *cell_coord = nullptr;
+  int32_t *cell_node = nullptr;
+  // element tables (device)
+  double *B = nullptr, *w = nullptr, *R = nullptr, *M0 = nullptr;
+  // boundary conditions
+  uint8_t *isbc = nullptr;       // per local node
+  int32_t *bc_nodes = nullptr;   // owned Dirichlet nodes
+  int64_t num_bc_owned = 0;
+  int64_t *bc_diag_slot = nullptr;  // dof-level slot of the diagonal entry, per (bc node, comp)
+  // node-level sparsity
+  int64_t *nrowptr = nullptr;    // num_owned_nodes + 1
+  int32_t *ncolidx = nullptr;    // node_nnz
+  int64_t node_nnz = 0;
+  int32_t max_row_nodes = 0;
+  uint8_t *pos8 = nullptr;       // num_cells x nd x nd : position of node j inside node row i
+  // row -> (cell, local index) adjacency, built for the pattern and reused by gather kernels
+  int64_t *adj_ptr = nullptr;    // num_owned_nodes + 1
+  int32_t *adj_cell = nullptr;   // cell * 32 + local index (nd <= 20 < 32)
+  int32_t max_degree = 0;
+  // options
+  int64_t opt_scatter = 0;
+  // scratch
+  double *h2d_x = nullptr, *h2d_xdot = nullptr, *d_f = nullptr, *d_vals = nullptr;  // host-variant staging
+  int64_t launches = 0;
+  cudaStream_t own_stream = nullptr;
+};
+
+void fdts_set_error(const std::string &msg);
+#define FDTS_CHECK(call)                                                                              \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess) {                                                                          \
+      fdts_set_error(std::string(#call) + " failed: " + cudaGetErrorString(e_) + " at " + __FILE__ + \
+                     ":" + std::to_string(__LINE__));                                                 \
+      return 2;                                                                                       \
+    }                                                                                                 \
+  } while (0)
+
+// dispatch entry points implemented per family (kernels_*.cu)
+int fdts_launch_residual(fdts_engine *e, const double *x, const double *xdot, double *f, int64_t c0, int64_t c1,
+                         cudaStream_t s);
+int fdts_launch_jacobian(fdts_engine *e, const double *x, const double *xdot, double shift, double *vals, int64_t c0,
+                         int64_t c1, cudaStream_t s);
+int fdts_launch_heat(fdts_engine *e, int which, const double *x, const double *xdot, double shift, double *out,
+                     int64_t c0, int64_t c1, cudaStream_t s);
+int fdts_build_pattern(fdts_engine *e, cudaStream_t s);
+
+// ------------------------------------------------------------------ device helpers
+__device__ __forceinline__ void red_add_f64(double *addr, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
+
+template <int DIM>
+struct Geom {
+  double Jinv[DIM][DIM];  // Jinv[a][k] = d xi_a / d x_k
+  double adet;
+};
+
+template <int DIM>
+__device__ __forceinline__ void compute_geometry(const double *__restrict__ coords,
+                                                 const int32_t *__restrict__ cc, Geom<DIM> &g) {
+  double X[DIM + 1][DIM];
+#pragma unroll
+  for (int v = 0; v <= DIM; ++v)
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) X[v][k] = __ldg(coords + (int64_t)cc[v] * DIM + k);
+  double J[DIM][DIM];
+#pragma unroll
+  for (int k = 0; k < DIM; ++k)
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) J[k][a] = X[a + 1][k] - X[0][k];
+  if constexpr (DIM == 1) {
+    g.adet = fabs(J[0][0]);
+    g.Jinv[0][0] = 1.0 / J[0][0];
+  } else if constexpr (DIM == 2) {
+    double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    double r = 1.0 / det;
+    g.Jinv[0][0] = J[1][1] * r;
+    g.Jinv[0][1] = -J[0][1] * r;
+    g.Jinv[1][0] = -J[1][0] * r;
+    g.Jinv[1][1] = J[0][0] * r;
+    g.adet = fabs(det);
+  } else {
+    double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+    double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+    double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+    double r = 1.0 / det;
+    g.Jinv[0][0] = c00 * r;
+    g.Jinv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * r;
+    g.Jinv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * r;
+    g.Jinv[1][0] = c01 * r;
+    g.Jinv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * r;
+    g.Jinv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * r;
+    g.Jinv[2][0] = c02 * r;
+    g.Jinv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * r;
+    g.Jinv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * r;
+    g.adet = fabs(det);
+  }
+}
+
+// dof index helpers (layout: 0 interleaved, 1 blocked)
+template <int NC, int LAYOUT>
+__device__ __forceinline__ int64_t dof_index(int64_t node, int comp, int64_t n_nodes) {
+  if constexpr (LAYOUT == 0) return node * NC + comp;
+  return (int64_t)comp * n_nodes + node;
+}
+
+// dof-level CSR slot from the node-level pattern:
+//   row (node rn, comp m), column (node position `pos` in node row, comp n)
+template <int NC, int LAYOUT>
+__device__ __forceinline__ int64_t dof_slot(int64_t nrp, int64_t len, int m, int pos, int n, int64_t node_nnz) {
+  if constexpr (LAYOUT == 0) return nrp * (NC * NC) + (int64_t)m * len * NC + (int64_t)pos * NC + n;
+  return (int64_t)m * NC * node_nnz + (int64_t)NC * nrp + (int64_t)n * len + pos;
+}

@@ -1,0 +1,268 @@
+"""ctypes shim over libfdts_b200.so (the C ABI declared in include/fdts.h).
+
+PyTorch is only used for device buffers and streams (``tensor.data_ptr()``,
+``torch.cuda.current_stream()``); every kernel on the assembly path lives in
+the shared library.  There is no CPU fallback: importing works without a GPU
+(so that host-side logic can be tested), but constructing an :class:`Engine`
+raises if the library or a CUDA device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import fem
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libfdts_b200.so")
+_LIB = None
+
+SYMBOLS = [
+    "fdts_last_error", "fdts_version", "fdts_create", "fdts_destroy", "fdts_sizes", "fdts_get_csr",
+    "fdts_get_node_csr", "fdts_set_param", "fdts_set_option", "fdts_get_option", "fdts_ifunction", "fdts_ijacobian",
+    "fdts_ifunction_range", "fdts_ijacobian_range", "fdts_ifunction_host", "fdts_ijacobian_host", "fdts_halo_pack",
+    "fdts_halo_unpack", "fdts_launch_count", "fdts_measure_fp64_peak",
+]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class _Config(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int32), ("degree", C.c_int32), ("nd", C.c_int32), ("ncomp", C.c_int32), ("layout", C.c_int32),
+        ("family", C.c_int32), ("nq", C.c_int32), ("memspace", C.c_int32), ("device", C.c_int32),
+        ("reserved", C.c_int32),
+        ("num_cells", C.c_int64), ("num_interior_cells", C.c_int64), ("num_nodes", C.c_int64),
+        ("num_owned_nodes", C.c_int64), ("num_coord_nodes", C.c_int64),
+        ("coords", C.c_void_p), ("cell_coord", C.c_void_p), ("cell_node", C.c_void_p),
+        ("B", C.c_void_p), ("w", C.c_void_p), ("R", C.c_void_p), ("M0", C.c_void_p),
+        ("params", C.c_double * 4),
+        ("num_bc_nodes", C.c_int64), ("bc_nodes", C.c_void_p),
+    ]
+
+
+class _Sizes(C.Structure):
+    _fields_ = [("num_rows", C.c_int64), ("num_cols", C.c_int64), ("nnz", C.c_int64), ("node_nnz", C.c_int64),
+                ("max_row_nodes", C.c_int32), ("reserved", C.c_int32)]
+
+
+def load_library():
+    """dlopen the in-tree library; raises EngineError when it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        lib.fdts_last_error.restype = C.c_char_p
+        lib.fdts_version.restype = C.c_char_p
+        lib.fdts_launch_count.restype = C.c_int64
+        lib.fdts_launch_count.argtypes = [C.c_void_p]
+        lib.fdts_create.argtypes = [C.POINTER(_Config), C.POINTER(C.c_void_p)]
+        lib.fdts_destroy.argtypes = [C.c_void_p]
+        lib.fdts_sizes.argtypes = [C.c_void_p, C.POINTER(_Sizes)]
+        lib.fdts_get_csr.argtypes = [C.c_void_p] * 4
+        lib.fdts_get_node_csr.argtypes = [C.c_void_p] * 4
+        lib.fdts_set_param.argtypes = [C.c_void_p, C.c_int32, C.c_double]
+        lib.fdts_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+        lib.fdts_get_option.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]
+        lib.fdts_ifunction.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.fdts_ijacobian.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
+                                       C.c_void_p]
+        lib.fdts_ifunction_range.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                             C.c_int64, C.c_int32, C.c_void_p]
+        lib.fdts_ijacobian_range.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
+                                             C.c_int64, C.c_int64, C.c_int32, C.c_void_p]
+        lib.fdts_ifunction_host.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.fdts_ijacobian_host.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+        lib.fdts_halo_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        lib.fdts_halo_unpack.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+        lib.fdts_measure_fp64_peak.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_double)]
+        _LIB = lib
+    return _LIB
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise EngineError(f"{what} failed (code {rc}): {load_library().fdts_last_error().decode()}")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def measure_fp64_peak(device=0, dmma=False) -> float:
+    out = C.c_double(0.0)
+    _check(load_library().fdts_measure_fp64_peak(device, 1 if dmma else 0, C.byref(out)), "fdts_measure_fp64_peak")
+    return out.value
+
+
+class Engine:
+    """One assembly problem resident on one GPU (replaces ``_assemble_residual``
+    / ``_assemble_jac`` of the reference's ``_TSContext``,
+    firedrake_ts/solving_utils.py:258,305)."""
+
+    def __init__(self, form, bcs=(), device=None, scatter=None):
+        if not torch.cuda.is_available():
+            raise EngineError("no CUDA device: the B200 assembly engine has no CPU fallback")
+        lib = load_library()
+        V = form.space
+        m = V.mesh
+        dev = torch.device(device if device is not None else (m.device if m.device.type == "cuda" else "cuda:0"))
+        self.device = dev
+        self.form, self.V = form, V
+        et = fem.element_tables(V.dim, V.degree, form.qdegree, V.variant)
+        bc_nodes = torch.zeros(0, dtype=torch.int32)
+        if bcs:
+            bc_nodes = torch.unique(torch.cat([bc.nodes.to(torch.int64).cpu() for bc in bcs])).to(torch.int32)
+
+        def dv(x, dtype):
+            if not torch.is_tensor(x):
+                x = torch.from_numpy(np.ascontiguousarray(x))
+            return x.to(device=dev, dtype=dtype).contiguous()
+
+        keep = dict(coords=dv(m.coords, torch.float64), cc=dv(m.cell_coord_map, torch.int32),
+                    cn=dv(V.cell_node_map, torch.int32), B=dv(et.B, torch.float64), w=dv(et.w, torch.float64),
+                    R=dv(et.R, torch.float64), M0=dv(et.M0, torch.float64), bc=dv(bc_nodes, torch.int32))
+        cfg = _Config()
+        cfg.dim, cfg.degree, cfg.nd, cfg.ncomp = V.dim, V.degree, V.nd, V.ncomp
+        cfg.layout = 0 if V.layout == "interleaved" else 1
+        cfg.family, cfg.nq, cfg.memspace = form.family, et.nq, 1
+        cfg.device = dev.index or 0
+        cfg.num_cells, cfg.num_interior_cells = m.num_cells, m.num_interior_cells
+        cfg.num_nodes, cfg.num_owned_nodes = V.num_nodes, V.num_owned_nodes
+        cfg.num_coord_nodes = m.num_coord_nodes
+        cfg.coords, cfg.cell_coord, cfg.cell_node = keep["coords"].data_ptr(), keep["cc"].data_ptr(), keep["cn"].data_ptr()
+        cfg.B, cfg.w, cfg.R, cfg.M0 = keep["B"].data_ptr(), keep["w"].data_ptr(), keep["R"].data_ptr(), keep["M0"].data_ptr()
+        for i, v in enumerate(form.params):
+            cfg.params[i] = v
+        cfg.num_bc_nodes, cfg.bc_nodes = bc_nodes.numel(), keep["bc"].data_ptr()
+        self._h = C.c_void_p()
+        torch.cuda.synchronize(dev)
+        with torch.cuda.device(dev):
+            _check(lib.fdts_create(C.byref(cfg), C.byref(self._h)), "fdts_create")
+        del keep  # the library holds its own copies
+        s = _Sizes()
+        _check(lib.fdts_sizes(self._h, C.byref(s)), "fdts_sizes")
+        self.num_rows, self.num_cols, self.nnz, self.node_nnz = s.num_rows, s.num_cols, s.nnz, s.node_nnz
+        self.max_row_nodes, self.max_degree = s.max_row_nodes, s.reserved
+        self.num_cells, self.num_interior_cells = m.num_cells, m.num_interior_cells
+        self._lib = lib
+        if scatter is not None:
+            self.set_option("scatter", scatter)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                self._lib.fdts_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    # -- options / params -------------------------------------------------
+    def set_option(self, key, value):
+        _check(self._lib.fdts_set_option(self._h, key.encode(), int(value)), "fdts_set_option")
+
+    def get_option(self, key):
+        v = C.c_int64(0)
+        _check(self._lib.fdts_get_option(self._h, key.encode(), C.byref(v)), "fdts_get_option")
+        return v.value
+
+    def set_param(self, index, value):
+        _check(self._lib.fdts_set_param(self._h, index, float(value)), "fdts_set_param")
+
+    @property
+    def launch_count(self):
+        return self._lib.fdts_launch_count(self._h)
+
+    # -- sparsity -----------------------------------------------------------
+    def csr(self):
+        """dof-level (rowptr int64, colidx int32) device tensors of the AIJ pattern."""
+        rowptr = torch.empty(self.num_rows + 1, dtype=torch.int64, device=self.device)
+        colidx = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=self.device)[: self.nnz]
+        with torch.cuda.device(self.device):
+            _check(self._lib.fdts_get_csr(self._h, rowptr.data_ptr(), colidx.data_ptr(), _stream()), "fdts_get_csr")
+        return rowptr, colidx
+
+    def node_csr(self):
+        nown = self.V.num_owned_nodes
+        rowptr = torch.empty(nown + 1, dtype=torch.int64, device=self.device)
+        colidx = torch.empty(max(self.node_nnz, 1), dtype=torch.int32, device=self.device)[: self.node_nnz]
+        with torch.cuda.device(self.device):
+            _check(self._lib.fdts_get_node_csr(self._h, rowptr.data_ptr(), colidx.data_ptr(), _stream()),
+                   "fdts_get_node_csr")
+        return rowptr, colidx
+
+    def new_values(self):
+        return torch.empty(max(self.nnz, 1), dtype=torch.float64, device=self.device)[: self.nnz]
+
+    # -- the hot path ---------------------------------------------------------
+    def _chk_vec(self, x, n, name):
+        if not (x.is_cuda and x.dtype == torch.float64 and x.is_contiguous() and x.numel() == n):
+            raise EngineError(f"{name}: expected a contiguous float64 CUDA tensor of {n} entries, got "
+                              f"{tuple(x.shape)} {x.dtype} {x.device}")
+
+    def ifunction(self, t, x, xdot, out=None):
+        """F(t, x, xdot) for the owned dofs; x/xdot are local (owned+ghost) vectors."""
+        self._chk_vec(x, self.num_cols, "x")
+        self._chk_vec(xdot, self.num_cols, "xdot")
+        if out is None:
+            out = torch.empty(self.num_rows, dtype=torch.float64, device=self.device)
+        self._chk_vec(out, self.num_rows, "F")
+        with torch.cuda.device(self.device):
+            _check(self._lib.fdts_ifunction(self._h, float(t), x.data_ptr(), xdot.data_ptr(), out.data_ptr(),
+                                            _stream()), "fdts_ifunction")
+        return out
+
+    def ijacobian(self, t, x, xdot, shift, out=None):
+        """CSR values of shift*dF/dxdot + dF/dx at (t, x, xdot)."""
+        self._chk_vec(x, self.num_cols, "x")
+        self._chk_vec(xdot, self.num_cols, "xdot")
+        if out is None:
+            out = self.new_values()
+        self._chk_vec(out, self.nnz, "J values")
+        with torch.cuda.device(self.device):
+            _check(self._lib.fdts_ijacobian(self._h, float(t), x.data_ptr(), xdot.data_ptr(), float(shift),
+                                            out.data_ptr(), _stream()), "fdts_ijacobian")
+        return out
+
+    def ifunction_range(self, t, x, xdot, out, c0, c1, flags):
+        with torch.cuda.device(self.device):
+            _check(self._lib.fdts_ifunction_range(self._h, float(t), x.data_ptr(), xdot.data_ptr(), out.data_ptr(),
+                                                  c0, c1, flags, _stream()), "fdts_ifunction_range")
+
+    def ijacobian_range(self, t, x, xdot, shift, out, c0, c1, flags):
+        with torch.cuda.device(self.device):
+            _check(self._lib.fdts_ijacobian_range(self._h, float(t), x.data_ptr(), xdot.data_ptr(), float(shift),
+                                                  out.data_ptr(), c0, c1, flags, _stream()), "fdts_ijacobian_range")
+
+    # host-buffer variants (reference-facing call with host Vec/Mat storage)
+    def ifunction_host(self, t, x, xdot, out):
+        for a in (x, xdot, out):
+            assert not a.is_cuda and a.dtype == torch.float64 and a.is_contiguous()
+        _check(self._lib.fdts_ifunction_host(self._h, float(t), x.data_ptr(), xdot.data_ptr(), out.data_ptr()),
+               "fdts_ifunction_host")
+        return out
+
+    def ijacobian_host(self, t, x, xdot, shift, out):
+        for a in (x, xdot, out):
+            assert not a.is_cuda and a.dtype == torch.float64 and a.is_contiguous()
+        _check(self._lib.fdts_ijacobian_host(self._h, float(t), x.data_ptr(), xdot.data_ptr(), float(shift),
+                                             out.data_ptr()), "fdts_ijacobian_host")
+        return out
+
+    # halo helpers ----------------------------------------------------------------
+    def halo_pack(self, x, nodes, buf):
+        with torch.cuda.device(self.device):
+            _check(self._lib.fdts_halo_pack(self._h, x.data_ptr(), nodes.data_ptr(), nodes.numel(), buf.data_ptr(),
+                                            _stream()), "fdts_halo_pack")
+
+    def halo_unpack(self, x, first, count, buf):
+        with torch.cuda.device(self.device):
+            _check(self._lib.fdts_halo_unpack(self._h, x.data_ptr(), first, count, buf.data_ptr(), _stream()),
+                   "fdts_halo_unpack")

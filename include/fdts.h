@@ -1,0 +1,137 @@
+/*
+ * fdts.h -- C ABI of libfdts_b200.so, the B200-native assembly engine behind
+ * firedrake-ts's IFunction / IJacobian callbacks.
+ *
+ * Every entry point returns 0 on success and a non-zero code on failure;
+ * fdts_last_error() then describes the failure (thread local).  No exception
+ * crosses this boundary; there is no global engine state (two solvers may
+ * coexist, reference tests/test_two_daesolver.py:6-40): everything hangs off
+ * the handle.  Plain pointers and sizes only.
+ *
+ * Reference interfaces replaced (paths relative to the reference repo):
+ *   fdts_create / fdts_destroy
+ *       _TSContext.__init__ + inherited _SNESContext.__init__, which build the
+ *       assemblers, the residual Cofunction and (first touch of ctx._jac in
+ *       set_ijacobian) the sparsity + Mat preallocation:
+ *       firedrake_ts/solving_utils.py:77-111, :115-122.
+ *   fdts_ifunction
+ *       the body of _TSContext.form_function, i.e.
+ *       ctx._assemble_residual(tensor=ctx._F) with zero_bc_nodes=True:
+ *       firedrake_ts/solving_utils.py:236-267 (assembly at :258).
+ *   fdts_ijacobian
+ *       the body of _TSContext.form_jacobian, i.e. ctx._shift.assign(shift);
+ *       ctx._assemble_jac(ctx._jac): firedrake_ts/solving_utils.py:270-317
+ *       (assembly at :304-305).  J = shift*dF/dudot + dF/du,
+ *       firedrake_ts/ts_solver.py:108.
+ *   fdts_ifunction_host / fdts_ijacobian_host
+ *       the same two callbacks when the caller's Vec/Mat live in host memory
+ *       (the reference's default VECSEQ/MATSEQAIJ, firedrake_ts/ts_solver.py:239,
+ *       solving_utils.py:122); copies are part of the call.
+ *   fdts_halo_pack / fdts_halo_unpack
+ *       PyOP2's global_to_local halo exchange of the READ Dats that the
+ *       reference triggers by leaving dat.vec_wo (solving_utils.py:249-252);
+ *       the wire transfer itself (NCCL send/recv) is driven by the host layer.
+ *   fdts_get_csr / fdts_sizes
+ *       ctx._jac.petscmat.getRowIJ() of the preallocated AIJ Mat.
+ */
+#ifndef FDTS_H
+#define FDTS_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fdts_engine *fdts_handle;
+
+enum { FDTS_HEAT = 0, FDTS_BURGERS = 1, FDTS_BBM = 2, FDTS_CAHN_HILLIARD = 3 };
+enum { FDTS_INTERLEAVED = 0, FDTS_BLOCKED = 1 };
+enum { FDTS_MEM_HOST = 0, FDTS_MEM_DEVICE = 1 };
+
+typedef struct {
+  int32_t dim;       /* 1, 2, 3 */
+  int32_t degree;    /* 1, 2, 3 */
+  int32_t nd;        /* nodes per cell of the scalar element */
+  int32_t ncomp;     /* components (vector space) or fields (mixed space V*V) */
+  int32_t layout;    /* FDTS_INTERLEAVED / FDTS_BLOCKED */
+  int32_t family;    /* FDTS_HEAT ... */
+  int32_t nq;        /* quadrature points */
+  int32_t memspace;  /* where the arrays below live: FDTS_MEM_HOST / FDTS_MEM_DEVICE */
+  int32_t device;    /* CUDA device ordinal */
+  int32_t reserved;
+  int64_t num_cells;          /* local cells, interior cells first */
+  int64_t num_interior_cells; /* cells touching no ghost node */
+  int64_t num_nodes;          /* local nodes: owned first, then ghosts */
+  int64_t num_owned_nodes;
+  int64_t num_coord_nodes;
+  const double *coords;       /* num_coord_nodes x dim */
+  const int32_t *cell_coord;  /* num_cells x (dim+1) */
+  const int32_t *cell_node;   /* num_cells x nd */
+  const double *B;            /* nq x (dim+1) x nd   basis values / reference derivatives */
+  const double *w;            /* nq */
+  const double *R;            /* (dim+1) x (dim+1) x nd x nd  reference tensors */
+  const double *M0;           /* nd  integrals of the basis functions */
+  double params[4];           /* family constants (source | nu | - | lambda) */
+  int64_t num_bc_nodes;
+  const int32_t *bc_nodes;    /* Dirichlet nodes (all components) */
+} fdts_config;
+
+typedef struct {
+  int64_t num_rows;        /* owned dofs */
+  int64_t num_cols;        /* local dofs (owned + ghost) */
+  int64_t nnz;             /* dof-level non-zeros */
+  int64_t node_nnz;        /* node-level non-zeros */
+  int32_t max_row_nodes;   /* longest node row */
+  int32_t reserved;
+} fdts_sizes_t;
+
+const char *fdts_last_error(void);
+const char *fdts_version(void);
+
+int fdts_create(const fdts_config *cfg, fdts_handle *out);
+int fdts_destroy(fdts_handle h);
+int fdts_sizes(fdts_handle h, fdts_sizes_t *out);
+
+/* copy the dof-level CSR pattern into caller buffers (device pointers):
+ * rowptr: (num_rows+1) int64, colidx: nnz int32; either may be NULL */
+int fdts_get_csr(fdts_handle h, int64_t *rowptr_dev, int32_t *colidx_dev, void *stream);
+/* node-level pattern (owned node rows x local node columns) */
+int fdts_get_node_csr(fdts_handle h, int64_t *rowptr_dev, int32_t *colidx_dev, void *stream);
+
+int fdts_set_param(fdts_handle h, int32_t index, double value);
+/* options: "scatter" 0 = atomic (REDG.ADD.F64), 1 = owner-computes gather (deterministic) */
+int fdts_set_option(fdts_handle h, const char *key, int64_t value);
+int fdts_get_option(fdts_handle h, const char *key, int64_t *value);
+
+/* x, xdot: local vectors (owned + ghost dofs, space layout), device memory.
+ * f: owned dofs, device memory.  vals: nnz values of the dof-level CSR, device memory. */
+int fdts_ifunction(fdts_handle h, double t, const double *x, const double *xdot, double *f, void *stream);
+int fdts_ijacobian(fdts_handle h, double t, const double *x, const double *xdot, double shift, double *vals,
+                   void *stream);
+/* cell-range variants used to overlap the halo exchange with interior cells:
+ * flags bit0 = zero the output first, bit1 = apply the boundary-condition fix-up afterwards */
+int fdts_ifunction_range(fdts_handle h, double t, const double *x, const double *xdot, double *f,
+                         int64_t cell_begin, int64_t cell_end, int32_t flags, void *stream);
+int fdts_ijacobian_range(fdts_handle h, double t, const double *x, const double *xdot, double shift, double *vals,
+                         int64_t cell_begin, int64_t cell_end, int32_t flags, void *stream);
+
+/* host-buffer variants: pinned or pageable host pointers; H2D / D2H copies are part of the call */
+int fdts_ifunction_host(fdts_handle h, double t, const double *x_host, const double *xdot_host, double *f_host);
+int fdts_ijacobian_host(fdts_handle h, double t, const double *x_host, const double *xdot_host, double shift,
+                        double *vals_host);
+
+/* halo: gather `count` nodes (all components) of local vector x into buf / scatter buf into x.
+ * nodes: device int32 node ids; buf layout [component][node]. */
+int fdts_halo_pack(fdts_handle h, const double *x, const int32_t *nodes, int64_t count, double *buf, void *stream);
+int fdts_halo_unpack(fdts_handle h, double *x, int64_t first_node, int64_t count, const double *buf, void *stream);
+
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t fdts_launch_count(fdts_handle h);
+
+/* micro-benchmarks used for the roofline denominators: return GB/s resp. GFLOP/s */
+int fdts_measure_fp64_peak(int32_t device, int32_t use_dmma, double *gflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
