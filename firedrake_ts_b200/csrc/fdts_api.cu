@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <vector>
 
 #include "kargs.cuh"
 
@@ -217,6 +218,19 @@ extern "C" int fdts_create(const fdts_config *cfg, fdts_handle *out) {
       break;
     }
     rc = fdts_build_pattern(e, e->own_stream);
+    if (rc) break;
+    {  // which compiled reference table (if any) matches the tensors we were given?
+      const size_t nR = (size_t)(d + 1) * (d + 1) * nd * nd;
+      std::vector<double> Rh(nR);
+      if (cudaMemcpy(Rh.data(), e->R, sizeof(double) * nR, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        fdts_set_error("reading back the reference tensors failed");
+        rc = 2;
+        break;
+      }
+      e->variant = fdts_heat_match_tables(d, cfg->degree, Rh.data());
+      // default path: closed form + atomics for the heat family when the tables match
+      e->opt_scatter = (cfg->family == FDTS_HEAT && cfg->ncomp == 1 && e->variant >= 0) ? 1 : 0;
+    }
   } while (0);
   cudaFree(tmp_cc);
   cudaFree(tmp_cn);
@@ -239,6 +253,7 @@ extern "C" int fdts_destroy(fdts_handle e) {
                   e->d_f, e->d_vals};
   for (void *p : ptrs)
     if (p) cudaFree(p);
+  fdts_free_plan(e);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
   return 0;
@@ -294,11 +309,21 @@ extern "C" int fdts_set_param(fdts_handle e, int32_t index, double value) {
 extern "C" int fdts_set_option(fdts_handle e, const char *key, int64_t value) {
   if (!e || !key) return 1;
   if (!strcmp(key, "scatter")) {
+    if (value < 0 || value > 2) {
+      fdts_set_error("scatter must be 0 (generic, atomic), 1 (closed form, atomic) or 2 (owner-computes gather)");
+      return 1;
+    }
     e->opt_scatter = value;
     return 0;
   }
   fdts_set_error(std::string("unknown option ") + key);
   return 1;
+}
+
+extern "C" int fdts_set_row_blocks(fdts_handle e, const int64_t *starts_host, int64_t nblocks) {
+  if (!e || !starts_host) return 1;
+  FDTS_CHECK(cudaSetDevice(e->device));
+  return fdts_build_plan(e, starts_host, nblocks);
 }
 
 extern "C" int fdts_get_option(fdts_handle e, const char *key, int64_t *value) {
@@ -307,12 +332,24 @@ extern "C" int fdts_get_option(fdts_handle e, const char *key, int64_t *value) {
     *value = e->opt_scatter;
     return 0;
   }
+  if (!strcmp(key, "plan_cells_max")) {
+    *value = e->plan.cmax;
+    return 0;
+  }
+  if (!strcmp(key, "plan_contributions")) {
+    *value = e->plan.total_contrib;
+    return 0;
+  }
+  if (!strcmp(key, "plan_blocks")) {
+    *value = e->plan.nblocks;
+    return 0;
+  }
   fdts_set_error(std::string("unknown option ") + key);
   return 1;
 }
 
 static bool use_fast_heat(fdts_engine *e) {
-  return e->opt_scatter == 1 && e->cfg.family == FDTS_HEAT && e->cfg.ncomp == 1;
+  return e->opt_scatter >= 1 && e->cfg.family == FDTS_HEAT && e->cfg.ncomp == 1 && e->variant >= 0;
 }
 
 extern "C" int fdts_ifunction_range(fdts_handle e, double t, const double *x, const double *xdot, double *f,

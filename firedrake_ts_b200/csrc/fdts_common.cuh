@@ -8,6 +8,22 @@
 
 #define FDTS_MAXD 3
 
+// owner-computes gather plan (gather_plan.cu)
+struct GatherPlan {
+  bool ready = false;
+  int64_t nblocks = 0;
+  int64_t *bstart = nullptr;    // nblocks+1 row offsets
+  int32_t cmax = 0;             // max cells per block (stride of bcells)
+  int32_t *bcells = nullptr;    // nblocks x cmax sorted cell ids
+  int32_t *bcount = nullptr;    // cells per block
+  int64_t *bbase = nullptr;     // nblocks+1 offsets into cidx
+  uint16_t *cend = nullptr;     // per node-level slot: inclusive end of its contribution segment (block relative)
+  uint16_t *cidx = nullptr;     // staged element-matrix addresses
+  uint16_t *ridx = nullptr;     // per adjacency entry: staged element-vector address
+  int64_t total_contrib = 0;
+  int ne = 0, nep = 0, ndp = 0; // staged entries per cell (symmetric packing), odd-padded strides
+};
+
 struct fdts_engine {
   fdts_config cfg;  // scalars only are meaningful after create; pointers below are device copies
   int device = 0;
@@ -34,6 +50,8 @@ struct fdts_engine {
   int32_t max_degree = 0;
   // options
   int64_t opt_scatter = 0;
+  GatherPlan plan;
+  int variant = -1;              // which baked RefT table matches cfg.R (-1: none, closed-form path off)
   // scratch
   double *h2d_x = nullptr, *h2d_xdot = nullptr, *d_f = nullptr, *d_vals = nullptr;  // host-variant staging
   int64_t launches = 0;
@@ -59,6 +77,9 @@ int fdts_launch_jacobian(fdts_engine *e, const double *x, const double *xdot, do
 int fdts_launch_heat(fdts_engine *e, int which, const double *x, const double *xdot, double shift, double *out,
                      int64_t c0, int64_t c1, cudaStream_t s);
 int fdts_build_pattern(fdts_engine *e, cudaStream_t s);
+int fdts_heat_match_tables(int dim, int deg, const double *R_host);
+int fdts_build_plan(fdts_engine *e, const int64_t *starts_host, int64_t nblocks);
+void fdts_free_plan(fdts_engine *e);
 
 // ------------------------------------------------------------------ device helpers
 __device__ __forceinline__ void red_add_f64(double *addr, double v) {

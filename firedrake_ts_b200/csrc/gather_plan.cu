@@ -1,0 +1,347 @@
+// gather_plan.cu -- one-off construction of the owner-computes gather plan (K6).
+//
+// The deterministic scatter variant of SURVEY.md section 8(a) ("K6 deterministic
+// segmented scatter variant (sorted contribution lists)").  Owned node rows are
+// cut into contiguous row blocks (one CTA each).  For every block the plan holds
+//   * the sorted list of cells touching its rows (the CTA recomputes their
+//     element matrices into shared memory -- overlap-1 redundancy, exactly like
+//     the exec-halo of the MPI decomposition, only at CTA scale);
+//   * for every CSR slot of the block, the list of staged element-matrix entries
+//     that sum to it, as 16-bit shared-memory addresses in ascending cell order
+//     (fixed order => bitwise reproducible sums);
+//   * for every row, the list of staged element-vector entries (residual).
+// Dirichlet rows/columns get empty lists (PyOP2's negative-lgmap "drop").
+// All of it is integer work on the GPU, derived from the cell->node map, the
+// node-level CSR and the row->cell adjacency built in pattern.cu.
+#include <cub/cub.cuh>
+
+#include "fdts_common.cuh"
+
+namespace {
+
+constexpr int PLAN_THREADS = 256;
+
+__global__ void block_candidates(const int64_t *__restrict__ bstart, int64_t nb, const int64_t *__restrict__ adj_ptr,
+                                 int64_t *__restrict__ ncand) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < nb) ncand[b] = adj_ptr[bstart[b + 1]] - adj_ptr[bstart[b]];
+}
+
+// one CTA per row block: sorted unique cells adjacent to the block's rows
+template <bool WRITE>
+__global__ void __launch_bounds__(PLAN_THREADS) block_cells(const int64_t *__restrict__ bstart,
+                                                            const int64_t *__restrict__ adj_ptr,
+                                                            const int32_t *__restrict__ adj_cell, int kpad, int cmax,
+                                                            int32_t *__restrict__ bcount,
+                                                            int32_t *__restrict__ bcells) {
+  extern __shared__ int32_t cand[];
+  __shared__ int warp_tot[PLAN_THREADS / 32];
+  const int64_t b = blockIdx.x;
+  const int64_t a0 = adj_ptr[bstart[b]];
+  const int n = (int)(adj_ptr[bstart[b + 1]] - a0);
+  for (int t = threadIdx.x; t < kpad; t += PLAN_THREADS) cand[t] = t < n ? (adj_cell[a0 + t] >> 5) : INT32_MAX;
+  __syncthreads();
+  for (int kk = 2; kk <= kpad; kk <<= 1)
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < kpad; t += PLAN_THREADS) {
+        const int p = t ^ j;
+        if (p > t) {
+          const int32_t x = cand[t], y = cand[p];
+          const bool up = (t & kk) == 0;
+          if ((x > y) == up) {
+            cand[t] = y;
+            cand[p] = x;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  // ordered compaction of first occurrences, PLAN_THREADS elements per round
+  int base = 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t0 = 0; t0 < kpad; t0 += PLAN_THREADS) {
+    const int t = t0 + threadIdx.x;
+    const int32_t v = cand[t];
+    const bool first = v != INT32_MAX && (t == 0 || cand[t - 1] != v);
+    const unsigned m = __ballot_sync(0xffffffffu, first);
+    if (lane == 0) warp_tot[warp] = __popc(m);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    if (WRITE && first) bcells[b * cmax + off + __popc(m & ((1u << lane) - 1u))] = v;
+    for (int w = 0; w < PLAN_THREADS / 32; ++w) base += warp_tot[w];
+    __syncthreads();
+  }
+  if (!WRITE && threadIdx.x == 0) bcount[b] = base;
+}
+
+__device__ __forceinline__ int sym_index(int i, int j, int nd) {
+  if (i > j) {
+    const int t = i;
+    i = j;
+    j = t;
+  }
+  return i * nd - (i * (i - 1)) / 2 + (j - i);
+}
+
+__device__ __forceinline__ int find_cell(const int32_t *__restrict__ list, int n, int32_t cell) {
+  int lo = 0, hi = n - 1;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1;
+    const int32_t v = list[mid];
+    if (v == cell) return mid;
+    if (v < cell) lo = mid + 1; else hi = mid - 1;
+  }
+  return -1;
+}
+
+// MODE 0: count contributions per slot (cnt8).  MODE 1: write the staged addresses.
+template <int MODE>
+__global__ void slot_contributions(const int64_t *__restrict__ bstart, const int64_t *__restrict__ adj_ptr,
+                                   const int32_t *__restrict__ adj_cell, const int32_t *__restrict__ cell_node_t,
+                                   int64_t nc, int nd, int nep, const uint8_t *__restrict__ pos8_t,
+                                   const uint8_t *__restrict__ isbc, const int64_t *__restrict__ nrp,
+                                   uint8_t *__restrict__ cnt8, const uint16_t *__restrict__ cend,
+                                   const int64_t *__restrict__ bbase, const int32_t *__restrict__ bcells,
+                                   const int32_t *__restrict__ bcount, int cmax, uint16_t *__restrict__ cidx,
+                                   int *__restrict__ err) {
+  const int64_t b = blockIdx.x;
+  const int64_t r0 = bstart[b], r1 = bstart[b + 1];
+  const int64_t s0 = nrp[r0];
+  for (int64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+    if (isbc[r]) continue;
+    const int64_t rb = nrp[r];
+    for (int64_t a = adj_ptr[r]; a < adj_ptr[r + 1]; ++a) {
+      const int32_t code = adj_cell[a];
+      const int64_t cell = code >> 5;
+      const int i = code & 31;
+      int cs = 0;
+      if (MODE == 1) {
+        cs = find_cell(bcells + b * cmax, bcount[b], (int32_t)cell);
+        if (cs < 0) {
+          atomicExch(err, 2);
+          continue;
+        }
+      }
+      for (int j = 0; j < nd; ++j) {
+        if (isbc[cell_node_t[(int64_t)j * nc + cell]]) continue;
+        const int64_t slot = rb + pos8_t[(int64_t)(i * nd + j) * nc + cell];
+        if (MODE == 0) {
+          if (cnt8[slot] == 255) atomicExch(err, 3);
+          cnt8[slot]++;
+        } else {
+          const int k = cnt8[slot]++;
+          const int64_t beg = slot == s0 ? 0 : cend[slot - 1];
+          cidx[bbase[b] + beg + k] = (uint16_t)(cs * nep + sym_index(i, j, nd));
+        }
+      }
+    }
+  }
+}
+
+// per block inclusive scan of the slot counts -> 16-bit segment ends, block totals
+__global__ void __launch_bounds__(PLAN_THREADS) block_scan_counts(const int64_t *__restrict__ bstart,
+                                                                  const int64_t *__restrict__ nrp,
+                                                                  const uint8_t *__restrict__ cnt8,
+                                                                  uint16_t *__restrict__ cend,
+                                                                  int64_t *__restrict__ btotal,
+                                                                  int *__restrict__ err) {
+  using Scan = cub::BlockScan<int, PLAN_THREADS>;
+  __shared__ typename Scan::TempStorage tmp;
+  const int64_t b = blockIdx.x;
+  const int64_t s0 = nrp[bstart[b]], s1 = nrp[bstart[b + 1]];
+  int running = 0;
+  for (int64_t base = s0; base < s1; base += PLAN_THREADS) {
+    const int64_t s = base + threadIdx.x;
+    const int v = s < s1 ? cnt8[s] : 0;
+    int incl, total;
+    Scan(tmp).InclusiveSum(v, incl, total);
+    if (s < s1) {
+      const int e = running + incl;
+      if (e > 65535) atomicExch(err, 4);
+      cend[s] = (uint16_t)e;
+    }
+    running += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) btotal[b] = running;
+}
+
+// residual lists: per row the staged element-vector entries, cell ascending
+template <int MODE>
+__global__ void row_contributions(const int64_t *__restrict__ bstart, const int64_t *__restrict__ adj_ptr,
+                                  const int32_t *__restrict__ adj_cell, const uint8_t *__restrict__ isbc, int ndp,
+                                  const int32_t *__restrict__ bcells, const int32_t *__restrict__ bcount, int cmax,
+                                  uint16_t *__restrict__ ridx, int *__restrict__ err) {
+  const int64_t b = blockIdx.x;
+  const int64_t r0 = bstart[b], r1 = bstart[b + 1];
+  for (int64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+    for (int64_t a = adj_ptr[r]; a < adj_ptr[r + 1]; ++a) {
+      const int32_t code = adj_cell[a];
+      const int cs = find_cell(bcells + b * cmax, bcount[b], code >> 5);
+      if (cs < 0) {
+        atomicExch(err, 5);
+        continue;
+      }
+      ridx[a] = (uint16_t)(cs * ndp + (code & 31));
+    }
+    (void)isbc;
+  }
+}
+
+struct Widen8 {
+  __host__ __device__ int64_t operator()(uint8_t v) const { return (int64_t)v; }
+};
+
+}  // namespace
+
+#define GRID(n, b) (unsigned)(((n) + (b)-1) / (b))
+
+void fdts_free_plan(fdts_engine *e) {
+  GatherPlan &p = e->plan;
+  void *ptrs[] = {p.bstart, p.bcells, p.bcount, p.bbase, p.cend, p.cidx, p.ridx};
+  for (void *q : ptrs)
+    if (q) cudaFree(q);
+  p = GatherPlan();
+}
+
+// starts: host array of nblocks+1 owned-node row offsets (contiguous row blocks)
+int fdts_build_plan(fdts_engine *e, const int64_t *starts, int64_t nb) {
+  fdts_free_plan(e);
+  GatherPlan &p = e->plan;
+  cudaStream_t s = e->own_stream;
+  const int64_t nown = e->cfg.num_owned_nodes, nc = e->cfg.num_cells;
+  const int nd = e->cfg.nd;
+  if (nb <= 0 || starts[0] != 0 || starts[nb] != nown) {
+    fdts_set_error("row blocks must cover the owned rows [0, num_owned_nodes)");
+    return 1;
+  }
+  if (e->cfg.ncomp != 1) {
+    fdts_set_error("gather plan: scalar spaces only");
+    return 3;
+  }
+  p.nblocks = nb;
+  p.ne = nd * (nd + 1) / 2;
+  p.nep = p.ne | 1;  // odd stride: conflict-free staging stores
+  p.ndp = nd | 1;
+  FDTS_CHECK(cudaMalloc(&p.bstart, sizeof(int64_t) * (nb + 1)));
+  FDTS_CHECK(cudaMemcpyAsync(p.bstart, starts, sizeof(int64_t) * (nb + 1), cudaMemcpyHostToDevice, s));
+  // candidate counts -> padded sort size
+  int64_t *ncand = nullptr, *btotal = nullptr;
+  int *derr = nullptr;
+  FDTS_CHECK(cudaMalloc(&ncand, sizeof(int64_t) * nb));
+  FDTS_CHECK(cudaMalloc(&btotal, sizeof(int64_t) * (nb + 1)));
+  FDTS_CHECK(cudaMalloc(&derr, sizeof(int)));
+  FDTS_CHECK(cudaMemsetAsync(derr, 0, sizeof(int), s));
+  block_candidates<<<GRID(nb, 256), 256, 0, s>>>(p.bstart, nb, e->adj_ptr, ncand);
+  void *tmp = nullptr;
+  size_t tb = 0, tb2 = 0;
+  int64_t *dmax = nullptr;
+  FDTS_CHECK(cudaMalloc(&dmax, sizeof(int64_t) * 2));
+  cub::DeviceReduce::Max(nullptr, tb, ncand, dmax, nb, s);
+  cub::DeviceScan::ExclusiveSum(nullptr, tb2, btotal, btotal, nb + 1, s);
+  tb = tb > tb2 ? tb : tb2;
+  FDTS_CHECK(cudaMalloc(&tmp, tb + 16));
+  cub::DeviceReduce::Max(tmp, tb, ncand, dmax, nb, s);
+  int64_t maxcand = 0;
+  FDTS_CHECK(cudaMemcpyAsync(&maxcand, dmax, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  FDTS_CHECK(cudaStreamSynchronize(s));
+  int kpad = PLAN_THREADS;
+  while (kpad < maxcand) kpad <<= 1;
+  int rc = 0;
+  do {
+    if (kpad > 32768) {
+      fdts_set_error("gather plan: a row block touches too many cells (use smaller / more compact row blocks)");
+      rc = 4;
+      break;
+    }
+    const size_t sm = sizeof(int32_t) * (size_t)kpad;
+    if (sm > 48 * 1024) {
+      cudaFuncSetAttribute(block_cells<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      cudaFuncSetAttribute(block_cells<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    }
+    if (cudaMalloc(&p.bcount, sizeof(int32_t) * nb) != cudaSuccess) { rc = 2; break; }
+    block_cells<false><<<(unsigned)nb, PLAN_THREADS, sm, s>>>(p.bstart, e->adj_ptr, e->adj_cell, kpad, 0, p.bcount,
+                                                            nullptr);
+    int32_t *cm = nullptr;
+    if (cudaMalloc(&cm, sizeof(int32_t) * 2) != cudaSuccess) { rc = 2; break; }
+    size_t tb3 = 0;
+    cub::DeviceReduce::Max(nullptr, tb3, p.bcount, cm, nb, s);
+    void *tmp3 = nullptr;
+    if (cudaMalloc(&tmp3, tb3 + 16) != cudaSuccess) { rc = 2; break; }
+    cub::DeviceReduce::Max(tmp3, tb3, p.bcount, cm, nb, s);
+    int32_t cmax = 0;
+    cudaMemcpyAsync(&cmax, cm, sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    cudaFree(cm);
+    cudaFree(tmp3);
+    p.cmax = cmax;
+    if ((int64_t)cmax * p.nep > 65535) {
+      fdts_set_error("gather plan: staged entries per row block exceed the 16-bit address space");
+      rc = 4;
+      break;
+    }
+    if (cudaMalloc(&p.bcells, sizeof(int32_t) * (size_t)nb * cmax) != cudaSuccess) {
+      fdts_set_error("gather plan: out of memory (block cell lists)");
+      rc = 2;
+      break;
+    }
+    block_cells<true><<<(unsigned)nb, PLAN_THREADS, sm, s>>>(p.bstart, e->adj_ptr, e->adj_cell, kpad, cmax, nullptr,
+                                                           p.bcells);
+    // slot contribution counts -> segment ends
+    uint8_t *cnt8 = nullptr;
+    const int64_t nnz = e->node_nnz;
+    if (cudaMalloc(&cnt8, (size_t)nnz + 1) != cudaSuccess || cudaMalloc(&p.cend, sizeof(uint16_t) * (nnz + 1)) != cudaSuccess ||
+        cudaMalloc(&p.bbase, sizeof(int64_t) * (nb + 1)) != cudaSuccess) {
+      fdts_set_error("gather plan: out of memory (slot tables)");
+      rc = 2;
+      break;
+    }
+    cudaMemsetAsync(cnt8, 0, (size_t)nnz + 1, s);
+    slot_contributions<0><<<(unsigned)nb, 128, 0, s>>>(p.bstart, e->adj_ptr, e->adj_cell, e->cell_node, nc, nd, p.nep,
+                                                      e->pos8, e->isbc, e->nrowptr, cnt8, nullptr, nullptr, nullptr,
+                                                      nullptr, cmax, nullptr, derr);
+    cudaMemsetAsync(btotal, 0, sizeof(int64_t) * (nb + 1), s);
+    block_scan_counts<<<(unsigned)nb, PLAN_THREADS, 0, s>>>(p.bstart, e->nrowptr, cnt8, p.cend, btotal, derr);
+    cub::DeviceScan::ExclusiveSum(tmp, tb, btotal, p.bbase, nb + 1, s);
+    int64_t total = 0;
+    cudaMemcpyAsync(&total, p.bbase + nb, sizeof(int64_t), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    p.total_contrib = total;
+    if (cudaMalloc(&p.cidx, sizeof(uint16_t) * (size_t)(total + 1)) != cudaSuccess ||
+        cudaMalloc(&p.ridx, sizeof(uint16_t) * (size_t)(nc * nd + 1)) != cudaSuccess) {
+      fdts_set_error("gather plan: out of memory (contribution lists)");
+      rc = 2;
+      cudaFree(cnt8);
+      break;
+    }
+    cudaMemsetAsync(cnt8, 0, (size_t)nnz + 1, s);
+    slot_contributions<1><<<(unsigned)nb, 128, 0, s>>>(p.bstart, e->adj_ptr, e->adj_cell, e->cell_node, nc, nd, p.nep,
+                                                      e->pos8, e->isbc, e->nrowptr, cnt8, p.cend, p.bbase, p.bcells,
+                                                      p.bcount, cmax, p.cidx, derr);
+    row_contributions<1><<<(unsigned)nb, 128, 0, s>>>(p.bstart, e->adj_ptr, e->adj_cell, e->isbc, p.ndp, p.bcells,
+                                                     p.bcount, cmax, p.ridx, derr);
+    int herr = 0;
+    cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, s);
+    cudaError_t ce = cudaStreamSynchronize(s);
+    cudaFree(cnt8);
+    if (ce != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+      fdts_set_error(std::string("gather plan kernels failed: ") + cudaGetErrorString(ce));
+      rc = 2;
+      break;
+    }
+    if (herr) {
+      fdts_set_error("gather plan: internal inconsistency (code " + std::to_string(herr) + ")");
+      rc = 5;
+      break;
+    }
+    p.ready = true;
+  } while (0);
+  cudaFree(ncand);
+  cudaFree(btotal);
+  cudaFree(derr);
+  cudaFree(dmax);
+  cudaFree(tmp);
+  if (rc) fdts_free_plan(e);
+  return rc;
+}

@@ -1,7 +1,395 @@
-#include "fdts_common.cuh"
+// kernels_heat.cu -- closed-form kernels for the constant-coefficient heat family
+// (examples/heat.py:11; headline configuration C4 of SURVEY.md section 8(d)).
+//
+// On affine simplices the heat element matrix is a linear combination of
+// reference tensors,
+//     A = shift*|detJ| * R00 + sum_{a<=b} (|detJ| G_ab) * S_ab ,   G = Jinv Jinv^T,
+// so no quadrature loop is needed at run time: the tensors are compile-time
+// constants (ref_tables.cuh), fully unrolled into DFMA immediates with their
+// zeros dropped.  Two scatter strategies share this element kernel:
+//   path 1  one thread per cell, `red.global.add.f64` into Vec / CSR (atomic)
+//   path 2  owner-computes gather (deterministic, write-once), see heat_gather.cuh
+#include <type_traits>
+#include <utility>
+
+#include "kargs.cuh"
+#include "ref_tables.cuh"
+
+namespace {
+
+template <class F, int... Is>
+__device__ __forceinline__ void static_for_impl(F &&f, std::integer_sequence<int, Is...>) {
+  (f(std::integral_constant<int, Is>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+  static_for_impl(f, std::make_integer_sequence<int, N>{});
+}
+
+// g[p] = |detJ| * (Jinv Jinv^T)_{ab} for the pairs a<=b in the order of RefT::S
+template <int DIM>
+__device__ __forceinline__ void metric(const Geom<DIM> &g, double (&gm)[DIM * (DIM + 1) / 2]) {
+  int p = 0;
+#pragma unroll
+  for (int a = 0; a < DIM; ++a)
+#pragma unroll
+    for (int b = a; b < DIM; ++b) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) t += g.Jinv[a][k] * g.Jinv[b][k];
+      gm[p++] = t * g.adet;
+    }
+}
+
+template <class T, int I, int J, int NP>
+__device__ __forceinline__ double heat_entry(double m, const double (&gm)[NP]) {
+  double v = 0.0;
+  constexpr double r = T::R00[I][J];
+  if constexpr (r != 0.0) v = m * r;
+  static_for<NP>([&](auto P) {
+    constexpr int p = decltype(P)::value;
+    constexpr double s = T::S[p][I][J];
+    if constexpr (s != 0.0) v = fma(gm[p], s, v);
+  });
+  return v;
+}
+
+// ------------------------------------------------------------------ path 1: atomic
+template <int DIM, int DEG, int VAR>
+__global__ void __launch_bounds__(128) heat_jacobian_atomic(const KArgs a) {
+  using T = RefT<DIM, DEG, VAR>;
+  constexpr int ND = T::ND, NP = T::NP;
+  const int64_t c = a.c0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.c1) return;
+  int32_t cc[DIM + 1];
+#pragma unroll
+  for (int v = 0; v <= DIM; ++v) cc[v] = a.cell_coord_t[v * a.ncells_total + c];
+  Geom<DIM> g;
+  compute_geometry<DIM>(a.coords, cc, g);
+  double gm[NP];
+  metric<DIM>(g, gm);
+  const double m = a.shift * g.adet;
+  int64_t rowbase[ND];
+  uint32_t colbc = 0, rowok = 0;
+#pragma unroll
+  for (int i = 0; i < ND; ++i) {
+    const int32_t n = a.cell_node_t[i * a.ncells_total + c];
+    const bool bc = a.isbc[n];
+    colbc |= (bc ? 1u : 0u) << i;
+    const bool ok = n < a.nown && !bc;
+    rowok |= (ok ? 1u : 0u) << i;
+    rowbase[i] = ok ? a.nrowptr[n] : 0;
+  }
+  static_for<ND>([&](auto I) {
+    constexpr int i = decltype(I)::value;
+    static_for<ND - i>([&](auto JJ) {
+      constexpr int j = i + decltype(JJ)::value;
+      const double v = heat_entry<T, i, j, NP>(m, gm);
+      if (((rowok >> i) & 1u) && !((colbc >> j) & 1u))
+        red_add_f64(a.out + rowbase[i] + a.pos8_t[(int64_t)(i * ND + j) * a.ncells_total + c], v);
+      if (j != i && ((rowok >> j) & 1u) && !((colbc >> i) & 1u))
+        red_add_f64(a.out + rowbase[j] + a.pos8_t[(int64_t)(j * ND + i) * a.ncells_total + c], v);
+    });
+  });
+}
+
+template <int DIM, int DEG, int VAR>
+__global__ void __launch_bounds__(128) heat_residual_atomic(const KArgs a) {
+  using T = RefT<DIM, DEG, VAR>;
+  constexpr int ND = T::ND, NP = T::NP;
+  const int64_t c = a.c0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.c1) return;
+  int32_t cc[DIM + 1], nodes[ND];
+#pragma unroll
+  for (int v = 0; v <= DIM; ++v) cc[v] = a.cell_coord_t[v * a.ncells_total + c];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) nodes[i] = a.cell_node_t[i * a.ncells_total + c];
+  Geom<DIM> g;
+  compute_geometry<DIM>(a.coords, cc, g);
+  double gm[NP];
+  metric<DIM>(g, gm);
+  double u[ND], ud[ND];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) {
+    u[i] = __ldg(a.x + nodes[i]);
+    ud[i] = __ldg(a.xdot + nodes[i]);
+  }
+  static_for<ND>([&](auto I) {
+    constexpr int i = decltype(I)::value;
+    double mass = -a.p0 * T::M0[i];
+    static_for<ND>([&](auto J) {
+      constexpr int j = decltype(J)::value;
+      constexpr double r = T::R00[i][j];
+      if constexpr (r != 0.0) mass = fma(r, ud[j], mass);
+    });
+    double f = mass * g.adet;
+    static_for<NP>([&](auto P) {
+      constexpr int p = decltype(P)::value;
+      double s = 0.0;
+      static_for<ND>([&](auto J) {
+        constexpr int j = decltype(J)::value;
+        constexpr double sv = T::S[p][i][j];
+        if constexpr (sv != 0.0) s = fma(sv, u[j], s);
+      });
+      f = fma(gm[p], s, f);
+    });
+    const int64_t n = nodes[i];
+    if (n < a.nown && !a.isbc[n]) red_add_f64(a.out + n, f);
+  });
+}
+
+template <int DIM, int DEG, int VAR>
+int launch_atomic(int which, const KArgs &a, cudaStream_t s) {
+  const int64_t n = a.c1 - a.c0;
+  if (n <= 0) return 0;
+  const int threads = 128;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  if (which == 0)
+    heat_residual_atomic<DIM, DEG, VAR><<<blocks, threads, 0, s>>>(a);
+  else
+    heat_jacobian_atomic<DIM, DEG, VAR><<<blocks, threads, 0, s>>>(a);
+  return cudaGetLastError() == cudaSuccess ? 0 : 2;
+}
+
+// ------------------------------------------------------------------ path 2: owner-computes gather
+struct GArgs {
+  const double *coords;
+  const int32_t *cell_coord_t, *cell_node_t;
+  const double *x, *xdot;
+  double *out;
+  const uint8_t *isbc;
+  const int64_t *nrowptr, *adj_ptr;
+  const int64_t *bstart, *bbase;
+  const int32_t *bcells, *bcount;
+  const uint16_t *cend, *cidx, *ridx;
+  int64_t ncells_total;
+  int32_t cmax;
+  double shift, p0;
+};
+
+// one CTA per row block.  Phase A: element matrices of the block's cells -> shared memory
+// (symmetric packing, odd stride).  Phase B: one thread per CSR slot sums its staged
+// contributions in fixed order and writes the value once (coalesced, no atomics, no zero-fill).
+template <int DIM, int DEG, int VAR>
+__global__ void __launch_bounds__(256) heat_jacobian_gather(const GArgs a) {
+  using T = RefT<DIM, DEG, VAR>;
+  constexpr int ND = T::ND, NP = T::NP, NEP = (ND * (ND + 1) / 2) | 1;
+  extern __shared__ double stage[];
+  const int64_t b = blockIdx.x;
+  const int ncell = a.bcount[b];
+  const int32_t *cells = a.bcells + b * a.cmax;
+  for (int k = threadIdx.x; k < ncell; k += blockDim.x) {
+    const int64_t c = cells[k];
+    int32_t cc[DIM + 1];
+#pragma unroll
+    for (int v = 0; v <= DIM; ++v) cc[v] = a.cell_coord_t[v * a.ncells_total + c];
+    Geom<DIM> g;
+    compute_geometry<DIM>(a.coords, cc, g);
+    double gm[NP];
+    metric<DIM>(g, gm);
+    const double m = a.shift * g.adet;
+    double *st = stage + k * NEP;
+    static_for<ND>([&](auto I) {
+      constexpr int i = decltype(I)::value;
+      static_for<ND - i>([&](auto JJ) {
+        constexpr int j = i + decltype(JJ)::value;
+        constexpr int e = i * ND - (i * (i - 1)) / 2 + (j - i);
+        st[e] = heat_entry<T, i, j, NP>(m, gm);
+      });
+    });
+  }
+  __syncthreads();
+  const int64_t s0 = a.nrowptr[a.bstart[b]], s1 = a.nrowptr[a.bstart[b + 1]];
+  const uint16_t *idx = a.cidx + a.bbase[b];
+  for (int64_t s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+    const int beg = s == s0 ? 0 : a.cend[s - 1];
+    const int end = a.cend[s];
+    double acc = 0.0;
+    for (int k = beg; k < end; ++k) acc += stage[idx[k]];
+    a.out[s] = acc;
+  }
+}
+
+template <int DIM, int DEG, int VAR>
+__global__ void __launch_bounds__(256) heat_residual_gather(const GArgs a) {
+  using T = RefT<DIM, DEG, VAR>;
+  constexpr int ND = T::ND, NP = T::NP, NDP = ND | 1;
+  extern __shared__ double stage[];
+  const int64_t b = blockIdx.x;
+  const int ncell = a.bcount[b];
+  const int32_t *cells = a.bcells + b * a.cmax;
+  for (int k = threadIdx.x; k < ncell; k += blockDim.x) {
+    const int64_t c = cells[k];
+    int32_t cc[DIM + 1], nodes[ND];
+#pragma unroll
+    for (int v = 0; v <= DIM; ++v) cc[v] = a.cell_coord_t[v * a.ncells_total + c];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) nodes[i] = a.cell_node_t[i * a.ncells_total + c];
+    Geom<DIM> g;
+    compute_geometry<DIM>(a.coords, cc, g);
+    double gm[NP];
+    metric<DIM>(g, gm);
+    double u[ND], ud[ND];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) {
+      u[i] = __ldg(a.x + nodes[i]);
+      ud[i] = __ldg(a.xdot + nodes[i]);
+    }
+    double *st = stage + k * NDP;
+    static_for<ND>([&](auto I) {
+      constexpr int i = decltype(I)::value;
+      double mass = -a.p0 * T::M0[i];
+      static_for<ND>([&](auto J) {
+        constexpr int j = decltype(J)::value;
+        constexpr double r = T::R00[i][j];
+        if constexpr (r != 0.0) mass = fma(r, ud[j], mass);
+      });
+      double f = mass * g.adet;
+      static_for<NP>([&](auto P) {
+        constexpr int p = decltype(P)::value;
+        double sacc = 0.0;
+        static_for<ND>([&](auto J) {
+          constexpr int j = decltype(J)::value;
+          constexpr double sv = T::S[p][i][j];
+          if constexpr (sv != 0.0) sacc = fma(sv, u[j], sacc);
+        });
+        f = fma(gm[p], sacc, f);
+      });
+      st[i] = f;
+    });
+  }
+  __syncthreads();
+  const int64_t r0 = a.bstart[b], r1 = a.bstart[b + 1];
+  for (int64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+    double acc = 0.0;
+    if (!a.isbc[r])
+      for (int64_t k = a.adj_ptr[r]; k < a.adj_ptr[r + 1]; ++k) acc += stage[a.ridx[k]];
+    a.out[r] = acc;
+  }
+}
+
+template <int DIM, int DEG, int VAR>
+int launch_gather(int which, const GArgs &a, int64_t nblocks, cudaStream_t s) {
+  using T = RefT<DIM, DEG, VAR>;
+  constexpr int ND = T::ND;
+  const size_t smem = sizeof(double) * (size_t)a.cmax * (which == 0 ? (ND | 1) : ((ND * (ND + 1) / 2) | 1));
+  if (smem > 227 * 1024) return 4;
+  if (which == 0) {
+    auto k = heat_residual_gather<DIM, DEG, VAR>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<(unsigned)nblocks, 256, smem, s>>>(a);
+  } else {
+    auto k = heat_jacobian_gather<DIM, DEG, VAR>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<(unsigned)nblocks, 256, smem, s>>>(a);
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : 2;
+}
+
+__global__ void set_values_k(double *__restrict__ v, const int64_t *__restrict__ slots, int64_t n, double val) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n && slots[t] >= 0) v[slots[t]] = val;
+}
+
+}  // namespace
+
+template <int DIM, int DEG, int VAR>
+static bool tables_match(const double *R) {
+  using T = RefT<DIM, DEG, VAR>;
+  constexpr int ND = T::ND;
+  const int d1 = DIM + 1;
+  double err = 0.0;
+  for (int i = 0; i < ND; ++i)
+    for (int j = 0; j < ND; ++j) {
+      err = fmax(err, fabs(R[i * ND + j] - T::R00[i][j]));
+      int p = 0;
+      for (int a = 1; a <= DIM; ++a)
+        for (int b = a; b <= DIM; ++b, ++p) {
+          const double rab = R[((a * d1 + b) * ND + i) * ND + j], rba = R[((b * d1 + a) * ND + i) * ND + j];
+          const double s = a == b ? rab : rab + rba;
+          const double st = a == b ? R[((a * d1 + b) * ND + j) * ND + i] : R[((a * d1 + b) * ND + j) * ND + i] + R[((b * d1 + a) * ND + j) * ND + i];
+          err = fmax(err, fabs(0.5 * (s + st) - T::S[p][i][j]));
+        }
+    }
+  return err < 1e-13;
+}
+
+// returns the RefT variant whose compile-time tensors equal the run-time tensors, or -1
+int fdts_heat_match_tables(int dim, int deg, const double *R) {
+#define CASE(D, K, V) \
+  if (dim == D && deg == K && tables_match<D, K, V>(R)) return V;
+  CASE(1, 1, 1) CASE(1, 2, 1) CASE(1, 3, 0) CASE(1, 3, 1)
+  CASE(2, 1, 1) CASE(2, 2, 1) CASE(2, 3, 0) CASE(2, 3, 1)
+  CASE(3, 1, 1) CASE(3, 2, 1) CASE(3, 3, 0) CASE(3, 3, 1)
+#undef CASE
+  return -1;
+}
+
+// which: 0 residual, 1 Jacobian.  Full call: zero, assemble, boundary fix-up.
 int fdts_launch_heat(fdts_engine *e, int which, const double *x, const double *xdot, double shift, double *out,
                      int64_t c0, int64_t c1, cudaStream_t s) {
-  (void)e; (void)which; (void)x; (void)xdot; (void)shift; (void)out; (void)c0; (void)c1; (void)s;
-  fdts_set_error("owner-computes heat path not built yet");
-  return 3;
+  if (e->cfg.family != FDTS_HEAT || e->cfg.ncomp != 1) {
+    fdts_set_error("closed-form path: heat family only");
+    return 3;
+  }
+  KArgs a = fdts_make_kargs(e, x, xdot, shift, out, c0, c1);
+  const int dim = e->cfg.dim, deg = e->cfg.degree, var = e->variant;
+  if (e->opt_scatter == 2) {
+    if (!e->plan.ready) {
+      fdts_set_error("gather path requested but no gather plan is built (fdts_set_row_blocks)");
+      return 3;
+    }
+    const GatherPlan &p = e->plan;
+    GArgs g;
+    g.coords = e->coords; g.cell_coord_t = e->cell_coord; g.cell_node_t = e->cell_node;
+    g.x = x; g.xdot = xdot; g.out = out; g.isbc = e->isbc;
+    g.nrowptr = e->nrowptr; g.adj_ptr = e->adj_ptr; g.bstart = p.bstart; g.bbase = p.bbase;
+    g.bcells = p.bcells; g.bcount = p.bcount; g.cend = p.cend; g.cidx = p.cidx; g.ridx = p.ridx;
+    g.ncells_total = e->cfg.num_cells; g.cmax = p.cmax; g.shift = shift; g.p0 = e->cfg.params[0];
+    int rc = 3;
+#define GCASE(D, K, V) \
+  if (dim == D && deg == K && (K < 3 || var == V)) rc = launch_gather<D, K, V>(which, g, p.nblocks, s);
+    GCASE(1, 1, 1) GCASE(1, 2, 1) GCASE(1, 3, 0) GCASE(1, 3, 1)
+    GCASE(2, 1, 1) GCASE(2, 2, 1) GCASE(2, 3, 0) GCASE(2, 3, 1)
+    GCASE(3, 1, 1) GCASE(3, 2, 1) GCASE(3, 3, 0) GCASE(3, 3, 1)
+#undef GCASE
+    if (rc == 4) fdts_set_error("gather path: a row block needs more shared memory than one SM has");
+    if (rc == 3) fdts_set_error("gather path: unsupported dimension/degree");
+    if (rc == 2) fdts_set_error(std::string("gather kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    if (rc) return rc;
+    e->launches++;
+    if (which == 1 && e->cfg.num_bc_nodes > 0) {
+      const int64_t n = e->cfg.num_bc_nodes;
+      set_values_k<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, e->bc_diag_slot, n, 1.0);
+      e->launches++;
+    }
+    FDTS_CHECK(cudaGetLastError());
+    return 0;
+  }
+  if (var < 0) {
+    fdts_set_error("closed-form heat path: run-time reference tensors do not match the compiled tables");
+    return 3;
+  }
+  if (which == 0)
+    FDTS_CHECK(cudaMemsetAsync(out, 0, sizeof(double) * e->cfg.num_owned_nodes, s));
+  else
+    FDTS_CHECK(cudaMemsetAsync(out, 0, sizeof(double) * e->node_nnz, s));
+  int rc = 3;
+#define CASE(D, K, V) \
+  if (dim == D && deg == K && (K < 3 || var == V)) rc = launch_atomic<D, K, V>(which, a, s);
+  CASE(1, 1, 1) CASE(1, 2, 1) CASE(1, 3, 0) CASE(1, 3, 1)
+  CASE(2, 1, 1) CASE(2, 2, 1) CASE(2, 3, 0) CASE(2, 3, 1)
+  CASE(3, 1, 1) CASE(3, 2, 1) CASE(3, 3, 0) CASE(3, 3, 1)
+#undef CASE
+  if (rc == 3) fdts_set_error("closed-form heat kernel: unsupported dimension/degree");
+  if (rc == 2) fdts_set_error(std::string("heat kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+  if (rc) return rc;
+  e->launches++;
+  if (which == 1 && e->cfg.num_bc_nodes > 0) {
+    const int64_t n = e->cfg.num_bc_nodes;
+    set_values_k<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, e->bc_diag_slot, n, 1.0);
+    e->launches++;
+  }
+  FDTS_CHECK(cudaGetLastError());
+  return 0;
 }

@@ -24,7 +24,7 @@ SYMBOLS = [
     "fdts_last_error", "fdts_version", "fdts_create", "fdts_destroy", "fdts_sizes", "fdts_get_csr",
     "fdts_get_node_csr", "fdts_set_param", "fdts_set_option", "fdts_get_option", "fdts_ifunction", "fdts_ijacobian",
     "fdts_ifunction_range", "fdts_ijacobian_range", "fdts_ifunction_host", "fdts_ijacobian_host", "fdts_halo_pack",
-    "fdts_halo_unpack", "fdts_launch_count", "fdts_measure_fp64_peak",
+    "fdts_halo_unpack", "fdts_launch_count", "fdts_measure_fp64_peak", "fdts_csr_spmv", "fdts_csr_diagonal", "fdts_set_row_blocks",
 ]
 
 
@@ -82,6 +82,10 @@ def load_library():
         lib.fdts_ijacobian_host.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         lib.fdts_halo_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         lib.fdts_halo_unpack.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+        lib.fdts_set_row_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        lib.fdts_csr_spmv.argtypes = [C.c_int64] + [C.c_void_p] * 6
+        lib.fdts_csr_diagonal.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                          C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         lib.fdts_measure_fp64_peak.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_double)]
         _LIB = lib
     return _LIB
@@ -154,6 +158,12 @@ class Engine:
         self.num_cells, self.num_interior_cells = m.num_cells, m.num_interior_cells
         self._lib = lib
         if scatter is not None:
+            if int(scatter) == 2:
+                starts = V.row_block_starts()
+                if starts is None:  # untiled numbering: uniform blocks
+                    starts = torch.arange(0, V.num_owned_nodes + 128, 128).clamp(max=V.num_owned_nodes)
+                    starts = torch.unique(starts)
+                self.set_row_blocks(starts)
             self.set_option("scatter", scatter)
 
     def __del__(self):
@@ -172,6 +182,12 @@ class Engine:
         v = C.c_int64(0)
         _check(self._lib.fdts_get_option(self._h, key.encode(), C.byref(v)), "fdts_get_option")
         return v.value
+
+    def set_row_blocks(self, starts):
+        """row blocks (owned-node row offsets) of the owner-computes gather path; builds the plan."""
+        st = torch.as_tensor(starts, dtype=torch.int64).cpu().contiguous()
+        with torch.cuda.device(self.device):
+            _check(self._lib.fdts_set_row_blocks(self._h, st.data_ptr(), st.numel() - 1), "fdts_set_row_blocks")
 
     def set_param(self, index, value):
         _check(self._lib.fdts_set_param(self._h, index, float(value)), "fdts_set_param")

@@ -47,10 +47,24 @@ for perm in [(0, 1, 2), (0, 2, 1), (2, 0, 1), (1, 0, 2), (2, 1, 0), (1, 2, 0)]:
     _CELLS[3].append(path)
 
 
-def _tiled_index(p, dims, tile):
+def _tile_sizes(n, tile, offset):
+    """sizes of the 1-D tiles of range(n): the first tile has ``offset`` points
+    (if offset > 0), then full tiles of ``tile`` points, then the remainder."""
+    out = []
+    if offset > 0:
+        out.append(min(offset, n))
+    left = n - sum(out)
+    while left > 0:
+        out.append(min(tile, left))
+        left -= out[-1]
+    return out
+
+
+def _tiled_index(p, dims, tile, offset=0):
     """Bijective numbering of the integer box prod(range(dims[a])) that walks
-    tile by tile (tile edge ``tile``; last tiles ragged), x fastest inside a
-    tile.  ``p``: (..., dim) int64 tensor.  tile <= 0 means lexicographic."""
+    tile by tile (tile edge ``tile``; tile boundaries at offset + k*tile; first
+    and last tiles ragged), x fastest inside a tile.  ``p``: (..., dim) int64
+    tensor.  tile <= 0 means lexicographic."""
     dim = len(dims)
     if tile is None or tile <= 0:
         idx = p[..., dim - 1]
@@ -58,14 +72,21 @@ def _tiled_index(p, dims, tile):
             idx = idx * dims[a] + p[..., a]
         return idx
     T = int(tile)
-    t = [torch.div(p[..., a], T, rounding_mode="floor") for a in range(dim)]
-    l = [p[..., a] - t[a] * T for a in range(dim)]
-    s = [torch.clamp(dims[a] - t[a] * T, max=T) for a in range(dim)]
+    sh = (T - int(offset) % T) % T  # shift so that tiles are uniform on x' = x + sh
+    start, l, s = [], [], []
+    for a in range(dim):
+        xs = p[..., a] + sh
+        t = torch.div(xs, T, rounding_mode="floor")
+        st = torch.clamp(t * T, min=sh)
+        en = torch.clamp((t + 1) * T, max=dims[a] + sh)
+        start.append(st - sh)
+        l.append(xs - st)
+        s.append(en - st)
     # offset of the tile: full slabs of higher dimensions first
     off = torch.zeros_like(p[..., 0])
     # dims above `a` are restricted to the current tile extent s[b], dims below are full
     for a in range(dim - 1, -1, -1):
-        block = t[a] * T
+        block = start[a]
         for b in range(dim):
             if b < a:
                 block = block * dims[b]
@@ -221,12 +242,13 @@ class FunctionSpace:
     """
 
     def __init__(self, mesh: SimplexMesh, degree: int, ncomp: int = 1, layout: str = "interleaved",
-                 variant: str = "gll", tile=None):
+                 variant: str = "gll", tile=None, tile_offset=0):
         assert degree in (1, 2, 3)
         assert layout in ("interleaved", "blocked")
         self.mesh, self.degree, self.ncomp, self.layout, self.variant = mesh, degree, ncomp, layout, variant
         self.dim = mesh.dim
         self.tile = mesh.tile * degree if tile is None else int(tile)
+        self.tile_offset = int(tile_offset)
         self.nd = fem.num_nodes(self.dim, degree)
         self._build()
 
@@ -273,7 +295,7 @@ class FunctionSpace:
         owned = ((q >= 0) & (q < dims_t)).all(dim=-1)
         ids = torch.full(p.shape[:-1], -1, dtype=torch.int64, device=dev)
         qo = torch.where(owned[..., None], q, torch.zeros_like(q))
-        ids_owned = _tiled_index(qo, dims, self.tile)
+        ids_owned = _tiled_index(qo, dims, self.tile, self.tile_offset)
         ids = torch.where(owned, ids_owned, ids)
         if part.size > 1:
             gl = self._ghost_table(rank)
@@ -405,7 +427,7 @@ class FunctionSpace:
             sel = orank == r
             if sel.any():
                 q = lat[sel] - torch.tensor(lo, device=lat.device)
-                out[sel] = base + _tiled_index(q, dims, self.tile)
+                out[sel] = base + _tiled_index(q, dims, self.tile, self.tile_offset)
             base += int(np.prod(dims))
         return out
 
@@ -441,6 +463,24 @@ class FunctionSpace:
                 ids = self._local_ids(gtr["points"][sel])
                 assert int(ids.min()) >= 0 and int(ids.max()) < self.num_owned_nodes
                 self.send_lists[r] = ids.to(torch.int32).contiguous()
+
+    def row_block_starts(self):
+        """owned-node row ranges of the numbering tiles (each tile is contiguous
+        in the numbering): int64 tensor of nblocks+1 offsets.  The gather kernels
+        use them as row blocks (one CTA per tile)."""
+        dims = [self.owned_hi[a] - self.owned_lo[a] for a in range(self.dim)]
+        if self.tile <= 0:
+            return None
+        per_dim = [_tile_sizes(dims[a], self.tile, self.tile_offset) for a in range(self.dim)]
+        sizes = torch.tensor(per_dim[self.dim - 1], dtype=torch.int64)
+        # order: slowest dimension outermost; tile (t_{d-1}, ..., t_0) has prod of sizes
+        out = torch.ones(1, dtype=torch.int64)
+        for a in range(self.dim - 1, -1, -1):
+            out = (out[:, None] * torch.tensor(per_dim[a], dtype=torch.int64)[None, :]).reshape(-1)
+        starts = torch.zeros(out.numel() + 1, dtype=torch.int64)
+        starts[1:] = torch.cumsum(out, 0)
+        assert int(starts[-1]) == self.num_owned_nodes
+        return starts
 
     # dof-level helpers --------------------------------------------------------
     @property

@@ -1,0 +1,349 @@
+"""Minimal PETSc-TS stand-in: the *caller* of the hot path.
+
+PETSc (TS/SNES/KSP) is what invokes ``form_function`` / ``form_jacobian`` in the
+reference (firedrake_ts/ts_solver.py:233-272, :364) and stays in place in a real
+deployment (out of scope).  PETSc is absent in this image,
+so this module provides just enough of its surface -- ``Vec``, ``Mat``, ``DM``,
+``SNES``/``KSP`` settings and ``TS`` with the BEULER / THETA integrators of
+SURVEY.md A.5 -- for the drop-in ``DAESolver`` to run standalone and for the
+trajectory tests.  Callback signatures are PETSc's:
+``IFunction(ts, t, X, Xdot, F)`` and ``IJacobian(ts, t, X, Xdot, shift, J, P)``.
+
+Everything here works on torch tensors, on the GPU or (for the oracle-driven
+tests) on the CPU.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+
+class Vec:
+    """PETSc.Vec look-alike over one torch tensor (the rank's owned dofs)."""
+
+    def __init__(self, array: torch.Tensor, comm=None):
+        self.array = array
+        self.comm = comm
+
+    @property
+    def handle(self):
+        return id(self)
+
+    def copy(self, result=None):
+        if result is None:
+            return Vec(self.array.clone(), self.comm)
+        if result.array.data_ptr() != self.array.data_ptr():
+            result.array.copy_(self.array)
+        return result
+
+    def duplicate(self):
+        return Vec(torch.zeros_like(self.array), self.comm)
+
+    def getSize(self):
+        return self.array.numel()
+
+    def set(self, v):
+        self.array.fill_(v)
+
+    def axpy(self, alpha, x):
+        self.array.add_(x.array, alpha=alpha)
+
+    def dot(self, other):
+        return _allreduce_sum(torch.dot(self.array, other.array), self.comm)
+
+    def norm(self):
+        return math.sqrt(float(self.dot(self)))
+
+
+def _allreduce_sum(t, comm):
+    if comm is not None:
+        import torch.distributed as dist
+
+        t = t.clone()
+        dist.all_reduce(t, group=comm)
+    return t
+
+
+class Mat:
+    """PETSc.Mat (AIJ) look-alike: device-resident CSR whose value array the
+    engine fills in place (``assert J.handle == ctx._jac.petscmat.handle``,
+    firedrake_ts/solving_utils.py:284)."""
+
+    def __init__(self, rowptr, colidx, values, ncols, halo=None):
+        self.rowptr, self.colidx, self.values = rowptr, colidx, values
+        self.nrows = rowptr.numel() - 1
+        self.ncols = ncols
+        self.halo = halo  # forward exchange for the off-process columns (None on one rank)
+        self._nullspace = None
+        self._lu = None
+
+    @property
+    def handle(self):
+        return id(self)
+
+    def zeroEntries(self):
+        self.values.zero_()
+
+    def getValuesCSR(self):
+        return self.rowptr, self.colidx, self.values
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+
+        return sp.csr_matrix((self.values.cpu().numpy(), self.colidx.cpu().numpy(), self.rowptr.cpu().numpy()),
+                             shape=(self.nrows, self.ncols))
+
+    def mult(self, x_local: torch.Tensor) -> torch.Tensor:
+        """y = A x for a *local* (owned+ghost) x; returns owned rows."""
+        from . import linalg
+
+        return linalg.csr_spmv(self.rowptr, self.colidx, self.values, x_local)
+
+    def diagonal(self):
+        from . import linalg
+
+        return linalg.csr_diagonal(self.rowptr, self.colidx, self.values)
+
+
+class DM:
+    """DMShell stand-in that carries the application context (the reference looks
+    its ``_TSContext`` up through ``dmhooks.get_appctx(ts.getDM())``,
+    firedrake_ts/solving_utils.py:245-246)."""
+
+    def __init__(self, comm=None):
+        self.comm = comm
+        self._appctx = []
+
+
+class SNES:
+    def __init__(self):
+        self.rtol, self.atol, self.stol, self.max_it = 1e-8, 1e-50, 1e-8, 50
+        self.ksp = KSP()
+        self.its = 0
+        self.reason = 0
+
+
+class KSP:
+    def __init__(self):
+        self.type, self.pc_type = "gmres", "jacobi"
+        self.rtol, self.atol, self.max_it, self.restart = 1e-5, 1e-50, 10000, 30
+        self.its = 0
+
+
+class ConvergedReason:
+    CONVERGED_ITERATING = 0
+    CONVERGED_TIME = 1
+    CONVERGED_ITS = 2
+    DIVERGED_NONLINEAR_SOLVE = -1
+    DIVERGED_STEP_REJECTED = -2
+
+
+class TS:
+    """BEULER / THETA time stepper with Newton + Krylov, PETSc callback protocol."""
+
+    ConvergedReason = ConvergedReason
+
+    class EquationType:
+        IMPLICIT = 1
+
+    def __init__(self, comm=None):
+        self.comm = comm
+        self.dm = None
+        self.snes = SNES()
+        self.type, self.theta = "beuler", 1.0
+        self.time, self.max_time, self.dt = 0.0, 1.0, 0.1  # PETSc's default step is 0.1
+        self.max_steps = 5000
+        self.exact_final_time = "stepover"
+        self.steps = 0
+        self.reason = 0
+        self._ifunction = self._ijacobian = None
+        self._F = self._J = self._P = None
+        self._monitor = None
+        self.equation_type = None
+        self.newton_its = 0
+        self.linear_its = 0
+
+    # -- PETSc-like setters / getters -------------------------------------------
+    def create(self, comm=None):
+        self.comm = comm
+        return self
+
+    def getSNES(self):
+        return self.snes
+
+    def setDM(self, dm):
+        self.dm = dm
+
+    def getDM(self):
+        return self.dm
+
+    def setMonitor(self, monitor):
+        self._monitor = monitor
+
+    def setTime(self, t):
+        self.time = float(t)
+
+    def getTime(self):
+        return self.time
+
+    def setMaxTime(self, t):
+        self.max_time = float(t)
+
+    def setTimeStep(self, dt):
+        self.dt = float(dt)
+
+    def getTimeStep(self):
+        return self.dt
+
+    def setMaxSteps(self, n):
+        self.max_steps = int(n)
+
+    def getStepNumber(self):
+        return self.steps
+
+    def setEquationType(self, et):
+        self.equation_type = et
+
+    def setType(self, name):
+        assert name in ("beuler", "theta"), f"TS type {name!r} is not provided by the stand-in"
+        self.type = name
+        if name == "beuler":
+            self.theta = 1.0
+
+    def setTheta(self, theta):
+        self.theta = float(theta)
+
+    def setIFunction(self, f, vec=None):
+        self._ifunction, self._F = f, vec
+
+    def setIJacobian(self, f, J=None, P=None):
+        self._ijacobian, self._J, self._P = f, J, P
+
+    def getConvergedReason(self):
+        return self.reason
+
+    def setFromOptions(self, opts: dict):
+        o = dict(opts or {})
+        if "ts_type" in o:
+            self.setType(o["ts_type"])
+        if "ts_theta_theta" in o:
+            self.setTheta(o["ts_theta_theta"])
+        if "ts_dt" in o:
+            self.setTimeStep(o["ts_dt"])
+        if "ts_max_steps" in o:
+            self.setMaxSteps(o["ts_max_steps"])
+        if "ts_exact_final_time" in o:
+            self.exact_final_time = o["ts_exact_final_time"]
+        s, k = self.snes, self.snes.ksp
+        s.rtol = float(o.get("snes_rtol", s.rtol))
+        s.atol = float(o.get("snes_atol", s.atol))
+        s.stol = float(o.get("snes_stol", s.stol))
+        s.max_it = int(o.get("snes_max_it", s.max_it))
+        k.type = o.get("ksp_type", k.type)
+        k.pc_type = o.get("pc_type", k.pc_type)
+        k.rtol = float(o.get("ksp_rtol", k.rtol))
+        k.atol = float(o.get("ksp_atol", k.atol))
+        k.max_it = int(o.get("ksp_max_it", k.max_it))
+        k.restart = int(o.get("ksp_gmres_restart", k.restart))
+
+    # -- linear solve ---------------------------------------------------------------
+    def _to_local(self, x_owned):
+        """owned vector -> local (owned + ghost) vector for the mat-vec."""
+        halo = self._J.halo
+        if halo is None:
+            return x_owned
+        return halo.owned_to_local(x_owned)
+
+    def _linear_solve(self, rhs: torch.Tensor) -> torch.Tensor:
+        from . import linalg
+
+        k, A = self.snes.ksp, self._J
+        comm = self.comm
+
+        def matvec(v):
+            return A.mult(self._to_local(v))
+
+        def dot(a, b):
+            return float(_allreduce_sum(torch.dot(a, b), comm))
+
+        if k.pc_type == "lu":
+            assert comm is None, "pc_type lu is a single-rank test facility"
+            import numpy as np
+            import scipy.sparse.linalg as spla
+
+            lu = spla.splu(A.to_scipy().tocsc())
+            sol = lu.solve(rhs.cpu().numpy())
+            k.its = 1
+            return torch.from_numpy(np.ascontiguousarray(sol)).to(rhs.device)
+        if k.pc_type == "jacobi":
+            dinv = 1.0 / A.diagonal()
+            prec = lambda r: r * dinv  # noqa: E731
+        else:
+            prec = lambda r: r  # noqa: E731
+        if k.type == "cg":
+            x, k.its = linalg.pcg(matvec, rhs, prec, dot, k.rtol, k.atol, k.max_it)
+        else:
+            x, k.its = linalg.gmres(matvec, rhs, prec, dot, k.rtol, k.atol, k.max_it, k.restart)
+        return x
+
+    # -- the integrator ---------------------------------------------------------------
+    def _stage_solve(self, X: Vec, X0: torch.Tensor, ts_time: float, shift: float):
+        s = self.snes
+        Xdot = Vec(torch.empty_like(X.array), self.comm)
+        F = self._F if self._F is not None else X.duplicate()
+        fnorm0 = None
+        for it in range(s.max_it + 1):
+            torch.sub(X.array, X0, out=Xdot.array)
+            Xdot.array.mul_(shift)
+            self._ifunction(self, ts_time, X, Xdot, F)
+            fnorm = F.norm()
+            if fnorm0 is None:
+                fnorm0 = fnorm
+            if fnorm <= s.atol or fnorm <= s.rtol * fnorm0:
+                s.its, s.reason = it, 1
+                return Xdot
+            if it == s.max_it:
+                break
+            self._ijacobian(self, ts_time, X, Xdot, shift, self._J, self._P)
+            dx = self._linear_solve(-F.array)
+            self.linear_its += s.ksp.its
+            X.array.add_(dx)
+            self.newton_its += 1
+            xnorm = X.norm()
+            if float(_allreduce_sum(torch.dot(dx, dx), self.comm)) ** 0.5 <= s.stol * xnorm:
+                # step tolerance: re-evaluate once so that Xdot matches the final X
+                torch.sub(X.array, X0, out=Xdot.array)
+                Xdot.array.mul_(shift)
+                s.its, s.reason = it + 1, 2
+                return Xdot
+        s.reason = -1
+        return None
+
+    def solve(self, u: Vec):
+        assert self._ifunction is not None and self._ijacobian is not None
+        self.steps, self.reason = 0, 0
+        theta = self.theta
+        if self._monitor:
+            self._monitor(self, self.steps, self.time, u)
+        X = Vec(u.array.clone(), self.comm)
+        while self.time < self.max_time * (1 - 1e-14) and self.steps < self.max_steps:
+            dt = self.dt
+            if self.exact_final_time == "matchstep" and self.time + dt > self.max_time:
+                dt = self.max_time - self.time
+            X0 = u.array.clone()
+            X.array.copy_(X0)
+            shift = 1.0 / (theta * dt)
+            Xdot = self._stage_solve(X, X0, self.time + theta * dt, shift)
+            if Xdot is None:
+                self.reason = ConvergedReason.DIVERGED_NONLINEAR_SOLVE
+                return
+            if theta == 1.0:
+                u.array.copy_(X.array)
+            else:
+                u.array.add_(Xdot.array, alpha=dt)
+            self.time += dt
+            self.steps += 1
+            if self._monitor:
+                self._monitor(self, self.steps, self.time, u)
+        self.reason = ConvergedReason.CONVERGED_TIME if self.time >= self.max_time * (1 - 1e-14) else ConvergedReason.CONVERGED_ITS

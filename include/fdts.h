@@ -99,7 +99,14 @@ int fdts_get_csr(fdts_handle h, int64_t *rowptr_dev, int32_t *colidx_dev, void *
 int fdts_get_node_csr(fdts_handle h, int64_t *rowptr_dev, int32_t *colidx_dev, void *stream);
 
 int fdts_set_param(fdts_handle h, int32_t index, double value);
-/* options: "scatter" 0 = atomic (REDG.ADD.F64), 1 = owner-computes gather (deterministic) */
+/* Row blocks of the owner-computes gather path: starts_host[0..nblocks] are owned-node row
+ * offsets of contiguous blocks (one CTA each); builds the gather plan on the device.
+ * Replaces nothing in the reference: it is the engine's own scatter schedule (K6). */
+int fdts_set_row_blocks(fdts_handle h, const int64_t *starts_host, int64_t nblocks);
+/* options: "scatter" 0 = generic quadrature kernels + atomic scatter (REDG.ADD.F64),
+ *                    1 = closed-form heat kernels + atomic scatter,
+ *                    2 = closed-form heat kernels + owner-computes gather (deterministic, write-once);
+ * read-only: "plan_cells_max", "plan_contributions", "plan_blocks" */
 int fdts_set_option(fdts_handle h, const char *key, int64_t value);
 int fdts_get_option(fdts_handle h, const char *key, int64_t *value);
 
@@ -127,6 +134,13 @@ int fdts_halo_unpack(fdts_handle h, double *x, int64_t first_node, int64_t count
 
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t fdts_launch_count(fdts_handle h);
+
+/* CSR mat-vec / diagonal on device arrays (standalone Newton-Krylov harness; stands in for
+ * PETSc's MatMult / MatGetDiagonal on the MATAIJCUSPARSE Mat the reference's KSP would hold) */
+int fdts_csr_spmv(int64_t nrows, const int64_t *rowptr, const int32_t *colidx, const double *vals, const double *x,
+                  double *y, void *stream);
+int fdts_csr_diagonal(int64_t nrows, const int64_t *rowptr, const int32_t *colidx, const double *vals,
+                      int64_t nown_nodes, int64_t nnodes, int32_t ncomp, int32_t layout, double *d, void *stream);
 
 /* micro-benchmarks used for the roofline denominators: return GB/s resp. GFLOP/s */
 int fdts_measure_fp64_peak(int32_t device, int32_t use_dmma, double *gflops);

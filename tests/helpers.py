@@ -8,14 +8,13 @@ from firedrake_ts_b200 import forms, mesh as M
 from firedrake_ts_b200.function import DirichletBC, Function
 
 
-def make_problem(family, dim, degree, n, *, tile=0, partition=None, device="cpu", variant="gll", seed=0):
+def make_problem(family, dim, degree, n, *, tile=0, partition=None, device="cpu", variant="gll", seed=0,
+                 ftile=None, foffset=0):
     """returns (form, bcs, u, udot) with the seeded states of SURVEY.md 8(d)."""
     shape = (n,) * dim
     msh = M.SimplexMesh(shape, partition=partition, tile=tile, device=device)
-    if family == "heat":
-        V = M.FunctionSpace(msh, degree, variant=variant)
-    elif family == "bbm":
-        V = M.FunctionSpace(msh, degree, variant=variant)
+    if family in ("heat", "bbm"):
+        V = M.FunctionSpace(msh, degree, variant=variant, tile=ftile, tile_offset=foffset)
     elif family == "burgers":
         V = M.FunctionSpace(msh, degree, ncomp=dim, layout="interleaved", variant=variant)
     elif family == "cahn_hilliard":

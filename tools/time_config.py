@@ -20,18 +20,23 @@ ap.add_argument("--tile", type=int, default=4)
 ap.add_argument("--scatter", type=int, default=0)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--peak", action="store_true")
+ap.add_argument("--ftile", type=int, default=None)
+ap.add_argument("--foffset", type=int, default=0)
 a = ap.parse_args()
 
 if a.peak:
     print("fp64 DFMA GFLOP/s", measure_fp64_peak(0, False), "DMMA GFLOP/s", measure_fp64_peak(0, True), flush=True)
 t0 = time.time()
-form, bcs, u, udot = make_problem(a.family, a.dim, a.degree, a.n, tile=a.tile, device="cuda:0")
+form, bcs, u, udot = make_problem(a.family, a.dim, a.degree, a.n, tile=a.tile, device="cuda:0", ftile=a.ftile,
+                                  foffset=a.foffset)
 torch.cuda.synchronize()
 print("mesh+space", time.time() - t0, "s; cells", form.space.mesh.num_cells, "dofs", form.space.num_dofs, flush=True)
 t0 = time.time()
 eng = Engine(form, bcs, scatter=a.scatter)
 torch.cuda.synchronize()
 print("engine create", time.time() - t0, "s; nnz", eng.nnz, "maxrow", eng.max_row_nodes, "maxdeg", eng.max_degree, flush=True)
+if a.scatter == 2:
+    print("plan: blocks", eng.get_option("plan_blocks"), "cells_max", eng.get_option("plan_cells_max"), "contrib", eng.get_option("plan_contributions"), flush=True)
 x, xd = u.data, udot.data
 F = torch.empty(eng.num_rows, dtype=torch.float64, device="cuda")
 J = eng.new_values()
