@@ -21,6 +21,10 @@ struct GatherPlan {
   uint16_t *cidx = nullptr;     // staged element-matrix addresses
   uint16_t *ridx = nullptr;     // per adjacency entry: staged element-vector address
   int64_t total_contrib = 0;
+  int32_t max_block_contrib = 0;  // padded to a multiple of 8
+  int32_t max_block_slots = 0;
+  int32_t max_block_rows = 0;
+  int32_t max_block_adj = 0;
   int ne = 0, nep = 0, ndp = 0; // staged entries per cell (symmetric packing), odd-padded strides
 };
 
@@ -133,6 +137,31 @@ __device__ __forceinline__ void compute_geometry(const double *__restrict__ coor
     g.Jinv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * r;
     g.adet = fabs(det);
   }
+}
+
+// ---- TMA 1-D bulk copy (global -> shared) completing on an mbarrier (SASS: UBLKCP / SYNCS)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
 }
 
 // dof index helpers (layout: 0 interleaved, 1 blocked)

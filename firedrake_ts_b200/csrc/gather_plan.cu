@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) block_scan_counts(const int64_t 
     running += total;
     __syncthreads();
   }
-  if (threadIdx.x == 0) btotal[b] = running;
+  if (threadIdx.x == 0) btotal[b] = (running + 7) & ~7;  // 16-byte granules for the bulk copies
 }
 
 // residual lists: per row the staged element-vector entries, cell ascending
@@ -187,6 +187,19 @@ __global__ void row_contributions(const int64_t *__restrict__ bstart, const int6
     }
     (void)isbc;
   }
+}
+
+__global__ void block_extents(const int64_t *__restrict__ bstart, int64_t nb, const int64_t *__restrict__ nrp,
+                              const int64_t *__restrict__ adj_ptr, const int64_t *__restrict__ bbase,
+                              int64_t *__restrict__ out4) {
+  // out4: max contributions, max slots, max rows, max adjacency entries per block
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const int64_t r0 = bstart[b], r1 = bstart[b + 1];
+  atomicMax((unsigned long long *)&out4[0], (unsigned long long)(bbase[b + 1] - bbase[b]));
+  atomicMax((unsigned long long *)&out4[1], (unsigned long long)(nrp[r1] - nrp[r0]));
+  atomicMax((unsigned long long *)&out4[2], (unsigned long long)(r1 - r0));
+  atomicMax((unsigned long long *)&out4[3], (unsigned long long)(adj_ptr[r1] - adj_ptr[r0]));
 }
 
 struct Widen8 {
@@ -291,7 +304,7 @@ int fdts_build_plan(fdts_engine *e, const int64_t *starts, int64_t nb) {
     // slot contribution counts -> segment ends
     uint8_t *cnt8 = nullptr;
     const int64_t nnz = e->node_nnz;
-    if (cudaMalloc(&cnt8, (size_t)nnz + 1) != cudaSuccess || cudaMalloc(&p.cend, sizeof(uint16_t) * (nnz + 1)) != cudaSuccess ||
+    if (cudaMalloc(&cnt8, (size_t)nnz + 1) != cudaSuccess || cudaMalloc(&p.cend, sizeof(uint16_t) * (nnz + 32)) != cudaSuccess ||
         cudaMalloc(&p.bbase, sizeof(int64_t) * (nb + 1)) != cudaSuccess) {
       fdts_set_error("gather plan: out of memory (slot tables)");
       rc = 2;
@@ -308,8 +321,21 @@ int fdts_build_plan(fdts_engine *e, const int64_t *starts, int64_t nb) {
     cudaMemcpyAsync(&total, p.bbase + nb, sizeof(int64_t), cudaMemcpyDeviceToHost, s);
     cudaStreamSynchronize(s);
     p.total_contrib = total;
-    if (cudaMalloc(&p.cidx, sizeof(uint16_t) * (size_t)(total + 1)) != cudaSuccess ||
-        cudaMalloc(&p.ridx, sizeof(uint16_t) * (size_t)(nc * nd + 1)) != cudaSuccess) {
+    {
+      int64_t *ext = nullptr, hext[4] = {0, 0, 0, 0};
+      if (cudaMalloc(&ext, sizeof(int64_t) * 4) != cudaSuccess) { rc = 2; break; }
+      cudaMemsetAsync(ext, 0, sizeof(int64_t) * 4, s);
+      block_extents<<<GRID(nb, 256), 256, 0, s>>>(p.bstart, nb, e->nrowptr, e->adj_ptr, p.bbase, ext);
+      cudaMemcpyAsync(hext, ext, sizeof(int64_t) * 4, cudaMemcpyDeviceToHost, s);
+      cudaStreamSynchronize(s);
+      cudaFree(ext);
+      p.max_block_contrib = (int32_t)hext[0];
+      p.max_block_slots = (int32_t)hext[1];
+      p.max_block_rows = (int32_t)hext[2];
+      p.max_block_adj = (int32_t)hext[3];
+    }
+    if (cudaMalloc(&p.cidx, sizeof(uint16_t) * (size_t)(total + 32)) != cudaSuccess ||
+        cudaMalloc(&p.ridx, sizeof(uint16_t) * (size_t)(nc * nd + 32)) != cudaSuccess) {
       fdts_set_error("gather plan: out of memory (contribution lists)");
       rc = 2;
       cudaFree(cnt8);

@@ -164,21 +164,41 @@ struct GArgs {
   const uint16_t *cend, *cidx, *ridx;
   int64_t ncells_total;
   int32_t cmax;
+  int32_t off_idx, off_end, off_bar;  // shared-memory layout (bytes)
   double shift, p0;
 };
 
-// one CTA per row block.  Phase A: element matrices of the block's cells -> shared memory
-// (symmetric packing, odd stride).  Phase B: one thread per CSR slot sums its staged
-// contributions in fixed order and writes the value once (coalesced, no atomics, no zero-fill).
+// one CTA per row block.  A single thread first launches TMA bulk copies of the block's index
+// segments into shared memory (they land while phase A computes).  Phase A: element matrices of
+// the block's cells -> shared memory (symmetric packing, odd stride).  Phase B: one thread per CSR
+// slot sums its staged contributions in fixed order and writes the value once (coalesced, no
+// atomics, no zero-fill).
+constexpr int GATHER_THREADS = 512;
+
 template <int DIM, int DEG, int VAR>
-__global__ void __launch_bounds__(256) heat_jacobian_gather(const GArgs a) {
+__global__ void __launch_bounds__(GATHER_THREADS) heat_jacobian_gather(const GArgs a) {
   using T = RefT<DIM, DEG, VAR>;
   constexpr int ND = T::ND, NP = T::NP, NEP = (ND * (ND + 1) / 2) | 1;
-  extern __shared__ double stage[];
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double *stage = reinterpret_cast<double *>(smraw);
+  uint16_t *sidx = reinterpret_cast<uint16_t *>(smraw + a.off_idx);
+  uint16_t *send = reinterpret_cast<uint16_t *>(smraw + a.off_end);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smraw + a.off_bar);
   const int64_t b = blockIdx.x;
+  const int64_t s0 = a.nrowptr[a.bstart[b]], s1 = a.nrowptr[a.bstart[b + 1]];
+  const int64_t s0a = s0 & ~7ll;
+  if (threadIdx.x == 0) {
+    const int64_t base = a.bbase[b];
+    const uint32_t nb_idx = (uint32_t)(a.bbase[b + 1] - base) * 2u;
+    const uint32_t nb_end = (uint32_t)(((s1 + 7) & ~7ll) - s0a) * 2u;
+    mbar_init(bar, 1);
+    mbar_expect_tx(bar, nb_idx + nb_end);
+    if (nb_idx) bulk_g2s(sidx, a.cidx + base, nb_idx, bar);
+    if (nb_end) bulk_g2s(send, a.cend + s0a, nb_end, bar);
+  }
   const int ncell = a.bcount[b];
   const int32_t *cells = a.bcells + b * a.cmax;
-  for (int k = threadIdx.x; k < ncell; k += blockDim.x) {
+  for (int k = threadIdx.x; k < ncell; k += GATHER_THREADS) {
     const int64_t c = cells[k];
     int32_t cc[DIM + 1];
 #pragma unroll
@@ -199,26 +219,41 @@ __global__ void __launch_bounds__(256) heat_jacobian_gather(const GArgs a) {
     });
   }
   __syncthreads();
-  const int64_t s0 = a.nrowptr[a.bstart[b]], s1 = a.nrowptr[a.bstart[b + 1]];
-  const uint16_t *idx = a.cidx + a.bbase[b];
-  for (int64_t s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
-    const int beg = s == s0 ? 0 : a.cend[s - 1];
-    const int end = a.cend[s];
+  mbar_wait(bar, 0);
+  for (int64_t s = s0 + threadIdx.x; s < s1; s += GATHER_THREADS) {
+    const int beg = s == s0 ? 0 : send[s - 1 - s0a];
+    const int end = send[s - s0a];
     double acc = 0.0;
-    for (int k = beg; k < end; ++k) acc += stage[idx[k]];
+    for (int k = beg; k < end; ++k) acc += stage[sidx[k]];
     a.out[s] = acc;
   }
 }
 
 template <int DIM, int DEG, int VAR>
-__global__ void __launch_bounds__(256) heat_residual_gather(const GArgs a) {
+__global__ void __launch_bounds__(GATHER_THREADS) heat_residual_gather(const GArgs a) {
   using T = RefT<DIM, DEG, VAR>;
   constexpr int ND = T::ND, NP = T::NP, NDP = ND | 1;
-  extern __shared__ double stage[];
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double *stage = reinterpret_cast<double *>(smraw);
+  uint16_t *sidx = reinterpret_cast<uint16_t *>(smraw + a.off_idx);
+  int64_t *sptr = reinterpret_cast<int64_t *>(smraw + a.off_end);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smraw + a.off_bar);
   const int64_t b = blockIdx.x;
+  const int64_t r0 = a.bstart[b], r1 = a.bstart[b + 1];
+  const int64_t r0a = r0 & ~1ll;
+  const int64_t a0 = a.adj_ptr[r0], a1 = a.adj_ptr[r1];
+  const int64_t a0a = a0 & ~7ll;
+  if (threadIdx.x == 0) {
+    const uint32_t nb_idx = (uint32_t)(((a1 + 7) & ~7ll) - a0a) * 2u;
+    const uint32_t nb_ptr = (uint32_t)(((r1 + 2) & ~1ll) - r0a) * 8u;
+    mbar_init(bar, 1);
+    mbar_expect_tx(bar, nb_idx + nb_ptr);
+    if (nb_idx) bulk_g2s(sidx, a.ridx + a0a, nb_idx, bar);
+    bulk_g2s(sptr, a.adj_ptr + r0a, nb_ptr, bar);
+  }
   const int ncell = a.bcount[b];
   const int32_t *cells = a.bcells + b * a.cmax;
-  for (int k = threadIdx.x; k < ncell; k += blockDim.x) {
+  for (int k = threadIdx.x; k < ncell; k += GATHER_THREADS) {
     const int64_t c = cells[k];
     int32_t cc[DIM + 1], nodes[ND];
 #pragma unroll
@@ -259,29 +294,38 @@ __global__ void __launch_bounds__(256) heat_residual_gather(const GArgs a) {
     });
   }
   __syncthreads();
-  const int64_t r0 = a.bstart[b], r1 = a.bstart[b + 1];
-  for (int64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+  mbar_wait(bar, 0);
+  for (int64_t r = r0 + threadIdx.x; r < r1; r += GATHER_THREADS) {
     double acc = 0.0;
-    if (!a.isbc[r])
-      for (int64_t k = a.adj_ptr[r]; k < a.adj_ptr[r + 1]; ++k) acc += stage[a.ridx[k]];
+    if (!a.isbc[r]) {
+      const int64_t kb = sptr[r - r0a] - a0a, ke = sptr[r + 1 - r0a] - a0a;
+      for (int64_t k = kb; k < ke; ++k) acc += stage[sidx[k]];
+    }
     a.out[r] = acc;
   }
 }
 
 template <int DIM, int DEG, int VAR>
-int launch_gather(int which, const GArgs &a, int64_t nblocks, cudaStream_t s) {
+int launch_gather(int which, GArgs a, const GatherPlan &p, cudaStream_t s) {
   using T = RefT<DIM, DEG, VAR>;
   constexpr int ND = T::ND;
-  const size_t smem = sizeof(double) * (size_t)a.cmax * (which == 0 ? (ND | 1) : ((ND * (ND + 1) / 2) | 1));
+  auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  size_t off = up16(sizeof(double) * (size_t)p.cmax * (which == 0 ? (ND | 1) : ((ND * (ND + 1) / 2) | 1)));
+  a.off_idx = (int)off;
+  off += up16(2 * (size_t)((which == 0 ? p.max_block_adj : p.max_block_contrib) + 16));
+  a.off_end = (int)off;
+  off += up16(which == 0 ? 8 * (size_t)(p.max_block_rows + 4) : 2 * (size_t)(p.max_block_slots + 16));
+  a.off_bar = (int)off;
+  const size_t smem = off + 16;
   if (smem > 227 * 1024) return 4;
   if (which == 0) {
     auto k = heat_residual_gather<DIM, DEG, VAR>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<(unsigned)nblocks, 256, smem, s>>>(a);
+    k<<<(unsigned)p.nblocks, GATHER_THREADS, smem, s>>>(a);
   } else {
     auto k = heat_jacobian_gather<DIM, DEG, VAR>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<(unsigned)nblocks, 256, smem, s>>>(a);
+    k<<<(unsigned)p.nblocks, GATHER_THREADS, smem, s>>>(a);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
@@ -348,7 +392,7 @@ int fdts_launch_heat(fdts_engine *e, int which, const double *x, const double *x
     g.ncells_total = e->cfg.num_cells; g.cmax = p.cmax; g.shift = shift; g.p0 = e->cfg.params[0];
     int rc = 3;
 #define GCASE(D, K, V) \
-  if (dim == D && deg == K && (K < 3 || var == V)) rc = launch_gather<D, K, V>(which, g, p.nblocks, s);
+  if (dim == D && deg == K && (K < 3 || var == V)) rc = launch_gather<D, K, V>(which, g, p, s);
     GCASE(1, 1, 1) GCASE(1, 2, 1) GCASE(1, 3, 0) GCASE(1, 3, 1)
     GCASE(2, 1, 1) GCASE(2, 2, 1) GCASE(2, 3, 0) GCASE(2, 3, 1)
     GCASE(3, 1, 1) GCASE(3, 2, 1) GCASE(3, 3, 0) GCASE(3, 3, 1)

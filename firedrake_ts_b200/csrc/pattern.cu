@@ -191,7 +191,7 @@ int fdts_build_pattern(fdts_engine *e, cudaStream_t s) {
   FDTS_CHECK(cudaMalloc(&derr, sizeof(int)));
   FDTS_CHECK(cudaMemsetAsync(derr, 0, sizeof(int), s));
   if (nc * nd > 0) count_incidence<<<GRID(nc * nd, 256), 256, 0, s>>>(e->cell_node, nc, nd, nown, cnt);
-  FDTS_CHECK(cudaMalloc(&e->adj_ptr, sizeof(int64_t) * (nown + 1)));
+  FDTS_CHECK(cudaMalloc(&e->adj_ptr, sizeof(int64_t) * (nown + 4)));
   // exclusive scan int32 -> int64 (cnt has nown+1 entries, the last one zero)
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, WideIt(cnt, Widen()), e->adj_ptr, nown + 1, s);
   size_t tb2 = 0;

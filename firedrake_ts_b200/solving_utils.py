@@ -98,8 +98,12 @@ class _TSContext:
         if assembler == "b200":
             from .engine import Engine
 
-            self.engine = Engine(problem.F, self.bcs_F, device=dev if dev.type == "cuda" else None)
+            self.engine = Engine(problem.F, self.bcs_F, device=dev if dev.type == "cuda" else None,
+                                 scatter=self.appctx.get("scatter"))
             self._device = self.engine.device
+            # device-resident state: the Functions the callbacks update live on the engine's GPU
+            self._x.data = self._x.data.to(self._device)
+            self._xdot.data = self._xdot.data.to(self._device)
             rowptr, colidx = self.engine.csr()
             values = self.engine.new_values()
         else:

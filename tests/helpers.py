@@ -62,3 +62,31 @@ def rel_err(a, b):
     b = np.asarray(b, dtype=np.float64)
     scale = max(np.abs(b).max(), 1e-300)
     return np.abs(a - b).max() / scale
+
+
+class OracleAssembler:
+    """plugs the CPU oracle behind _TSContext's assembler interface (tests only): reference
+    trajectories are produced through the very same callbacks and time stepper."""
+
+    def __init__(self, form, bcs):
+        from oracle import Oracle
+
+        self.o = Oracle.from_form(form, bcs)
+        self.device = torch.device("cpu")
+
+    def pattern(self):
+        return self.o.pattern()
+
+    def ifunction(self, t, x, xdot, out=None):
+        F = torch.from_numpy(self.o.ifunction(t, x, xdot))
+        if out is not None:
+            out.copy_(F)
+            return out
+        return F
+
+    def ijacobian(self, t, x, xdot, shift, out=None):
+        J = torch.from_numpy(self.o.ijacobian(t, x, xdot, shift))
+        if out is not None:
+            out.copy_(J)
+            return out
+        return J
