@@ -316,6 +316,14 @@ extern "C" int fdts_set_option(fdts_handle e, const char *key, int64_t value) {
     e->opt_scatter = value;
     return 0;
   }
+  if (!strcmp(key, "gather_residual")) {
+    e->opt_gather_residual = value ? 1 : 0;
+    return 0;
+  }
+  if (!strcmp(key, "persist")) {
+    e->opt_persist = value ? 1 : 0;
+    return 0;
+  }
   fdts_set_error(std::string("unknown option ") + key);
   return 1;
 }

@@ -26,6 +26,18 @@ struct GatherPlan {
   int32_t max_block_rows = 0;
   int32_t max_block_adj = 0;
   int ne = 0, nep = 0, ndp = 0; // staged entries per cell (symmetric packing), odd-padded strides
+  // bulk-copyable phase-A inputs of the persistent kernel
+  int32_t vmax = 0;             // max coordinate nodes per block
+  double *bvcoords = nullptr;   // nblocks x vmax x dim coordinates of the block's vertices
+  uint32_t *bcc = nullptr;      // nblocks x cmax: (dim+1) block-local vertex ids, one byte each
+  struct BlockDesc *bdesc = nullptr;
+};
+
+struct BlockDesc {              // 32 bytes, one per row block
+  int64_t s0;                   // first node-level CSR slot of the block
+  int64_t cbase;                // first entry of the block in cidx
+  int32_t nslots, ncontrib;     // ncontrib padded to a multiple of 8
+  int32_t ncell, nvert;
 };
 
 struct fdts_engine {
@@ -54,6 +66,8 @@ struct fdts_engine {
   int32_t max_degree = 0;
   // options
   int64_t opt_scatter = 0;
+  int64_t opt_gather_residual = 0;  // gather path also for the residual (slower than atomics today)
+  int64_t opt_persist = 1;       // gather path: persistent pipelined Jacobian kernel
   GatherPlan plan;
   int variant = -1;              // which baked RefT table matches cfg.R (-1: none, closed-form path off)
   // scratch
@@ -97,13 +111,7 @@ struct Geom {
 };
 
 template <int DIM>
-__device__ __forceinline__ void compute_geometry(const double *__restrict__ coords,
-                                                 const int32_t *__restrict__ cc, Geom<DIM> &g) {
-  double X[DIM + 1][DIM];
-#pragma unroll
-  for (int v = 0; v <= DIM; ++v)
-#pragma unroll
-    for (int k = 0; k < DIM; ++k) X[v][k] = __ldg(coords + (int64_t)cc[v] * DIM + k);
+__device__ __forceinline__ void geometry_from_vertices(const double (&X)[DIM + 1][DIM], Geom<DIM> &g) {
   double J[DIM][DIM];
 #pragma unroll
   for (int k = 0; k < DIM; ++k)
@@ -137,6 +145,17 @@ __device__ __forceinline__ void compute_geometry(const double *__restrict__ coor
     g.Jinv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * r;
     g.adet = fabs(det);
   }
+}
+
+template <int DIM>
+__device__ __forceinline__ void compute_geometry(const double *__restrict__ coords,
+                                                 const int32_t *__restrict__ cc, Geom<DIM> &g) {
+  double X[DIM + 1][DIM];
+#pragma unroll
+  for (int v = 0; v <= DIM; ++v)
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) X[v][k] = __ldg(coords + (int64_t)cc[v] * DIM + k);
+  geometry_from_vertices<DIM>(X, g);
 }
 
 // ---- TMA 1-D bulk copy (global -> shared) completing on an mbarrier (SASS: UBLKCP / SYNCS)

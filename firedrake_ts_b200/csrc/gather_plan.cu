@@ -202,6 +202,100 @@ __global__ void block_extents(const int64_t *__restrict__ bstart, int64_t nb, co
   atomicMax((unsigned long long *)&out4[3], (unsigned long long)(adj_ptr[r1] - adj_ptr[r0]));
 }
 
+// one CTA per row block: block-local vertex table (coordinates copied) and per-cell local vertex ids
+template <bool WRITE>
+__global__ void __launch_bounds__(PLAN_THREADS) block_vertices(const int32_t *__restrict__ bcells,
+                                                               const int32_t *__restrict__ bcount, int cmax,
+                                                               const int32_t *__restrict__ cell_coord_t, int64_t nc,
+                                                               int dim, const double *__restrict__ coords, int kpad,
+                                                               int vmax, int32_t *__restrict__ vcount,
+                                                               double *__restrict__ bvcoords,
+                                                               uint32_t *__restrict__ bcc, int *__restrict__ err) {
+  extern __shared__ int32_t cand[];  // kpad candidates, then kpad unique
+  int32_t *uniq = cand + kpad;
+  __shared__ int warp_tot[PLAN_THREADS / 32];
+  const int64_t b = blockIdx.x;
+  const int ncell = bcount[b];
+  const int nv1 = dim + 1;
+  const int n = ncell * nv1;
+  for (int t = threadIdx.x; t < kpad; t += PLAN_THREADS) {
+    int32_t v = INT32_MAX;
+    if (t < n) {
+      const int k = t / nv1, a = t - k * nv1;
+      v = cell_coord_t[(int64_t)a * nc + bcells[b * cmax + k]];
+    }
+    cand[t] = v;
+  }
+  __syncthreads();
+  for (int kk = 2; kk <= kpad; kk <<= 1)
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < kpad; t += PLAN_THREADS) {
+        const int p = t ^ j;
+        if (p > t) {
+          const int32_t x = cand[t], y = cand[p];
+          const bool up = (t & kk) == 0;
+          if ((x > y) == up) {
+            cand[t] = y;
+            cand[p] = x;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  int base = 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t0 = 0; t0 < kpad; t0 += PLAN_THREADS) {
+    const int t = t0 + threadIdx.x;
+    const int32_t v = cand[t];
+    const bool first = v != INT32_MAX && (t == 0 || cand[t - 1] != v);
+    const unsigned m = __ballot_sync(0xffffffffu, first);
+    if (lane == 0) warp_tot[warp] = __popc(m);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    if (first) uniq[off + __popc(m & ((1u << lane) - 1u))] = v;
+    for (int w = 0; w < PLAN_THREADS / 32; ++w) base += warp_tot[w];
+    __syncthreads();
+  }
+  const int nv = base;
+  if (!WRITE) {
+    if (threadIdx.x == 0) vcount[b] = nv;
+    return;
+  }
+  if (nv > 255) {
+    if (threadIdx.x == 0) atomicExch(err, 6);
+    return;
+  }
+  for (int t = threadIdx.x; t < nv * dim; t += PLAN_THREADS) {
+    const int lv = t / dim, d = t - lv * dim;
+    bvcoords[((int64_t)b * vmax + lv) * dim + d] = coords[(int64_t)uniq[lv] * dim + d];
+  }
+  for (int k = threadIdx.x; k < ncell; k += PLAN_THREADS) {
+    uint32_t packed = 0;
+    for (int a = 0; a < nv1; ++a) {
+      const int32_t gv = cell_coord_t[(int64_t)a * nc + bcells[b * cmax + k]];
+      const int lv = find_cell(uniq, nv, gv);
+      packed |= (uint32_t)(lv & 255) << (8 * a);
+    }
+    bcc[b * (int64_t)((cmax + 3) & ~3) + k] = packed;
+  }
+}
+
+__global__ void block_descriptors(const int64_t *__restrict__ bstart, int64_t nb, const int64_t *__restrict__ nrp,
+                                  const int64_t *__restrict__ bbase, const int32_t *__restrict__ bcount,
+                                  const int32_t *__restrict__ vcount, BlockDesc *__restrict__ d) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  BlockDesc x;
+  x.s0 = nrp[bstart[b]];
+  x.cbase = bbase[b];
+  x.nslots = (int32_t)(nrp[bstart[b + 1]] - x.s0);
+  x.ncontrib = (int32_t)(bbase[b + 1] - bbase[b]);
+  x.ncell = bcount[b];
+  x.nvert = vcount[b];
+  d[b] = x;
+}
+
 struct Widen8 {
   __host__ __device__ int64_t operator()(uint8_t v) const { return (int64_t)v; }
 };
@@ -212,7 +306,7 @@ struct Widen8 {
 
 void fdts_free_plan(fdts_engine *e) {
   GatherPlan &p = e->plan;
-  void *ptrs[] = {p.bstart, p.bcells, p.bcount, p.bbase, p.cend, p.cidx, p.ridx};
+  void *ptrs[] = {p.bstart, p.bcells, p.bcount, p.bbase, p.cend, p.cidx, p.ridx, p.bvcoords, p.bcc, p.bdesc};
   for (void *q : ptrs)
     if (q) cudaFree(q);
   p = GatherPlan();
@@ -347,6 +441,52 @@ int fdts_build_plan(fdts_engine *e, const int64_t *starts, int64_t nb) {
                                                       p.bcount, cmax, p.cidx, derr);
     row_contributions<1><<<(unsigned)nb, 128, 0, s>>>(p.bstart, e->adj_ptr, e->adj_cell, e->isbc, p.ndp, p.bcells,
                                                      p.bcount, cmax, p.ridx, derr);
+    {  // bulk-copyable phase-A inputs: block vertex tables, local vertex ids, descriptors
+      const int dim = e->cfg.dim;
+      int kpv = PLAN_THREADS;
+      while (kpv < cmax * (dim + 1)) kpv <<= 1;
+      const size_t smv = sizeof(int32_t) * 2 * (size_t)kpv;
+      if (smv > 48 * 1024) {
+        cudaFuncSetAttribute(block_vertices<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smv);
+        cudaFuncSetAttribute(block_vertices<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smv);
+      }
+      int32_t *vcount = nullptr, *vm = nullptr;
+      if (cudaMalloc(&vcount, sizeof(int32_t) * nb) != cudaSuccess || cudaMalloc(&vm, sizeof(int32_t) * 2) != cudaSuccess) {
+        rc = 2;
+        cudaFree(cnt8);
+        break;
+      }
+      block_vertices<false><<<(unsigned)nb, PLAN_THREADS, smv, s>>>(p.bcells, p.bcount, cmax, e->cell_coord, nc, dim,
+                                                                  e->coords, kpv, 0, vcount, nullptr, nullptr, derr);
+      size_t tb4 = 0;
+      cub::DeviceReduce::Max(nullptr, tb4, vcount, vm, nb, s);
+      void *tmp4 = nullptr;
+      cudaMalloc(&tmp4, tb4 + 16);
+      cub::DeviceReduce::Max(tmp4, tb4, vcount, vm, nb, s);
+      int32_t vmax = 0;
+      cudaMemcpyAsync(&vmax, vm, sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+      cudaStreamSynchronize(s);
+      cudaFree(tmp4);
+      cudaFree(vm);
+      vmax = (vmax + 1) & ~1;  // keep vmax*dim*8 a multiple of 16 bytes
+      p.vmax = vmax;
+      if (vmax > 254 || cudaMalloc(&p.bvcoords, sizeof(double) * (size_t)nb * vmax * dim + 64) != cudaSuccess ||
+          cudaMalloc(&p.bcc, sizeof(uint32_t) * ((size_t)nb * ((cmax + 3) & ~3) + 16)) != cudaSuccess ||
+          cudaMalloc(&p.bdesc, sizeof(BlockDesc) * (size_t)(nb + 4)) != cudaSuccess) {
+        fdts_set_error("gather plan: block vertex tables do not fit");
+        rc = 2;
+        cudaFree(vcount);
+        cudaFree(cnt8);
+        break;
+      }
+      cudaMemsetAsync(p.bvcoords, 0, sizeof(double) * (size_t)nb * vmax * dim + 64, s);
+      cudaMemsetAsync(p.bdesc, 0, sizeof(BlockDesc) * (size_t)(nb + 4), s);
+      block_vertices<true><<<(unsigned)nb, PLAN_THREADS, smv, s>>>(p.bcells, p.bcount, cmax, e->cell_coord, nc, dim,
+                                                                 e->coords, kpv, vmax, nullptr, p.bvcoords, p.bcc, derr);
+      block_descriptors<<<GRID(nb, 256), 256, 0, s>>>(p.bstart, nb, e->nrowptr, p.bbase, p.bcount, vcount, p.bdesc);
+      cudaStreamSynchronize(s);
+      cudaFree(vcount);
+    }
     int herr = 0;
     cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, s);
     cudaError_t ce = cudaStreamSynchronize(s);

@@ -164,7 +164,12 @@ struct GArgs {
   const uint16_t *cend, *cidx, *ridx;
   int64_t ncells_total;
   int32_t cmax;
-  int32_t off_idx, off_end, off_bar;  // shared-memory layout (bytes)
+  int32_t off_idx, off_end, off_bar, off_inA, inA_bytes;  // shared-memory layout (bytes)
+  int32_t vmax, persist;
+  int64_t nblocks;
+  const double *bvcoords;
+  const uint32_t *bcc;
+  const BlockDesc *bdesc;
   double shift, p0;
 };
 
@@ -226,6 +231,104 @@ __global__ void __launch_bounds__(GATHER_THREADS) heat_jacobian_gather(const GAr
     double acc = 0.0;
     for (int k = beg; k < end; ++k) acc += stage[sidx[k]];
     a.out[s] = acc;
+  }
+}
+
+// Persistent, software-pipelined form of the Jacobian gather (one CTA per SM, loops over row
+// blocks).  Every input of a block arrives through TMA bulk copies launched one step ahead:
+//   barA[s]  : the block-local vertex coordinates + per-cell local vertex ids (phase-A inputs,
+//              double buffered, fetched during the previous block's work);
+//   barIdx   : the block's contribution addresses + segment ends (phase-B inputs, fetched while
+//              phase A computes).
+// so neither phase waits on a dependent global load.
+template <int DIM, int DEG, int VAR>
+__global__ void __launch_bounds__(GATHER_THREADS, 1) heat_jacobian_gather_persist(const GArgs a) {
+  using T = RefT<DIM, DEG, VAR>;
+  constexpr int ND = T::ND, NP = T::NP, NEP = (ND * (ND + 1) / 2) | 1;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double *stage = reinterpret_cast<double *>(smraw);
+  uint16_t *sidx = reinterpret_cast<uint16_t *>(smraw + a.off_idx);
+  uint16_t *send = reinterpret_cast<uint16_t *>(smraw + a.off_end);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smraw + a.off_bar);  // [0] idx, [1..2] phase-A inputs
+  unsigned char *inA[2] = {smraw + a.off_inA, smraw + a.off_inA + a.inA_bytes};
+  const uint32_t vbytes = (uint32_t)a.vmax * DIM * 8u;  // multiple of 16
+  const uint32_t cbytes = (uint32_t)((a.cmax * 4 + 15) & ~15);
+
+  auto issue_inA = [&](int64_t b, int slot) {
+    mbar_expect_tx(&bars[1 + slot], vbytes + cbytes);
+    bulk_g2s(inA[slot], a.bvcoords + b * a.vmax * DIM, vbytes, &bars[1 + slot]);
+    bulk_g2s(inA[slot] + vbytes, a.bcc + b * (int64_t)((a.cmax + 3) & ~3), cbytes, &bars[1 + slot]);
+  };
+
+  const int64_t stride = gridDim.x;
+  int64_t b = blockIdx.x;
+  if (b >= a.nblocks) return;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    issue_inA(b, 0);
+  }
+  BlockDesc d = a.bdesc[b];
+  BlockDesc dn = a.bdesc[b + stride < a.nblocks ? b + stride : b];
+  __syncthreads();
+  for (int it = 0; b < a.nblocks; ++it, b += stride) {
+    const int slot = it & 1;
+    const int64_t bn = b + stride;
+    const int64_t s0a = d.s0 & ~7ll;
+    if (threadIdx.x == 0) {
+      const uint32_t nb_idx = (uint32_t)d.ncontrib * 2u;
+      const uint32_t nb_end = (uint32_t)(((d.s0 + d.nslots + 7) & ~7ll) - s0a) * 2u;
+      mbar_expect_tx(&bars[0], nb_idx + nb_end);
+      if (nb_idx) bulk_g2s(sidx, a.cidx + d.cbase, nb_idx, &bars[0]);
+      if (nb_end) bulk_g2s(send, a.cend + s0a, nb_end, &bars[0]);
+      if (bn < a.nblocks) issue_inA(bn, slot ^ 1);
+    }
+    // descriptor of the block after next (consumed two iterations from now)
+    const int64_t bnn = bn + stride;
+    BlockDesc dnn = a.bdesc[bnn < a.nblocks ? bnn : b];
+    // ---- phase A
+    mbar_wait(&bars[1 + slot], (uint32_t)((it >> 1) & 1));
+    const double *vtab = reinterpret_cast<const double *>(inA[slot]);
+    const uint32_t *lcc = reinterpret_cast<const uint32_t *>(inA[slot] + vbytes);
+    for (int k = threadIdx.x; k < d.ncell; k += GATHER_THREADS) {
+      const uint32_t packed = lcc[k];
+      double X[DIM + 1][DIM];
+#pragma unroll
+      for (int v = 0; v <= DIM; ++v) {
+        const int lv = (packed >> (8 * v)) & 255;
+#pragma unroll
+        for (int q = 0; q < DIM; ++q) X[v][q] = vtab[lv * DIM + q];
+      }
+      Geom<DIM> g;
+      geometry_from_vertices<DIM>(X, g);
+      double gm[NP];
+      metric<DIM>(g, gm);
+      const double m = a.shift * g.adet;
+      double *st = stage + k * NEP;
+      static_for<ND>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        static_for<ND - i>([&](auto JJ) {
+          constexpr int j = i + decltype(JJ)::value;
+          constexpr int e = i * ND - (i * (i - 1)) / 2 + (j - i);
+          st[e] = heat_entry<T, i, j, NP>(m, gm);
+        });
+      });
+    }
+    __syncthreads();
+    // ---- phase B
+    mbar_wait(&bars[0], (uint32_t)(it & 1));
+    const int64_t s1 = d.s0 + d.nslots;
+    for (int64_t s = d.s0 + threadIdx.x; s < s1; s += GATHER_THREADS) {
+      const int beg = s == d.s0 ? 0 : send[s - 1 - s0a];
+      const int end = send[s - s0a];
+      double acc = 0.0;
+      for (int k = beg; k < end; ++k) acc += stage[sidx[k]];
+      a.out[s] = acc;
+    }
+    __syncthreads();
+    d = dn;
+    dn = dnn;
   }
 }
 
@@ -316,8 +419,24 @@ int launch_gather(int which, GArgs a, const GatherPlan &p, cudaStream_t s) {
   a.off_end = (int)off;
   off += up16(which == 0 ? 8 * (size_t)(p.max_block_rows + 4) : 2 * (size_t)(p.max_block_slots + 16));
   a.off_bar = (int)off;
+  off += 32;
+  if (which == 1 && a.persist) {
+    a.inA_bytes = (int)(up16((size_t)p.vmax * DIM * 8) + up16((size_t)p.cmax * 4));
+    a.off_inA = (int)off;
+    off += 2 * (size_t)a.inA_bytes;
+  }
   const size_t smem = off + 16;
   if (smem > 227 * 1024) return 4;
+  if (which == 1 && a.persist) {
+    auto k = heat_jacobian_gather_persist<DIM, DEG, VAR>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t grid = p.nblocks < sms ? p.nblocks : sms;
+    k<<<(unsigned)grid, GATHER_THREADS, smem, s>>>(a);
+    return cudaGetLastError() == cudaSuccess ? 0 : 2;
+  }
   if (which == 0) {
     auto k = heat_residual_gather<DIM, DEG, VAR>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -378,7 +497,7 @@ int fdts_launch_heat(fdts_engine *e, int which, const double *x, const double *x
   }
   KArgs a = fdts_make_kargs(e, x, xdot, shift, out, c0, c1);
   const int dim = e->cfg.dim, deg = e->cfg.degree, var = e->variant;
-  if (e->opt_scatter == 2) {
+  if (e->opt_scatter == 2 && (which == 1 || e->opt_gather_residual)) {
     if (!e->plan.ready) {
       fdts_set_error("gather path requested but no gather plan is built (fdts_set_row_blocks)");
       return 3;
@@ -390,6 +509,8 @@ int fdts_launch_heat(fdts_engine *e, int which, const double *x, const double *x
     g.nrowptr = e->nrowptr; g.adj_ptr = e->adj_ptr; g.bstart = p.bstart; g.bbase = p.bbase;
     g.bcells = p.bcells; g.bcount = p.bcount; g.cend = p.cend; g.cidx = p.cidx; g.ridx = p.ridx;
     g.ncells_total = e->cfg.num_cells; g.cmax = p.cmax; g.shift = shift; g.p0 = e->cfg.params[0];
+    g.vmax = p.vmax; g.nblocks = p.nblocks; g.bvcoords = p.bvcoords; g.bcc = p.bcc; g.bdesc = p.bdesc;
+    g.persist = e->opt_persist ? 1 : 0; g.off_inA = 0; g.inA_bytes = 0;
     int rc = 3;
 #define GCASE(D, K, V) \
   if (dim == D && deg == K && (K < 3 || var == V)) rc = launch_gather<D, K, V>(which, g, p, s);

@@ -47,6 +47,7 @@ def test_engine_matches_oracle(family, dim, degree, n, tile):
             if starts is None:
                 starts = torch.unique(torch.arange(0, eng.num_rows + 50, 50).clamp(max=eng.num_rows))
             eng.set_row_blocks(starts)
+            eng.set_option("gather_residual", 1)
         eng.set_option("scatter", path)
         F = eng.ifunction(0.0, x, xd).cpu().numpy()
         assert rel_err(F, Fo) < TOL, (path, rel_err(F, Fo))
@@ -55,7 +56,7 @@ def test_engine_matches_oracle(family, dim, degree, n, tile):
     assert eng.launch_count > 0
 
 
-@pytest.mark.parametrize("dim,degree,n,ftile,foffset", [(3, 2, 6, 5, 1), (3, 2, 5, 7, 1), (2, 2, 9, 5, 1), (3, 1, 7, 3, 1),
+@pytest.mark.parametrize("dim,degree,n,ftile,foffset", [(3, 2, 6, 5, 1), (3, 2, 5, 6, 0), (2, 2, 9, 5, 1), (3, 1, 7, 3, 1),
                                                         (3, 3, 3, 4, 1), (2, 3, 5, 7, 2), (1, 2, 20, 5, 1)])
 def test_gather_path_tiled_numbering(dim, degree, n, ftile, foffset):
     """owner-computes gather (write-once, deterministic) on tile-numbered spaces with offset tiles;
@@ -66,11 +67,15 @@ def test_gather_path_tiled_numbering(dim, degree, n, ftile, foffset):
     form, bcs, u, udot = make_problem("heat", dim, degree, n, tile=2, ftile=ftile, foffset=foffset)
     orc = Oracle.from_form(form, bcs)
     eng = Engine(form, bcs, device="cuda:0", scatter=2)
+    eng.set_option("gather_residual", 1)
     assert eng.get_option("scatter") == 2 and eng.get_option("plan_blocks") > 0
     x, xd = u.data.cuda(), udot.data.cuda()
     J1 = eng.ijacobian(0.0, x, xd, 7.5)
     J2 = eng.ijacobian(0.0, x, xd, 7.5)
     assert torch.equal(J1, J2)
+    eng.set_option("persist", 0)  # one CTA per row block instead of the persistent pipelined kernel
+    assert torch.equal(J1, eng.ijacobian(0.0, x, xd, 7.5))
+    eng.set_option("persist", 1)
     F1 = eng.ifunction(0.0, x, xd)
     F2 = eng.ifunction(0.0, x, xd)
     assert torch.equal(F1, F2)
