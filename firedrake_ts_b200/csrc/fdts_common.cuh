@@ -17,7 +17,9 @@ struct GatherPlan {
   int32_t *bcells = nullptr;    // nblocks x cmax sorted cell ids
   int32_t *bcount = nullptr;    // cells per block
   int64_t *bbase = nullptr;     // nblocks+1 offsets into cidx
-  uint16_t *cend = nullptr;     // per node-level slot: inclusive end of its contribution segment (block relative)
+  uint16_t *sdst = nullptr;     // per slot position in SELL order: destination offset inside its 2048-slot window
+  uint32_t *soff = nullptr;     // per slice: offset of its first entry in the block's cidx segment (+ end marker)
+  int64_t *slbase = nullptr;    // nblocks+1 offsets into soff (padded to 4 entries)
   uint16_t *cidx = nullptr;     // staged element-matrix addresses
   uint16_t *ridx = nullptr;     // per adjacency entry: staged element-vector address
   int64_t total_contrib = 0;
@@ -25,6 +27,8 @@ struct GatherPlan {
   int32_t max_block_slots = 0;
   int32_t max_block_rows = 0;
   int32_t max_block_adj = 0;
+  int32_t max_block_slices = 0;   // padded slice-offset entries per block
+  int32_t zaddr = 0;              // staged address holding 0.0
   int ne = 0, nep = 0, ndp = 0; // staged entries per cell (symmetric packing), odd-padded strides
   // bulk-copyable phase-A inputs of the persistent kernel
   int32_t vmax = 0;             // max coordinate nodes per block
@@ -33,11 +37,13 @@ struct GatherPlan {
   struct BlockDesc *bdesc = nullptr;
 };
 
-struct BlockDesc {              // 32 bytes, one per row block
+struct BlockDesc {              // 48 bytes, one per row block
   int64_t s0;                   // first node-level CSR slot of the block
   int64_t cbase;                // first entry of the block in cidx
-  int32_t nslots, ncontrib;     // ncontrib padded to a multiple of 8
+  int64_t slbase;               // first entry of the block in soff
+  int32_t nslots, ncontrib;     // ncontrib: padded SELL entries (multiple of 32)
   int32_t ncell, nvert;
+  int32_t nslpad, pad;          // slice-offset entries incl. end marker, padded to 4
 };
 
 struct fdts_engine {

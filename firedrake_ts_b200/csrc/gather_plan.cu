@@ -8,7 +8,11 @@
 //     the exec-halo of the MPI decomposition, only at CTA scale);
 //   * for every CSR slot of the block, the list of staged element-matrix entries
 //     that sum to it, as 16-bit shared-memory addresses in ascending cell order
-//     (fixed order => bitwise reproducible sums);
+//     (fixed order => bitwise reproducible sums), stored SELL-32-sigma style: inside
+//     windows of 2048 slots the slots are sorted by contribution count, cut into
+//     slices of 32, and each slice stores its addresses column-major, padded to the
+//     slice's longest list with the address of a staged zero -- so the summation
+//     loop of a warp is divergence-free and its index loads are coalesced;
 //   * for every row, the list of staged element-vector entries (residual).
 // Dirichlet rows/columns get empty lists (PyOP2's negative-lgmap "drop").
 // All of it is integer work on the GPU, derived from the cell->node map, the
@@ -101,13 +105,12 @@ __global__ void slot_contributions(const int64_t *__restrict__ bstart, const int
                                    const int32_t *__restrict__ adj_cell, const int32_t *__restrict__ cell_node_t,
                                    int64_t nc, int nd, int nep, const uint8_t *__restrict__ pos8_t,
                                    const uint8_t *__restrict__ isbc, const int64_t *__restrict__ nrp,
-                                   uint8_t *__restrict__ cnt8, const uint16_t *__restrict__ cend,
+                                   uint8_t *__restrict__ cnt8, const uint32_t *__restrict__ sellpos,
                                    const int64_t *__restrict__ bbase, const int32_t *__restrict__ bcells,
                                    const int32_t *__restrict__ bcount, int cmax, uint16_t *__restrict__ cidx,
                                    int *__restrict__ err) {
   const int64_t b = blockIdx.x;
   const int64_t r0 = bstart[b], r1 = bstart[b + 1];
-  const int64_t s0 = nrp[r0];
   for (int64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
     if (isbc[r]) continue;
     const int64_t rb = nrp[r];
@@ -131,40 +134,91 @@ __global__ void slot_contributions(const int64_t *__restrict__ bstart, const int
           cnt8[slot]++;
         } else {
           const int k = cnt8[slot]++;
-          const int64_t beg = slot == s0 ? 0 : cend[slot - 1];
-          cidx[bbase[b] + beg + k] = (uint16_t)(cs * nep + sym_index(i, j, nd));
+          cidx[bbase[b] + sellpos[slot] + (int64_t)k * 32] = (uint16_t)(cs * nep + sym_index(i, j, nd));
         }
       }
     }
   }
 }
 
-// per block inclusive scan of the slot counts -> 16-bit segment ends, block totals
-__global__ void __launch_bounds__(PLAN_THREADS) block_scan_counts(const int64_t *__restrict__ bstart,
-                                                                  const int64_t *__restrict__ nrp,
-                                                                  const uint8_t *__restrict__ cnt8,
-                                                                  uint16_t *__restrict__ cend,
-                                                                  int64_t *__restrict__ btotal,
-                                                                  int *__restrict__ err) {
-  using Scan = cub::BlockScan<int, PLAN_THREADS>;
-  __shared__ typename Scan::TempStorage tmp;
+constexpr int SELL_WINDOW = 2048;
+
+__global__ void block_slices(const int64_t *__restrict__ bstart, int64_t nb, const int64_t *__restrict__ nrp,
+                             int64_t *__restrict__ nsl_padded) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const int64_t n = nrp[bstart[b + 1]] - nrp[bstart[b]];
+  const int64_t full = n / SELL_WINDOW, rem = n - full * SELL_WINDOW;
+  const int64_t nsl = full * (SELL_WINDOW / 32) + (rem + 31) / 32;
+  nsl_padded[b] = (nsl + 1 + 3) & ~3ll;  // +1 end marker, 16-byte granules
+}
+
+// one CTA per row block: SELL-32-sigma layout of its slots (sigma = SELL_WINDOW)
+__global__ void __launch_bounds__(PLAN_THREADS) sell_layout(const int64_t *__restrict__ bstart,
+                                                            const int64_t *__restrict__ nrp,
+                                                            const uint8_t *__restrict__ cnt8,
+                                                            const int64_t *__restrict__ slbase,
+                                                            uint16_t *__restrict__ sdst, uint32_t *__restrict__ soff,
+                                                            uint32_t *__restrict__ sellpos,
+                                                            int64_t *__restrict__ btotal) {
+  __shared__ uint32_t keys[SELL_WINDOW];
+  __shared__ uint32_t woff[SELL_WINDOW / 32 + 1];
+  __shared__ uint32_t running_s;
   const int64_t b = blockIdx.x;
   const int64_t s0 = nrp[bstart[b]], s1 = nrp[bstart[b + 1]];
-  int running = 0;
-  for (int64_t base = s0; base < s1; base += PLAN_THREADS) {
-    const int64_t s = base + threadIdx.x;
-    const int v = s < s1 ? cnt8[s] : 0;
-    int incl, total;
-    Scan(tmp).InclusiveSum(v, incl, total);
-    if (s < s1) {
-      const int e = running + incl;
-      if (e > 65535) atomicExch(err, 4);
-      cend[s] = (uint16_t)e;
+  const int64_t nslots = s1 - s0;
+  uint32_t *boff = soff + slbase[b];
+  if (threadIdx.x == 0) running_s = 0;
+  int64_t slice0 = 0;
+  for (int64_t wb = 0; wb < nslots; wb += SELL_WINDOW) {
+    const int nw = (int)((nslots - wb) < SELL_WINDOW ? (nslots - wb) : SELL_WINDOW);
+    for (int t = threadIdx.x; t < SELL_WINDOW; t += PLAN_THREADS)
+      keys[t] = t < nw ? (((uint32_t)(255 - cnt8[s0 + wb + t]) << 16) | (uint32_t)t) : 0xFFFFFFFFu;
+    __syncthreads();
+    for (int kk = 2; kk <= SELL_WINDOW; kk <<= 1)
+      for (int j = kk >> 1; j > 0; j >>= 1) {
+        for (int t = threadIdx.x; t < SELL_WINDOW; t += PLAN_THREADS) {
+          const int q = t ^ j;
+          if (q > t) {
+            const uint32_t x = keys[t], y = keys[q];
+            const bool up = (t & kk) == 0;
+            if ((x > y) == up) {
+              keys[t] = y;
+              keys[q] = x;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    const int nsl = (nw + 31) / 32;
+    if (threadIdx.x == 0) {
+      uint32_t run = running_s;
+      for (int j = 0; j < nsl; ++j) {
+        woff[j] = run;
+        run += 32u * (255u - (keys[32 * j] >> 16));
+      }
+      woff[nsl] = run;
+      running_s = run;
     }
-    running += total;
+    __syncthreads();
+    for (int j = threadIdx.x; j < nsl; j += PLAN_THREADS) boff[slice0 + j] = woff[j];
+    for (int q = threadIdx.x; q < nw; q += PLAN_THREADS) {
+      const uint32_t t = keys[q] & 0xFFFFu;
+      sdst[s0 + wb + q] = (uint16_t)t;
+      sellpos[s0 + wb + t] = woff[q >> 5] + (uint32_t)(q & 31);
+    }
+    slice0 += nsl;
     __syncthreads();
   }
-  if (threadIdx.x == 0) btotal[b] = (running + 7) & ~7;  // 16-byte granules for the bulk copies
+  if (threadIdx.x == 0) {
+    boff[slice0] = running_s;
+    btotal[b] = running_s;  // a multiple of 32 entries = 64 bytes
+  }
+}
+
+__global__ void fill_u16(uint16_t *__restrict__ p, int64_t n, uint16_t v) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) p[t] = v;
 }
 
 // residual lists: per row the staged element-vector entries, cell ascending
@@ -191,8 +245,8 @@ __global__ void row_contributions(const int64_t *__restrict__ bstart, const int6
 
 __global__ void block_extents(const int64_t *__restrict__ bstart, int64_t nb, const int64_t *__restrict__ nrp,
                               const int64_t *__restrict__ adj_ptr, const int64_t *__restrict__ bbase,
-                              int64_t *__restrict__ out4) {
-  // out4: max contributions, max slots, max rows, max adjacency entries per block
+                              const int64_t *__restrict__ slbase, int64_t *__restrict__ out4) {
+  // out4: max contributions, max slots, max rows, max adjacency entries, max padded slice entries per block
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   const int64_t r0 = bstart[b], r1 = bstart[b + 1];
@@ -200,6 +254,7 @@ __global__ void block_extents(const int64_t *__restrict__ bstart, int64_t nb, co
   atomicMax((unsigned long long *)&out4[1], (unsigned long long)(nrp[r1] - nrp[r0]));
   atomicMax((unsigned long long *)&out4[2], (unsigned long long)(r1 - r0));
   atomicMax((unsigned long long *)&out4[3], (unsigned long long)(adj_ptr[r1] - adj_ptr[r0]));
+  atomicMax((unsigned long long *)&out4[4], (unsigned long long)(slbase[b + 1] - slbase[b]));
 }
 
 // one CTA per row block: block-local vertex table (coordinates copied) and per-cell local vertex ids
@@ -282,8 +337,9 @@ __global__ void __launch_bounds__(PLAN_THREADS) block_vertices(const int32_t *__
 }
 
 __global__ void block_descriptors(const int64_t *__restrict__ bstart, int64_t nb, const int64_t *__restrict__ nrp,
-                                  const int64_t *__restrict__ bbase, const int32_t *__restrict__ bcount,
-                                  const int32_t *__restrict__ vcount, BlockDesc *__restrict__ d) {
+                                  const int64_t *__restrict__ bbase, const int64_t *__restrict__ slbase,
+                                  const int32_t *__restrict__ bcount, const int32_t *__restrict__ vcount,
+                                  BlockDesc *__restrict__ d) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   BlockDesc x;
@@ -293,8 +349,13 @@ __global__ void block_descriptors(const int64_t *__restrict__ bstart, int64_t nb
   x.ncontrib = (int32_t)(bbase[b + 1] - bbase[b]);
   x.ncell = bcount[b];
   x.nvert = vcount[b];
+  x.slbase = slbase[b];
+  x.nslpad = (int32_t)(slbase[b + 1] - slbase[b]);
+  x.pad = 0;
   d[b] = x;
 }
+
+static inline bool hext_overflow(int32_t v) { return v < 0; }
 
 struct Widen8 {
   __host__ __device__ int64_t operator()(uint8_t v) const { return (int64_t)v; }
@@ -306,7 +367,7 @@ struct Widen8 {
 
 void fdts_free_plan(fdts_engine *e) {
   GatherPlan &p = e->plan;
-  void *ptrs[] = {p.bstart, p.bcells, p.bcount, p.bbase, p.cend, p.cidx, p.ridx, p.bvcoords, p.bcc, p.bdesc};
+  void *ptrs[] = {p.bstart, p.bcells, p.bcount, p.bbase, p.sdst, p.soff, p.slbase, p.cidx, p.ridx, p.bvcoords, p.bcc, p.bdesc};
   for (void *q : ptrs)
     if (q) cudaFree(q);
   p = GatherPlan();
@@ -395,52 +456,84 @@ int fdts_build_plan(fdts_engine *e, const int64_t *starts, int64_t nb) {
     }
     block_cells<true><<<(unsigned)nb, PLAN_THREADS, sm, s>>>(p.bstart, e->adj_ptr, e->adj_cell, kpad, cmax, nullptr,
                                                            p.bcells);
-    // slot contribution counts -> segment ends
+    // slot contribution counts -> SELL layout
     uint8_t *cnt8 = nullptr;
+    uint32_t *sellpos = nullptr;
     const int64_t nnz = e->node_nnz;
-    if (cudaMalloc(&cnt8, (size_t)nnz + 1) != cudaSuccess || cudaMalloc(&p.cend, sizeof(uint16_t) * (nnz + 32)) != cudaSuccess ||
-        cudaMalloc(&p.bbase, sizeof(int64_t) * (nb + 1)) != cudaSuccess) {
+    if (cudaMalloc(&cnt8, (size_t)nnz + 1) != cudaSuccess || cudaMalloc(&p.sdst, sizeof(uint16_t) * (nnz + 32)) != cudaSuccess ||
+        cudaMalloc(&sellpos, sizeof(uint32_t) * (nnz + 1)) != cudaSuccess ||
+        cudaMalloc(&p.bbase, sizeof(int64_t) * (nb + 1)) != cudaSuccess ||
+        cudaMalloc(&p.slbase, sizeof(int64_t) * (nb + 1)) != cudaSuccess) {
       fdts_set_error("gather plan: out of memory (slot tables)");
       rc = 2;
       break;
     }
     cudaMemsetAsync(cnt8, 0, (size_t)nnz + 1, s);
+    cudaMemsetAsync(p.sdst, 0, sizeof(uint16_t) * (nnz + 32), s);
     slot_contributions<0><<<(unsigned)nb, 128, 0, s>>>(p.bstart, e->adj_ptr, e->adj_cell, e->cell_node, nc, nd, p.nep,
                                                       e->pos8, e->isbc, e->nrowptr, cnt8, nullptr, nullptr, nullptr,
                                                       nullptr, cmax, nullptr, derr);
     cudaMemsetAsync(btotal, 0, sizeof(int64_t) * (nb + 1), s);
-    block_scan_counts<<<(unsigned)nb, PLAN_THREADS, 0, s>>>(p.bstart, e->nrowptr, cnt8, p.cend, btotal, derr);
+    block_slices<<<GRID(nb, 256), 256, 0, s>>>(p.bstart, nb, e->nrowptr, btotal);
+    cub::DeviceScan::ExclusiveSum(tmp, tb, btotal, p.slbase, nb + 1, s);
+    int64_t total_slices = 0;
+    cudaMemcpyAsync(&total_slices, p.slbase + nb, sizeof(int64_t), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    if (cudaMalloc(&p.soff, sizeof(uint32_t) * (size_t)(total_slices + 16)) != cudaSuccess) {
+      fdts_set_error("gather plan: out of memory (slice offsets)");
+      rc = 2;
+      cudaFree(cnt8);
+      cudaFree(sellpos);
+      break;
+    }
+    cudaMemsetAsync(p.soff, 0, sizeof(uint32_t) * (size_t)(total_slices + 16), s);
+    cudaMemsetAsync(btotal, 0, sizeof(int64_t) * (nb + 1), s);
+    sell_layout<<<(unsigned)nb, PLAN_THREADS, 0, s>>>(p.bstart, e->nrowptr, cnt8, p.slbase, p.sdst, p.soff, sellpos,
+                                                    btotal);
     cub::DeviceScan::ExclusiveSum(tmp, tb, btotal, p.bbase, nb + 1, s);
     int64_t total = 0;
     cudaMemcpyAsync(&total, p.bbase + nb, sizeof(int64_t), cudaMemcpyDeviceToHost, s);
     cudaStreamSynchronize(s);
     p.total_contrib = total;
     {
-      int64_t *ext = nullptr, hext[4] = {0, 0, 0, 0};
-      if (cudaMalloc(&ext, sizeof(int64_t) * 4) != cudaSuccess) { rc = 2; break; }
-      cudaMemsetAsync(ext, 0, sizeof(int64_t) * 4, s);
-      block_extents<<<GRID(nb, 256), 256, 0, s>>>(p.bstart, nb, e->nrowptr, e->adj_ptr, p.bbase, ext);
-      cudaMemcpyAsync(hext, ext, sizeof(int64_t) * 4, cudaMemcpyDeviceToHost, s);
+      int64_t *ext = nullptr, hext[5] = {0, 0, 0, 0, 0};
+      if (cudaMalloc(&ext, sizeof(int64_t) * 5) != cudaSuccess) { rc = 2; break; }
+      cudaMemsetAsync(ext, 0, sizeof(int64_t) * 5, s);
+      block_extents<<<GRID(nb, 256), 256, 0, s>>>(p.bstart, nb, e->nrowptr, e->adj_ptr, p.bbase, p.slbase, ext);
+      cudaMemcpyAsync(hext, ext, sizeof(int64_t) * 5, cudaMemcpyDeviceToHost, s);
       cudaStreamSynchronize(s);
       cudaFree(ext);
       p.max_block_contrib = (int32_t)hext[0];
       p.max_block_slots = (int32_t)hext[1];
       p.max_block_rows = (int32_t)hext[2];
       p.max_block_adj = (int32_t)hext[3];
+      p.max_block_slices = (int32_t)hext[4];
     }
-    if (cudaMalloc(&p.cidx, sizeof(uint16_t) * (size_t)(total + 32)) != cudaSuccess ||
+    p.zaddr = cmax * p.nep;  // staged zero that padded SELL entries point at
+    if (p.zaddr > 65535 || hext_overflow(p.max_block_contrib)) {
+      fdts_set_error("gather plan: a row block exceeds the 16-bit staging address space");
+      rc = 4;
+      cudaFree(cnt8);
+      cudaFree(sellpos);
+      break;
+    }
+    if (cudaMalloc(&p.cidx, sizeof(uint16_t) * (size_t)(total + 64)) != cudaSuccess ||
         cudaMalloc(&p.ridx, sizeof(uint16_t) * (size_t)(nc * nd + 32)) != cudaSuccess) {
       fdts_set_error("gather plan: out of memory (contribution lists)");
       rc = 2;
       cudaFree(cnt8);
+      cudaFree(sellpos);
       break;
     }
+    fill_u16<<<GRID(total + 64, 256), 256, 0, s>>>(p.cidx, total + 64, (uint16_t)p.zaddr);
     cudaMemsetAsync(cnt8, 0, (size_t)nnz + 1, s);
     slot_contributions<1><<<(unsigned)nb, 128, 0, s>>>(p.bstart, e->adj_ptr, e->adj_cell, e->cell_node, nc, nd, p.nep,
-                                                      e->pos8, e->isbc, e->nrowptr, cnt8, p.cend, p.bbase, p.bcells,
+                                                      e->pos8, e->isbc, e->nrowptr, cnt8, sellpos, p.bbase, p.bcells,
                                                       p.bcount, cmax, p.cidx, derr);
     row_contributions<1><<<(unsigned)nb, 128, 0, s>>>(p.bstart, e->adj_ptr, e->adj_cell, e->isbc, p.ndp, p.bcells,
                                                      p.bcount, cmax, p.ridx, derr);
+    cudaStreamSynchronize(s);
+    cudaFree(sellpos);
     {  // bulk-copyable phase-A inputs: block vertex tables, local vertex ids, descriptors
       const int dim = e->cfg.dim;
       int kpv = PLAN_THREADS;
@@ -483,7 +576,8 @@ int fdts_build_plan(fdts_engine *e, const int64_t *starts, int64_t nb) {
       cudaMemsetAsync(p.bdesc, 0, sizeof(BlockDesc) * (size_t)(nb + 4), s);
       block_vertices<true><<<(unsigned)nb, PLAN_THREADS, smv, s>>>(p.bcells, p.bcount, cmax, e->cell_coord, nc, dim,
                                                                  e->coords, kpv, vmax, nullptr, p.bvcoords, p.bcc, derr);
-      block_descriptors<<<GRID(nb, 256), 256, 0, s>>>(p.bstart, nb, e->nrowptr, p.bbase, p.bcount, vcount, p.bdesc);
+      block_descriptors<<<GRID(nb, 256), 256, 0, s>>>(p.bstart, nb, e->nrowptr, p.bbase, p.slbase, p.bcount, vcount,
+                                                      p.bdesc);
       cudaStreamSynchronize(s);
       cudaFree(vcount);
     }

@@ -161,10 +161,11 @@ struct GArgs {
   const int64_t *nrowptr, *adj_ptr;
   const int64_t *bstart, *bbase;
   const int32_t *bcells, *bcount;
-  const uint16_t *cend, *cidx, *ridx;
+  const uint16_t *sdst, *cidx, *ridx;
+  const uint32_t *soff;
   int64_t ncells_total;
   int32_t cmax;
-  int32_t off_idx, off_end, off_bar, off_inA, inA_bytes;  // shared-memory layout (bytes)
+  int32_t off_idx, off_end, off_bar, off_inA, inA_bytes, off_dst, off_soff, off_obuf, zaddr;  // smem layout (bytes)
   int32_t vmax, persist;
   int64_t nblocks;
   const double *bvcoords;
@@ -173,91 +174,53 @@ struct GArgs {
   double shift, p0;
 };
 
-// one CTA per row block.  A single thread first launches TMA bulk copies of the block's index
-// segments into shared memory (they land while phase A computes).  Phase A: element matrices of
-// the block's cells -> shared memory (symmetric packing, odd stride).  Phase B: one thread per CSR
-// slot sums its staged contributions in fixed order and writes the value once (coalesced, no
-// atomics, no zero-fill).
-constexpr int GATHER_THREADS = 512;
-
-template <int DIM, int DEG, int VAR>
-__global__ void __launch_bounds__(GATHER_THREADS) heat_jacobian_gather(const GArgs a) {
-  using T = RefT<DIM, DEG, VAR>;
-  constexpr int ND = T::ND, NP = T::NP, NEP = (ND * (ND + 1) / 2) | 1;
-  extern __shared__ __align__(16) unsigned char smraw[];
-  double *stage = reinterpret_cast<double *>(smraw);
-  uint16_t *sidx = reinterpret_cast<uint16_t *>(smraw + a.off_idx);
-  uint16_t *send = reinterpret_cast<uint16_t *>(smraw + a.off_end);
-  uint64_t *bar = reinterpret_cast<uint64_t *>(smraw + a.off_bar);
-  const int64_t b = blockIdx.x;
-  const int64_t s0 = a.nrowptr[a.bstart[b]], s1 = a.nrowptr[a.bstart[b + 1]];
-  const int64_t s0a = s0 & ~7ll;
-  if (threadIdx.x == 0) {
-    const int64_t base = a.bbase[b];
-    const uint32_t nb_idx = (uint32_t)(a.bbase[b + 1] - base) * 2u;
-    const uint32_t nb_end = (uint32_t)(((s1 + 7) & ~7ll) - s0a) * 2u;
-    mbar_init(bar, 1);
-    mbar_expect_tx(bar, nb_idx + nb_end);
-    if (nb_idx) bulk_g2s(sidx, a.cidx + base, nb_idx, bar);
-    if (nb_end) bulk_g2s(send, a.cend + s0a, nb_end, bar);
+constexpr int split_row(int nd) {
+  int half = nd * (nd + 1) / 4, acc = 0, i = 0;
+  while (i < nd && acc + (nd - i) <= half) {
+    acc += nd - i;
+    ++i;
   }
-  const int ncell = a.bcount[b];
-  const int32_t *cells = a.bcells + b * a.cmax;
-  for (int k = threadIdx.x; k < ncell; k += GATHER_THREADS) {
-    const int64_t c = cells[k];
-    int32_t cc[DIM + 1];
-#pragma unroll
-    for (int v = 0; v <= DIM; ++v) cc[v] = a.cell_coord_t[v * a.ncells_total + c];
-    Geom<DIM> g;
-    compute_geometry<DIM>(a.coords, cc, g);
-    double gm[NP];
-    metric<DIM>(g, gm);
-    const double m = a.shift * g.adet;
-    double *st = stage + k * NEP;
-    static_for<ND>([&](auto I) {
-      constexpr int i = decltype(I)::value;
-      static_for<ND - i>([&](auto JJ) {
-        constexpr int j = i + decltype(JJ)::value;
-        constexpr int e = i * ND - (i * (i - 1)) / 2 + (j - i);
-        st[e] = heat_entry<T, i, j, NP>(m, gm);
-      });
-    });
-  }
-  __syncthreads();
-  mbar_wait(bar, 0);
-  for (int64_t s = s0 + threadIdx.x; s < s1; s += GATHER_THREADS) {
-    const int beg = s == s0 ? 0 : send[s - 1 - s0a];
-    const int end = send[s - s0a];
-    double acc = 0.0;
-    for (int k = beg; k < end; ++k) acc += stage[sidx[k]];
-    a.out[s] = acc;
-  }
+  return i < 1 ? 1 : i;
 }
 
-// Persistent, software-pipelined form of the Jacobian gather (one CTA per SM, loops over row
-// blocks).  Every input of a block arrives through TMA bulk copies launched one step ahead:
-//   barA[s]  : the block-local vertex coordinates + per-cell local vertex ids (phase-A inputs,
-//              double buffered, fetched during the previous block's work);
-//   barIdx   : the block's contribution addresses + segment ends (phase-B inputs, fetched while
-//              phase A computes).
+constexpr int GATHER_THREADS = 512;    // residual gather (one CTA per row block)
+constexpr int JGATHER_THREADS = 1024;  // persistent Jacobian gather
+constexpr int SELL_WINDOW = 2048;      // must match gather_plan.cu
+
+// Persistent, software-pipelined Jacobian gather: one CTA per SM loops over row blocks.
+//   phase A  the block's cells' element matrices -> shared memory (symmetric packing, odd stride);
+//   phase B  SELL-32-sigma sweep: a warp owns a slice of 32 count-sorted slots and sums their staged
+//            contributions column by column (coalesced 16-bit address loads, no divergence), results
+//            go through a 2048-slot shared buffer and leave as coalesced 8-byte stores: every CSR
+//            value is written exactly once, no atomics, no zero-fill, bitwise reproducible.
+// Every input of a block arrives through TMA bulk copies launched one step ahead:
+//   bars[1..2]  block-local vertex coordinates + per-cell local vertex ids (phase-A inputs, double
+//               buffered, fetched during the previous block's work);
+//   bars[0]     contribution addresses, slice offsets, destination offsets (phase-B inputs, fetched
+//               while phase A computes);
 // so neither phase waits on a dependent global load.
 template <int DIM, int DEG, int VAR>
-__global__ void __launch_bounds__(GATHER_THREADS, 1) heat_jacobian_gather_persist(const GArgs a) {
+__global__ void __launch_bounds__(JGATHER_THREADS, 1) heat_jacobian_gather_persist(const GArgs a) {
   using T = RefT<DIM, DEG, VAR>;
   constexpr int ND = T::ND, NP = T::NP, NEP = (ND * (ND + 1) / 2) | 1;
+  constexpr int NWARPS = JGATHER_THREADS / 32;
   extern __shared__ __align__(16) unsigned char smraw[];
   double *stage = reinterpret_cast<double *>(smraw);
   uint16_t *sidx = reinterpret_cast<uint16_t *>(smraw + a.off_idx);
-  uint16_t *send = reinterpret_cast<uint16_t *>(smraw + a.off_end);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smraw + a.off_bar);  // [0] idx, [1..2] phase-A inputs
-  unsigned char *inA[2] = {smraw + a.off_inA, smraw + a.off_inA + a.inA_bytes};
+  uint16_t *sdst = reinterpret_cast<uint16_t *>(smraw + a.off_dst);
+  uint32_t *soff = reinterpret_cast<uint32_t *>(smraw + a.off_soff);
+  double *obuf = reinterpret_cast<double *>(smraw + a.off_obuf);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smraw + a.off_bar);
+  unsigned char *inA0 = smraw + a.off_inA;
   const uint32_t vbytes = (uint32_t)a.vmax * DIM * 8u;  // multiple of 16
   const uint32_t cbytes = (uint32_t)((a.cmax * 4 + 15) & ~15);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   auto issue_inA = [&](int64_t b, int slot) {
+    unsigned char *dst = inA0 + slot * a.inA_bytes;
     mbar_expect_tx(&bars[1 + slot], vbytes + cbytes);
-    bulk_g2s(inA[slot], a.bvcoords + b * a.vmax * DIM, vbytes, &bars[1 + slot]);
-    bulk_g2s(inA[slot] + vbytes, a.bcc + b * (int64_t)((a.cmax + 3) & ~3), cbytes, &bars[1 + slot]);
+    bulk_g2s(dst, a.bvcoords + b * a.vmax * DIM, vbytes, &bars[1 + slot]);
+    bulk_g2s(dst + vbytes, a.bcc + b * (int64_t)((a.cmax + 3) & ~3), cbytes, &bars[1 + slot]);
   };
 
   const int64_t stride = gridDim.x;
@@ -268,6 +231,7 @@ __global__ void __launch_bounds__(GATHER_THREADS, 1) heat_jacobian_gather_persis
     mbar_init(&bars[1], 1);
     mbar_init(&bars[2], 1);
     issue_inA(b, 0);
+    stage[a.zaddr] = 0.0;
   }
   BlockDesc d = a.bdesc[b];
   BlockDesc dn = a.bdesc[b + stride < a.nblocks ? b + stride : b];
@@ -278,20 +242,21 @@ __global__ void __launch_bounds__(GATHER_THREADS, 1) heat_jacobian_gather_persis
     const int64_t s0a = d.s0 & ~7ll;
     if (threadIdx.x == 0) {
       const uint32_t nb_idx = (uint32_t)d.ncontrib * 2u;
-      const uint32_t nb_end = (uint32_t)(((d.s0 + d.nslots + 7) & ~7ll) - s0a) * 2u;
-      mbar_expect_tx(&bars[0], nb_idx + nb_end);
+      const uint32_t nb_dst = (uint32_t)(((d.s0 + d.nslots + 7) & ~7ll) - s0a) * 2u;
+      const uint32_t nb_off = (uint32_t)d.nslpad * 4u;
+      mbar_expect_tx(&bars[0], nb_idx + nb_dst + nb_off);
       if (nb_idx) bulk_g2s(sidx, a.cidx + d.cbase, nb_idx, &bars[0]);
-      if (nb_end) bulk_g2s(send, a.cend + s0a, nb_end, &bars[0]);
+      if (nb_dst) bulk_g2s(sdst, a.sdst + s0a, nb_dst, &bars[0]);
+      if (nb_off) bulk_g2s(soff, a.soff + d.slbase, nb_off, &bars[0]);
       if (bn < a.nblocks) issue_inA(bn, slot ^ 1);
     }
-    // descriptor of the block after next (consumed two iterations from now)
     const int64_t bnn = bn + stride;
-    BlockDesc dnn = a.bdesc[bnn < a.nblocks ? bnn : b];
+    const BlockDesc dnn = a.bdesc[bnn < a.nblocks ? bnn : b];  // consumed two iterations from now
     // ---- phase A
     mbar_wait(&bars[1 + slot], (uint32_t)((it >> 1) & 1));
-    const double *vtab = reinterpret_cast<const double *>(inA[slot]);
-    const uint32_t *lcc = reinterpret_cast<const uint32_t *>(inA[slot] + vbytes);
-    for (int k = threadIdx.x; k < d.ncell; k += GATHER_THREADS) {
+    const double *vtab = reinterpret_cast<const double *>(inA0 + slot * a.inA_bytes);
+    const uint32_t *lcc = reinterpret_cast<const uint32_t *>(inA0 + slot * a.inA_bytes + vbytes);
+    for (int k = threadIdx.x; k < d.ncell; k += JGATHER_THREADS) {
       const uint32_t packed = lcc[k];
       double X[DIM + 1][DIM];
 #pragma unroll
@@ -318,15 +283,30 @@ __global__ void __launch_bounds__(GATHER_THREADS, 1) heat_jacobian_gather_persis
     __syncthreads();
     // ---- phase B
     mbar_wait(&bars[0], (uint32_t)(it & 1));
-    const int64_t s1 = d.s0 + d.nslots;
-    for (int64_t s = d.s0 + threadIdx.x; s < s1; s += GATHER_THREADS) {
-      const int beg = s == d.s0 ? 0 : send[s - 1 - s0a];
-      const int end = send[s - s0a];
-      double acc = 0.0;
-      for (int k = beg; k < end; ++k) acc += stage[sidx[k]];
-      a.out[s] = acc;
+    const uint16_t *dstp = sdst + (d.s0 - s0a);
+    int slice0 = 0;
+    for (int wb = 0; wb < d.nslots; wb += SELL_WINDOW) {
+      const int nw = d.nslots - wb < SELL_WINDOW ? d.nslots - wb : SELL_WINDOW;
+      const int nsl = (nw + 31) >> 5;
+      // slices are sorted by width: deal them to the warps in snake order to balance the load
+      for (int r0 = 0, rnd = 0; r0 < nsl; r0 += NWARPS, ++rnd) {
+        const int sl = r0 + ((rnd & 1) ? NWARPS - 1 - warp : warp);
+        if (sl >= nsl) continue;
+        const uint32_t off = soff[slice0 + sl];
+        const int wdt = (int)((soff[slice0 + sl + 1] - off) >> 5);
+        const uint16_t *ip = sidx + off + lane;
+        double acc = 0.0;
+#pragma unroll 4
+        for (int k = 0; k < wdt; ++k) acc += stage[ip[k * 32]];
+        const int q = sl * 32 + lane;
+        if (q < nw) obuf[dstp[wb + q]] = acc;
+      }
+      __syncthreads();
+      double *o = a.out + d.s0 + wb;
+      for (int t = threadIdx.x; t < nw; t += JGATHER_THREADS) o[t] = obuf[t];
+      __syncthreads();
+      slice0 += nsl;
     }
-    __syncthreads();
     d = dn;
     dn = dnn;
   }
@@ -413,39 +393,44 @@ int launch_gather(int which, GArgs a, const GatherPlan &p, cudaStream_t s) {
   using T = RefT<DIM, DEG, VAR>;
   constexpr int ND = T::ND;
   auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
-  size_t off = up16(sizeof(double) * (size_t)p.cmax * (which == 0 ? (ND | 1) : ((ND * (ND + 1) / 2) | 1)));
-  a.off_idx = (int)off;
-  off += up16(2 * (size_t)((which == 0 ? p.max_block_adj : p.max_block_contrib) + 16));
-  a.off_end = (int)off;
-  off += up16(which == 0 ? 8 * (size_t)(p.max_block_rows + 4) : 2 * (size_t)(p.max_block_slots + 16));
-  a.off_bar = (int)off;
-  off += 32;
-  if (which == 1 && a.persist) {
-    a.inA_bytes = (int)(up16((size_t)p.vmax * DIM * 8) + up16((size_t)p.cmax * 4));
-    a.off_inA = (int)off;
-    off += 2 * (size_t)a.inA_bytes;
-  }
-  const size_t smem = off + 16;
-  if (smem > 227 * 1024) return 4;
-  if (which == 1 && a.persist) {
-    auto k = heat_jacobian_gather_persist<DIM, DEG, VAR>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t grid = p.nblocks < sms ? p.nblocks : sms;
-    k<<<(unsigned)grid, GATHER_THREADS, smem, s>>>(a);
-    return cudaGetLastError() == cudaSuccess ? 0 : 2;
-  }
   if (which == 0) {
+    size_t off = up16(sizeof(double) * (size_t)p.cmax * (ND | 1));
+    a.off_idx = (int)off;
+    off += up16(2 * (size_t)(p.max_block_adj + 16));
+    a.off_end = (int)off;
+    off += up16(8 * (size_t)(p.max_block_rows + 4));
+    a.off_bar = (int)off;
+    const size_t smem = off + 48;
+    if (smem > 227 * 1024) return 4;
     auto k = heat_residual_gather<DIM, DEG, VAR>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<(unsigned)p.nblocks, GATHER_THREADS, smem, s>>>(a);
-  } else {
-    auto k = heat_jacobian_gather<DIM, DEG, VAR>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<(unsigned)p.nblocks, GATHER_THREADS, smem, s>>>(a);
+    return cudaGetLastError() == cudaSuccess ? 0 : 2;
   }
+  size_t off = up16(sizeof(double) * ((size_t)p.cmax * ((ND * (ND + 1) / 2) | 1) + 1));
+  a.off_idx = (int)off;
+  off += up16(2 * (size_t)(p.max_block_contrib + 32));
+  a.off_dst = (int)off;
+  off += up16(2 * (size_t)(p.max_block_slots + 16));
+  a.off_soff = (int)off;
+  off += up16(4 * (size_t)(p.max_block_slices + 4));
+  a.off_obuf = (int)off;
+  off += sizeof(double) * SELL_WINDOW;
+  a.off_bar = (int)off;
+  off += 32;
+  a.inA_bytes = (int)(up16((size_t)p.vmax * DIM * 8) + up16((size_t)p.cmax * 4));
+  a.off_inA = (int)off;
+  off += 2 * (size_t)a.inA_bytes;
+  a.zaddr = p.zaddr;
+  const size_t smem = off + 16;
+  if (smem > 227 * 1024) return 4;
+  auto k = heat_jacobian_gather_persist<DIM, DEG, VAR>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t grid = p.nblocks < sms ? p.nblocks : sms;
+  k<<<(unsigned)grid, JGATHER_THREADS, smem, s>>>(a);
   return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 
@@ -507,10 +492,10 @@ int fdts_launch_heat(fdts_engine *e, int which, const double *x, const double *x
     g.coords = e->coords; g.cell_coord_t = e->cell_coord; g.cell_node_t = e->cell_node;
     g.x = x; g.xdot = xdot; g.out = out; g.isbc = e->isbc;
     g.nrowptr = e->nrowptr; g.adj_ptr = e->adj_ptr; g.bstart = p.bstart; g.bbase = p.bbase;
-    g.bcells = p.bcells; g.bcount = p.bcount; g.cend = p.cend; g.cidx = p.cidx; g.ridx = p.ridx;
+    g.bcells = p.bcells; g.bcount = p.bcount; g.sdst = p.sdst; g.soff = p.soff; g.cidx = p.cidx; g.ridx = p.ridx;
     g.ncells_total = e->cfg.num_cells; g.cmax = p.cmax; g.shift = shift; g.p0 = e->cfg.params[0];
     g.vmax = p.vmax; g.nblocks = p.nblocks; g.bvcoords = p.bvcoords; g.bcc = p.bcc; g.bdesc = p.bdesc;
-    g.persist = e->opt_persist ? 1 : 0; g.off_inA = 0; g.inA_bytes = 0;
+    g.persist = 1; g.off_inA = 0; g.inA_bytes = 0; g.off_dst = g.off_soff = g.off_obuf = 0; g.zaddr = p.zaddr;
     int rc = 3;
 #define GCASE(D, K, V) \
   if (dim == D && deg == K && (K < 3 || var == V)) rc = launch_gather<D, K, V>(which, g, p, s);

@@ -73,9 +73,6 @@ def test_gather_path_tiled_numbering(dim, degree, n, ftile, foffset):
     J1 = eng.ijacobian(0.0, x, xd, 7.5)
     J2 = eng.ijacobian(0.0, x, xd, 7.5)
     assert torch.equal(J1, J2)
-    eng.set_option("persist", 0)  # one CTA per row block instead of the persistent pipelined kernel
-    assert torch.equal(J1, eng.ijacobian(0.0, x, xd, 7.5))
-    eng.set_option("persist", 1)
     F1 = eng.ifunction(0.0, x, xd)
     F2 = eng.ifunction(0.0, x, xd)
     assert torch.equal(F1, F2)
