@@ -33,7 +33,8 @@ def make_problem(family, dim, degree, n, *, tile=0, partition=None, device="cpu"
         raise ValueError(family)
     u, udot = Function(V), Function(V)
     g = torch.Generator().manual_seed(seed)
-    gid = V.global_node_ids.cpu()
+    # rank- and numbering-independent key of a node: its lexicographic index on the refined lattice
+    gid = V._lex_key(V.node_lattice).cpu()
     nglob = V.global_num_nodes
 
     def rnd(ncomp):
