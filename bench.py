@@ -221,10 +221,10 @@ def run_b200(a):
 
     def step():
         if halo is not None:
-            r1 = halo.start(x)
-            r2 = halo.start(xd)
-            halo.finish(x, r1)
-            halo.finish(xd, r2)
+            r1 = halo.start(x, 0)
+            r2 = halo.start(xd, 1)
+            halo.finish(x, r1, 0)
+            halo.finish(xd, r2, 1)
         eng.ifunction(0.0, x, xd, out=F)
         eng.ijacobian(0.0, x, xd, shift, out=J)
 
@@ -243,10 +243,10 @@ def run_b200(a):
     e_beg.record()
     for k in range(a.steps):
         if halo is not None:
-            r1 = halo.start(x)
-            r2 = halo.start(xd)
-            halo.finish(x, r1)
-            halo.finish(xd, r2)
+            r1 = halo.start(x, 0)
+            r2 = halo.start(xd, 1)
+            halo.finish(x, r1, 0)
+            halo.finish(xd, r2, 1)
         ev[k][0].record()
         eng.ifunction(0.0, x, xd, out=F)
         ev[k][1].record()
@@ -265,6 +265,11 @@ def run_b200(a):
         total_ms, t_if, t_ij = t.tolist()
         dist.barrier()
     clocks = sampler.summary(t_start, t_end) if sampler else None
+    # partition-independent checksums of the assembled objects (compare N = 1 with N > 1)
+    chk = torch.stack([F.sum(), F.abs().sum(), J.sum(), J.abs().sum()])
+    if world > 1:
+        dist.all_reduce(chk)
+    chk = [float(v) for v in chk.tolist()]
     ndofs = V.global_num_dofs
     ms_per_step = total_ms / a.steps
     value = ndofs / (ms_per_step * 1e-3)
@@ -327,6 +332,7 @@ def run_b200(a):
                        "owner-computes gather Jacobian", "shift": shift},
             "ms_ifunction": t_if, "ms_ijacobian": t_ij,
             "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": int(launches),
+            "checksum": {"sum_F": chk[0], "sum_absF": chk[1], "sum_J": chk[2], "sum_absJ": chk[3]},
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -25,12 +25,13 @@ class HaloExchange:
         self.nc = V.ncomp
         self.neighbours = sorted(set(V.recv_slices) | set(V.send_lists))
         self.send_idx = {r: V.send_lists[r].to(self.dev) for r in V.send_lists}
-        self.send_buf = {r: torch.empty(len(v) * self.nc, dtype=torch.float64, device=self.dev)
-                         for r, v in self.send_idx.items()}
+        # two buffer sets ("slots") so that the exchanges of u and udot can be in flight together
+        self.send_buf = {(k, r): torch.empty(len(v) * self.nc, dtype=torch.float64, device=self.dev)
+                         for r, v in self.send_idx.items() for k in (0, 1)}
         self.recv_buf = {}
         if self.nc > 1:
-            self.recv_buf = {r: torch.empty(c * self.nc, dtype=torch.float64, device=self.dev)
-                             for r, (s, c) in V.recv_slices.items()}
+            self.recv_buf = {(k, r): torch.empty(c * self.nc, dtype=torch.float64, device=self.dev)
+                             for r, (s, c) in V.recv_slices.items() for k in (0, 1)}
         self._dist = dist
         self.bytes_per_exchange = 8 * self.nc * sum(len(v) for v in self.send_idx.values())
 
@@ -38,13 +39,14 @@ class HaloExchange:
         return self._dist.get_global_rank(self.group, r) if self.group is not None else r
 
     # -- pieces (so that the caller can overlap interior work) -----------------
-    def start(self, x_local: torch.Tensor):
-        """pack + post sends/recvs; returns the list of pending requests."""
+    def start(self, x_local: torch.Tensor, slot: int = 0):
+        """pack + post sends/recvs; returns the list of pending requests.  Exchanges that are in
+        flight at the same time must use different buffer ``slot``s (0 or 1)."""
         dist, V, nc = self._dist, self.V, self.nc
         ops = []
         for r in self.neighbours:
             if r in self.send_idx:
-                idx, buf = self.send_idx[r], self.send_buf[r]
+                idx, buf = self.send_idx[r], self.send_buf[(slot, r)]
                 if x_local.is_cuda and self.engine is not None:
                     self.engine.halo_pack(x_local, idx, buf)
                 else:  # CPU tensors: host-side logic tests under gloo
@@ -56,17 +58,17 @@ class HaloExchange:
                 ops.append(dist.P2POp(dist.isend, buf, self._global_rank(r), group=self.group))
             if r in V.recv_slices:
                 s, c = V.recv_slices[r]
-                tgt = x_local[s:s + c] if nc == 1 else self.recv_buf[r]
+                tgt = x_local[s:s + c] if nc == 1 else self.recv_buf[(slot, r)]
                 ops.append(dist.P2POp(dist.irecv, tgt, self._global_rank(r), group=self.group))
         return dist.batch_isend_irecv(ops) if ops else []
 
-    def finish(self, x_local: torch.Tensor, reqs):
+    def finish(self, x_local: torch.Tensor, reqs, slot: int = 0):
         for q in reqs:
             q.wait()
         V, nc = self.V, self.nc
         if nc > 1:
             for r, (s, c) in V.recv_slices.items():
-                buf = self.recv_buf[r]
+                buf = self.recv_buf[(slot, r)]
                 if x_local.is_cuda and self.engine is not None:
                     self.engine.halo_unpack(x_local, s, c, buf)
                 elif V.layout == "interleaved":
