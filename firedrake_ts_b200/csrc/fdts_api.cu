@@ -1,5 +1,6 @@
 // fdts_api.cu -- the C ABI of libfdts_b200.so (see include/fdts.h for the
 // reference interfaces each entry point replaces).
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -254,6 +255,7 @@ extern "C" int fdts_destroy(fdts_handle e) {
   for (void *p : ptrs)
     if (p) cudaFree(p);
   fdts_free_plan(e);
+  fdts_free_plan2(e);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
   return 0;
@@ -324,6 +326,42 @@ extern "C" int fdts_set_option(fdts_handle e, const char *key, int64_t value) {
     e->opt_persist = value ? 1 : 0;
     return 0;
   }
+  if (!strcmp(key, "plan_version")) {
+    if (value != 1 && value != 2) {
+      fdts_set_error("plan_version must be 1 (windowed SELL + residual lists) or 2 (sector SELL + pattern dictionary)");
+      return 1;
+    }
+    e->opt_plan_version = value;
+    return 0;
+  }
+  if (!strcmp(key, "sector")) {
+    if (value != 1 && value != 2 && value != 4) {
+      fdts_set_error("sector must be 4 (32-byte store groups), 2 (16-byte store groups) or 1 (single slots)");
+      return 1;
+    }
+    e->opt_sector = value;
+    return 0;
+  }
+  if (!strcmp(key, "optimize")) {
+    e->opt_optimize = value ? 1 : 0;
+    return 0;
+  }
+  if (!strcmp(key, "threads")) {
+    if (value != 512 && value != 1024) {
+      fdts_set_error("threads must be 512 or 1024");
+      return 1;
+    }
+    e->opt_threads = value;
+    return 0;
+  }
+  if (!strcmp(key, "debug")) {
+    e->opt_debug = value;
+    return 0;
+  }
+  if (!strcmp(key, "dedup")) {
+    e->opt_dedup = value ? 1 : 0;
+    return 0;
+  }
   fdts_set_error(std::string("unknown option ") + key);
   return 1;
 }
@@ -331,6 +369,11 @@ extern "C" int fdts_set_option(fdts_handle e, const char *key, int64_t value) {
 extern "C" int fdts_set_row_blocks(fdts_handle e, const int64_t *starts_host, int64_t nblocks) {
   if (!e || !starts_host) return 1;
   FDTS_CHECK(cudaSetDevice(e->device));
+  if (e->opt_plan_version == 2) {
+    fdts_free_plan(e);
+    return fdts_build_plan2(e, starts_host, nblocks);
+  }
+  fdts_free_plan2(e);
   return fdts_build_plan(e, starts_host, nblocks);
 }
 
@@ -340,16 +383,33 @@ extern "C" int fdts_get_option(fdts_handle e, const char *key, int64_t *value) {
     *value = e->opt_scatter;
     return 0;
   }
+  const bool v2 = e->plan2.ready;
   if (!strcmp(key, "plan_cells_max")) {
-    *value = e->plan.cmax;
+    *value = v2 ? e->plan2.cmax : e->plan.cmax;
     return 0;
   }
   if (!strcmp(key, "plan_contributions")) {
-    *value = e->plan.total_contrib;
+    *value = v2 ? e->plan2.total_idx : e->plan.total_contrib;
     return 0;
   }
   if (!strcmp(key, "plan_blocks")) {
-    *value = e->plan.nblocks;
+    *value = v2 ? e->plan2.nblocks : e->plan.nblocks;
+    return 0;
+  }
+  if (!strcmp(key, "plan_version")) {
+    *value = v2 ? 2 : (e->plan.ready ? 1 : 0);
+    return 0;
+  }
+  if (!strcmp(key, "plan_patterns")) {
+    *value = v2 ? e->plan2.unique_patterns : e->plan.nblocks;
+    return 0;
+  }
+  if (!strcmp(key, "plan_shared_contributions")) {
+    *value = v2 ? e->plan2.shared_idx : e->plan.total_contrib;
+    return 0;
+  }
+  if (!strcmp(key, "plan_vertices_max")) {
+    *value = v2 ? e->plan2.vmax : e->plan.vmax;
     return 0;
   }
   fdts_set_error(std::string("unknown option ") + key);

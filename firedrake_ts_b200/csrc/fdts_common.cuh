@@ -46,6 +46,38 @@ struct BlockDesc {              // 48 bytes, one per row block
   int32_t nslpad, pad;          // slice-offset entries incl. end marker, padded to 4
 };
 
+// owner-computes gather plan, version 2 (gather_plan.cu: fdts_build_plan2).
+// Sector-grouped SELL: the unit of sorting is a 32-byte sector (4 consecutive CSR slots), so the lanes
+// that sum a sector also store it (full-sector writes, no transposition buffer, no barriers inside the
+// sweep).  Slots with more than SPLIT_CAP contributions are summed by 4 lanes each ("split" slices).
+// Blocks whose index lists are identical share one copy (pattern dictionary).
+struct BlockDesc2 {             // 64 bytes, one per row block
+  int64_t s0;                   // first node-level CSR slot of the block
+  int64_t idx_off;              // first entry of the block's pattern in cidx (uint16 units, multiple of 64)
+  int64_t meta_off;             // first slice of the pattern in smeta (multiple of 4); gdst holds 32/sector per slice
+  int64_t cc_off;               // first entry of the pattern in bcc (multiple of 4)
+  int64_t vc_off;               // first coordinate of the block's vertex table in bvcoords
+  int32_t nslots, nidx;         // CSR slots of the block; SELL entries (multiple of 32)
+  int32_t ncell, nvert;
+  int32_t nsl, s_align;         // slices; s0 & 3
+};
+
+struct GatherPlan2 {
+  bool ready = false;
+  int64_t nblocks = 0;
+  int32_t cmax = 0, vmax = 0, nep = 0, zaddr = 0;
+  int32_t max_nidx = 0, max_nsl = 0;  // per-block maxima (max_nsl padded to 4)
+  int32_t sector = 4;           // slots per store group: 4 = 32-byte sectors, 2 = 16-byte half sectors
+  uint16_t *cidx = nullptr;     // staged element-matrix addresses, SELL order
+  uint32_t *smeta = nullptr;    // per slice: (offset/64) | width << 16 | split << 24
+  uint16_t *gdst = nullptr;     // per slice: 32/sector block-local sector ids (0xffff = none)
+  uint32_t *bcc = nullptr;      // per cell: (dim+1) block-local vertex ids, one byte each
+  double *bvcoords = nullptr;   // per block: vmax x dim vertex coordinates
+  BlockDesc2 *bdesc = nullptr;
+  int64_t total_idx = 0, unique_patterns = 0, shared_idx = 0;
+  int32_t optimized = 0;        // unique patterns went through the bank-conflict-aware column ordering
+};
+
 struct fdts_engine {
   fdts_config cfg;  // scalars only are meaningful after create; pointers below are device copies
   int device = 0;
@@ -75,6 +107,13 @@ struct fdts_engine {
   int64_t opt_gather_residual = 0;  // gather path also for the residual (slower than atomics today)
   int64_t opt_persist = 1;       // gather path: persistent pipelined Jacobian kernel
   GatherPlan plan;
+  GatherPlan2 plan2;
+  int64_t opt_plan_version = 2;  // what fdts_set_row_blocks builds: 1 = windowed SELL (+ residual lists), 2 = sector SELL
+  int64_t opt_dedup = 1;         // plan 2: share identical block patterns
+  int64_t opt_sector = 4;        // plan 2: slots per store group (4 or 2)
+  int64_t opt_optimize = 1;      // plan 2: bank-conflict-aware column order for the unique patterns
+  int64_t opt_threads = 1024;    // plan 2: threads per persistent CTA (512 or 1024)
+  int64_t opt_debug = 0;         // development only (timing experiments with phases switched off)
   int variant = -1;              // which baked RefT table matches cfg.R (-1: none, closed-form path off)
   // scratch
   double *h2d_x = nullptr, *h2d_xdot = nullptr, *d_f = nullptr, *d_vals = nullptr;  // host-variant staging
@@ -103,7 +142,9 @@ int fdts_launch_heat(fdts_engine *e, int which, const double *x, const double *x
 int fdts_build_pattern(fdts_engine *e, cudaStream_t s);
 int fdts_heat_match_tables(int dim, int deg, const double *R_host);
 int fdts_build_plan(fdts_engine *e, const int64_t *starts_host, int64_t nblocks);
+int fdts_build_plan2(fdts_engine *e, const int64_t *starts_host, int64_t nblocks);
 void fdts_free_plan(fdts_engine *e);
+void fdts_free_plan2(fdts_engine *e);
 
 // ------------------------------------------------------------------ device helpers
 __device__ __forceinline__ void red_add_f64(double *addr, double v) {

@@ -605,3 +605,679 @@ int fdts_build_plan(fdts_engine *e, const int64_t *starts, int64_t nb) {
   if (rc) fdts_free_plan(e);
   return rc;
 }
+
+// =====================================================================================
+// Plan version 2: sector-grouped SELL with split slices and a pattern dictionary.
+// =====================================================================================
+#include <algorithm>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+
+constexpr int SPLIT_CAP = 8;        // slots with more contributions are summed by 4 lanes each
+constexpr int MAX_SECTORS = 8192;   // sectors per row block handled by the in-smem sort
+constexpr int MAX_SLICES = 2048;    // slices per row block
+constexpr uint32_t SPLIT_FLAG = 0x80000000u;
+
+// SELL storage of one slice of width w: ceil(w/2) rows of 32 lanes x 2 columns (one 32-bit load per
+// lane fetches two consecutive columns): entry (column k, lane l) sits at (k>>1)*64 + 2*l + (k&1).
+__device__ __forceinline__ uint32_t slice_entries(int w) { return 64u * (uint32_t)((w + 1) >> 1); }
+__device__ __forceinline__ int64_t sell_entry(int k, int lane) { return (int64_t)(k >> 1) * 64 + 2 * lane + (k & 1); }
+
+// one CTA per row block.  G = slots per sector (4: 32-byte sectors, 2: 16-byte half sectors, 1: single slots).
+// Sectors are sorted (split first, wide first); a normal slice holds 32/G sectors (one slot per lane),
+// a split slice 8/G sectors (four lanes per slot).  WRITE=false: slice and entry counts only.
+template <bool WRITE>
+__global__ void __launch_bounds__(PLAN_THREADS) sell2_layout(const int64_t *__restrict__ bstart,
+                                                             const int64_t *__restrict__ nrp,
+                                                             const uint8_t *__restrict__ cnt8, int G,
+                                                             const int64_t *__restrict__ meta_off,
+                                                             uint32_t *__restrict__ smeta, uint16_t *__restrict__ gdst,
+                                                             uint32_t *__restrict__ sellpos,
+                                                             int64_t *__restrict__ btotal, int64_t *__restrict__ bnsl,
+                                                             int *__restrict__ err) {
+  __shared__ uint32_t keys[MAX_SECTORS];
+  __shared__ uint32_t woff[MAX_SLICES + 2];
+  __shared__ int nsplit_s;
+  const int lg = G == 4 ? 2 : (G == 2 ? 1 : 0);
+  const int per_norm = 32 >> lg, per_split = 8 >> lg;  // sectors per normal / split slice
+  const int64_t b = blockIdx.x;
+  const int64_t s0 = nrp[bstart[b]], s1 = nrp[bstart[b + 1]];
+  const int64_t sec0 = s0 >> lg;
+  const int64_t nsec64 = s1 > s0 ? ((s1 + G - 1) >> lg) - sec0 : 0;
+  if (nsec64 > MAX_SECTORS) {
+    if (threadIdx.x == 0) {
+      atomicExch(err, 7);
+      btotal[b] = 0;
+      bnsl[b] = 0;
+    }
+    return;
+  }
+  const int nsec = (int)nsec64;
+  if (threadIdx.x == 0) nsplit_s = 0;
+  __syncthreads();
+  for (int t = threadIdx.x; t < MAX_SECTORS; t += PLAN_THREADS) {
+    uint32_t key = 0xFFFFFFFFu;
+    if (t < nsec) {
+      int m = 0;
+      for (int q = 0; q < G; ++q) {
+        const int64_t slot = (int64_t)G * (sec0 + t) + q;
+        if (slot >= s0 && slot < s1) m = max(m, (int)cnt8[slot]);
+      }
+      const int split = m > SPLIT_CAP ? 1 : 0;
+      const int width = split ? (m + 3) >> 2 : m;
+      if (split) atomicAdd(&nsplit_s, 1);
+      key = ((uint32_t)(0x1ff - ((split << 8) | width)) << 16) | (uint32_t)t;  // split first, wide first
+    }
+    keys[t] = key;
+  }
+  __syncthreads();
+  for (int kk = 2; kk <= MAX_SECTORS; kk <<= 1)
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < MAX_SECTORS; t += PLAN_THREADS) {
+        const int q = t ^ j;
+        if (q > t) {
+          const uint32_t x = keys[t], y = keys[q];
+          const bool up = (t & kk) == 0;
+          if ((x > y) == up) {
+            keys[t] = y;
+            keys[q] = x;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  const int nsplit = nsplit_s;
+  const int nslA = (nsplit + per_split - 1) / per_split, nslB = (nsec - nsplit + per_norm - 1) / per_norm;
+  const int nsl = nslA + nslB;
+  if (nsl > MAX_SLICES) {
+    if (threadIdx.x == 0) {
+      atomicExch(err, 7);
+      btotal[b] = 0;
+      bnsl[b] = 0;
+    }
+    return;
+  }
+  auto first_sector = [&](int j) { return j < nslA ? per_split * j : nsplit + per_norm * (j - nslA); };
+  auto width_of = [&](uint32_t key) { return (int)((0x1ff - (key >> 16)) & 0xff); };
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int j = 0; j < nsl; ++j) {
+      woff[j] = run;
+      run += slice_entries(width_of(keys[first_sector(j)]));
+    }
+    woff[nsl] = run;
+    btotal[b] = run;
+    bnsl[b] = WRITE ? nsl : ((nsl + 3) & ~3);
+    if ((run >> 6) > 65535u) atomicExch(err, 8);
+  }
+  if (!WRITE) return;
+  __syncthreads();
+  const int64_t mo = meta_off[b];
+  for (int j = threadIdx.x; j < ((nsl + 3) & ~3); j += PLAN_THREADS) {
+    uint32_t m = 0;
+    if (j < nsl) m = (woff[j] >> 6) | ((uint32_t)width_of(keys[first_sector(j)]) << 16) | (j < nslA ? 1u << 24 : 0u);
+    smeta[mo + j] = m;
+    for (int g = 0; g < per_norm; ++g) {
+      uint16_t v = 0xffff;
+      if (j < nslA) {
+        if (g < per_split && per_split * j + g < nsplit) v = (uint16_t)(keys[per_split * j + g] & 0xffffu);
+      } else if (j < nsl) {
+        const int q = nsplit + per_norm * (j - nslA) + g;
+        if (q < nsec) v = (uint16_t)(keys[q] & 0xffffu);
+      }
+      gdst[(mo + j) * per_norm + g] = v;
+    }
+  }
+  for (int q = threadIdx.x; q < nsec; q += PLAN_THREADS) {
+    const int t = (int)(keys[q] & 0xffffu);
+    int j, lanebase;
+    uint32_t flag = 0;
+    if (q < nsplit) {
+      j = q / per_split;
+      lanebase = (q % per_split) * 4 * G;
+      flag = SPLIT_FLAG;
+    } else {
+      const int qq = q - nsplit;
+      j = nslA + qq / per_norm;
+      lanebase = (qq % per_norm) * G;
+    }
+    for (int sub = 0; sub < G; ++sub) {
+      const int64_t slot = (int64_t)G * (sec0 + t) + sub;
+      // sellpos: slice offset (units of 64 entries) << 8 | first lane of the slot | split flag
+      if (slot >= s0 && slot < s1) sellpos[slot] = ((woff[j] >> 6) << 8) | (uint32_t)(lanebase + (flag ? sub * 4 : sub)) | flag;
+    }
+  }
+}
+
+// padding entries point at one of 16 staged zeros, bank = lane & 15 (conflict free among themselves)
+__global__ void fill_padding(uint16_t *__restrict__ p, int64_t n, int zaddr) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) p[t] = (uint16_t)(zaddr + (int)((t >> 1) & 15));
+}
+
+// writes the staged addresses of every contribution into its SELL position (one thread per row,
+// contributions in ascending cell order => reproducible sums)
+__global__ void slot_contributions2(const int64_t *__restrict__ bstart, const int64_t *__restrict__ adj_ptr,
+                                    const int32_t *__restrict__ adj_cell, const int32_t *__restrict__ cell_node_t,
+                                    int64_t nc, int nd, int nep, const uint8_t *__restrict__ pos8_t,
+                                    const uint8_t *__restrict__ isbc, const int64_t *__restrict__ nrp,
+                                    uint8_t *__restrict__ cnt8, const uint32_t *__restrict__ sellpos,
+                                    const int64_t *__restrict__ idx_off, const int32_t *__restrict__ bcells,
+                                    const int32_t *__restrict__ bcount, int cmax, uint16_t *__restrict__ cidx,
+                                    int *__restrict__ err) {
+  const int64_t b = blockIdx.x;
+  const int64_t r0 = bstart[b], r1 = bstart[b + 1];
+  for (int64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+    if (isbc[r]) continue;
+    const int64_t rb = nrp[r];
+    for (int64_t a = adj_ptr[r]; a < adj_ptr[r + 1]; ++a) {
+      const int32_t code = adj_cell[a];
+      const int64_t cell = code >> 5;
+      const int i = code & 31;
+      const int cs = find_cell(bcells + b * cmax, bcount[b], (int32_t)cell);
+      if (cs < 0) {
+        atomicExch(err, 2);
+        continue;
+      }
+      for (int j = 0; j < nd; ++j) {
+        if (isbc[cell_node_t[(int64_t)j * nc + cell]]) continue;
+        const int64_t slot = rb + pos8_t[(int64_t)(i * nd + j) * nc + cell];
+        const int k = cnt8[slot]++;
+        const uint32_t sp = sellpos[slot];
+        const int64_t base = (int64_t)((sp & ~SPLIT_FLAG) >> 8) * 64;
+        const int lane0 = (int)(sp & 0xffu);
+        const int64_t at = (sp & SPLIT_FLAG) ? base + sell_entry(k >> 2, lane0 + (k & 3)) : base + sell_entry(k, lane0);
+        cidx[idx_off[b] + at] = (uint16_t)(cs * nep + sym_index(i, j, nd));
+      }
+    }
+  }
+}
+
+__global__ void block_descriptors2(const int64_t *__restrict__ bstart, int64_t nb, const int64_t *__restrict__ nrp,
+                                   const int64_t *__restrict__ idx_off, const int64_t *__restrict__ meta_off,
+                                   const int64_t *__restrict__ bnsl_true, const int32_t *__restrict__ bcount,
+                                   const int32_t *__restrict__ vcount, int cmaxp, int vmax, int dim, int G,
+                                   BlockDesc2 *__restrict__ d) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  BlockDesc2 x;
+  x.s0 = nrp[bstart[b]];
+  x.idx_off = idx_off[b];
+  x.meta_off = meta_off[b];
+  x.cc_off = b * (int64_t)cmaxp;
+  x.vc_off = b * (int64_t)vmax * dim;
+  x.nslots = (int32_t)(nrp[bstart[b + 1]] - x.s0);
+  x.nidx = (int32_t)(idx_off[b + 1] - idx_off[b]);
+  x.ncell = bcount[b];
+  x.nvert = vcount[b];
+  x.nsl = (int32_t)bnsl_true[b];
+  x.s_align = (int32_t)(x.s0 & (G - 1));
+  d[b] = x;
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+
+// 128-bit content hash of a block's pattern (position-keyed, order-independent sum => parallel)
+__global__ void __launch_bounds__(PLAN_THREADS) block_hash(const BlockDesc2 *__restrict__ d,
+                                                           const uint16_t *__restrict__ cidx,
+                                                           const uint32_t *__restrict__ smeta,
+                                                           const uint16_t *__restrict__ gdst,
+                                                           const uint32_t *__restrict__ bcc, int per_norm,
+                                                           uint64_t *__restrict__ hash2) {
+  __shared__ unsigned long long h0, h1;
+  const BlockDesc2 x = d[blockIdx.x];
+  if (threadIdx.x == 0) {
+    h0 = mix64(((uint64_t)x.nslots << 32) ^ (uint64_t)x.nidx) + mix64(((uint64_t)x.ncell << 32) ^ (uint64_t)x.nvert ^ 0x51ull << 60);
+    h1 = mix64(((uint64_t)x.nsl << 32) ^ (uint64_t)x.s_align ^ 0x7ull << 58);
+  }
+  __syncthreads();
+  uint64_t a0 = 0, a1 = 0;
+  auto add = [&](uint64_t stream, uint64_t pos, uint64_t val) {
+    const uint64_t k = (stream << 56) ^ (pos << 20) ^ val;
+    a0 += mix64(k);
+    a1 += mix64(k ^ 0xa5a5a5a5deadbeefull);
+  };
+  for (int t = threadIdx.x; t < x.nidx; t += PLAN_THREADS) add(1, t, cidx[x.idx_off + t]);
+  const int nslp = (x.nsl + 3) & ~3;
+  for (int t = threadIdx.x; t < nslp; t += PLAN_THREADS) add(2, t, smeta[x.meta_off + t]);
+  for (int t = threadIdx.x; t < nslp * per_norm; t += PLAN_THREADS) add(3, t, gdst[x.meta_off * per_norm + t]);
+  for (int t = threadIdx.x; t < x.ncell; t += PLAN_THREADS) add(4, t, bcc[x.cc_off + t]);
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&h0, (unsigned long long)a0);
+    atomicAdd(&h1, (unsigned long long)a1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    hash2[2 * blockIdx.x] = h0;
+    hash2[2 * blockIdx.x + 1] = h1;
+  }
+}
+
+__global__ void apply_representatives(BlockDesc2 *__restrict__ d, const int64_t *__restrict__ rep, int64_t nb) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const int64_t r = rep[b];
+  if (r == b) return;
+  d[b].idx_off = d[r].idx_off;
+  d[b].meta_off = d[r].meta_off;
+  d[b].cc_off = d[r].cc_off;
+}
+
+struct PairHash {
+  size_t operator()(const std::pair<uint64_t, uint64_t> &p) const { return (size_t)(p.first ^ (p.second * 0x9e3779b97f4a7c15ull)); }
+};
+
+}  // namespace
+
+// Bank-conflict-aware column order (host side, unique patterns only).  The order in which a lane sums
+// its contributions is free, so each lane's address list is permuted to spread the 16 lanes of a
+// half-warp over the 16 eight-byte banks of every column; padding lanes then take a staged zero in
+// the least loaded bank.  Greedy lane by lane; exhaustive over the permutations of short lists.
+static void optimize_pattern(const BlockDesc2 &d, const uint32_t *meta, uint16_t *idx, int zaddr) {
+  uint64_t rng = 0x243f6a8885a308d3ull;
+  auto next = [&]() {
+    rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+    return (uint32_t)(rng >> 33);
+  };
+  struct Ent {
+    uint16_t addr;
+    uint16_t n;
+  };
+  std::vector<int> best, cand, ident;
+  for (int sl = 0; sl < d.nsl; ++sl) {
+    const uint32_t m = meta[sl];
+    const int w = (int)((m >> 16) & 0xffu);
+    if (w < 1) continue;
+    uint16_t *base = idx + (size_t)(m & 0xffffu) * 64;
+    auto at = [&](int k, int lane) -> uint16_t & { return base[(size_t)(k >> 1) * 64 + 2 * lane + (k & 1)]; };
+    // load[k][half][bank]: distinct addresses placed there, with multiplicity
+    std::vector<std::vector<Ent>> load((size_t)w * 2 * 16);
+    auto cell = [&](int k, int half, int bank) -> std::vector<Ent> & { return load[((size_t)k * 2 + half) * 16 + bank]; };
+    auto add = [&](int k, int half, uint16_t x) {
+      auto &v = cell(k, half, x & 15);
+      for (auto &e : v)
+        if (e.addr == x) {
+          ++e.n;
+          return;
+        }
+      v.push_back({x, 1});
+    };
+    auto remove = [&](int k, int half, uint16_t x) {
+      auto &v = cell(k, half, x & 15);
+      for (size_t i = 0; i < v.size(); ++i)
+        if (v[i].addr == x) {
+          if (--v[i].n == 0) v.erase(v.begin() + (long)i);
+          return;
+        }
+    };
+    auto cost_of = [&](int k, int half, uint16_t x) {
+      const auto &v = cell(k, half, x & 15);
+      for (const auto &e : v)
+        if (e.addr == x) return 0;  // same address: broadcast
+      return 2 * (int)v.size() + 1;
+    };
+    std::vector<std::vector<uint16_t>> cur(32);
+    ident.resize(w);
+    for (int k = 0; k < w; ++k) ident[k] = k;
+    for (int sweep = 0; sweep < 4; ++sweep) {
+      bool changed = false;
+      for (int lane = 0; lane < 32; ++lane) {
+        const int half = lane >> 4;
+        auto &vals = cur[lane];
+        if (sweep == 0) {
+          vals.resize(w);
+          for (int k = 0; k < w; ++k) vals[k] = at(k, lane);
+        } else {
+          for (int k = 0; k < w; ++k)
+            if (vals[k] < zaddr) remove(k, half, vals[k]);
+        }
+        int nreal = 0;
+        for (int k = 0; k < w; ++k) nreal += vals[k] < zaddr;
+        if (nreal == 0) continue;
+        int bestc = -1;
+        auto consider = [&](const std::vector<int> &pm) {
+          int c = 0;
+          for (int k = 0; k < w; ++k)
+            if (vals[pm[k]] < zaddr) c += cost_of(k, half, vals[pm[k]]);
+          if (bestc < 0 || c < bestc) {
+            bestc = c;
+            best = pm;
+          }
+        };
+        consider(ident);  // keep the current order on ties
+        if (w <= 5) {
+          cand = ident;
+          do consider(cand); while (std::next_permutation(cand.begin(), cand.end()));
+        } else {
+          for (int r = 0; r < w; ++r) {
+            cand.resize(w);
+            for (int k = 0; k < w; ++k) cand[k] = (k + r) % w;
+            consider(cand);
+            std::reverse(cand.begin(), cand.end());
+            consider(cand);
+          }
+          for (int t = 0; t < 128 && bestc > 0; ++t) {
+            cand = ident;
+            for (int k = w - 1; k > 0; --k) std::swap(cand[k], cand[next() % (uint32_t)(k + 1)]);
+            consider(cand);
+          }
+        }
+        std::vector<uint16_t> out(w);
+        for (int k = 0; k < w; ++k) out[k] = vals[best[k]];
+        changed |= out != vals;
+        vals = out;
+        for (int k = 0; k < w; ++k)
+          if (vals[k] < zaddr) add(k, half, vals[k]);
+      }
+      if (sweep > 0 && !changed) break;
+    }
+    for (int lane = 0; lane < 32; ++lane)
+      for (int k = 0; k < w; ++k) at(k, lane) = cur[lane][k];
+    for (int lane = 0; lane < 32; ++lane)  // padding: a staged zero in the least loaded bank
+      for (int k = 0; k < w; ++k) {
+        if (at(k, lane) < zaddr) continue;
+        const int half = lane >> 4;
+        int bb = 0;
+        size_t bl = (size_t)-1;
+        for (int bk = 0; bk < 16; ++bk) {
+          const auto &v = cell(k, half, bk);
+          size_t l = v.size();
+          for (const auto &e : v)
+            if (e.addr == (uint16_t)(zaddr + bk)) --l;  // the zero of this bank is already there: free
+          if (l < bl) {
+            bl = l;
+            bb = bk;
+          }
+        }
+        at(k, lane) = (uint16_t)(zaddr + bb);
+        add(k, half, (uint16_t)(zaddr + bb));
+      }
+  }
+}
+
+void fdts_free_plan2(fdts_engine *e) {
+  GatherPlan2 &p = e->plan2;
+  void *ptrs[] = {p.cidx, p.smeta, p.gdst, p.bcc, p.bvcoords, p.bdesc};
+  for (void *q : ptrs)
+    if (q) cudaFree(q);
+  p = GatherPlan2();
+}
+
+#define P2_ALLOC(ptr, bytes, what)                                              \
+  if (cudaMalloc((void **)&(ptr), (bytes)) != cudaSuccess) {                    \
+    fdts_set_error(std::string("gather plan 2: out of device memory (") + what + ")"); \
+    rc = 2;                                                                     \
+    break;                                                                      \
+  }
+
+int fdts_build_plan2(fdts_engine *e, const int64_t *starts, int64_t nb) {
+  fdts_free_plan2(e);
+  GatherPlan2 &p = e->plan2;
+  cudaStream_t s = e->own_stream;
+  const int64_t nown = e->cfg.num_owned_nodes, nc = e->cfg.num_cells, nnz = e->node_nnz;
+  const int nd = e->cfg.nd, dim = e->cfg.dim;
+  if (nb <= 0 || starts[0] != 0 || starts[nb] != nown) {
+    fdts_set_error("row blocks must cover the owned rows [0, num_owned_nodes)");
+    return 1;
+  }
+  if (e->cfg.ncomp != 1) {
+    fdts_set_error("gather plan: scalar spaces only");
+    return 3;
+  }
+  p.nblocks = nb;
+  p.nep = (nd * (nd + 1) / 2) | 1;
+  const int G = e->opt_sector == 2 ? 2 : (e->opt_sector == 1 ? 1 : 4);
+  const int per_norm = 32 / G;
+  p.sector = G;
+  int64_t *bstart = nullptr, *ncand = nullptr, *btotal = nullptr, *bnsl = nullptr, *idx_off = nullptr, *meta_off = nullptr,
+          *dmax = nullptr, *rep_d = nullptr;
+  int32_t *bcount = nullptr, *bcells = nullptr, *vcount = nullptr, *imax = nullptr;
+  uint8_t *cnt8 = nullptr;
+  uint32_t *sellpos = nullptr;
+  uint64_t *hash_d = nullptr;
+  int *derr = nullptr;
+  void *tmp = nullptr;
+  size_t tb = 0;
+  int rc = 0;
+  auto max_i64 = [&](const int64_t *src, int64_t n, int64_t &out) {
+    size_t t2 = 0;
+    cub::DeviceReduce::Max(nullptr, t2, src, dmax, n, s);
+    if (t2 > tb) return 2;
+    cub::DeviceReduce::Max(tmp, t2, src, dmax, n, s);
+    cudaMemcpyAsync(&out, dmax, sizeof(int64_t), cudaMemcpyDeviceToHost, s);
+    return cudaStreamSynchronize(s) == cudaSuccess ? 0 : 2;
+  };
+  auto max_i32 = [&](const int32_t *src, int64_t n, int32_t &out) {
+    size_t t2 = 0;
+    cub::DeviceReduce::Max(nullptr, t2, src, imax, n, s);
+    if (t2 > tb) return 2;
+    cub::DeviceReduce::Max(tmp, t2, src, imax, n, s);
+    cudaMemcpyAsync(&out, imax, sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+    return cudaStreamSynchronize(s) == cudaSuccess ? 0 : 2;
+  };
+  auto scan = [&](const int64_t *src, int64_t *dst, int64_t n) {
+    size_t t2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, t2, src, dst, n, s);
+    if (t2 > tb) return 2;
+    cub::DeviceScan::ExclusiveSum(tmp, t2, src, dst, n, s);
+    return 0;
+  };
+  do {
+    tb = 1 << 22;  // ample for CUB reductions/scans over nb+1 entries
+    {
+      size_t t2 = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, t2, btotal, btotal, nb + 1, s);
+      if (t2 > tb) tb = t2;
+    }
+    P2_ALLOC(tmp, tb + 16, "scratch");
+    P2_ALLOC(bstart, sizeof(int64_t) * (nb + 1), "block starts");
+    P2_ALLOC(ncand, sizeof(int64_t) * (nb + 1), "scratch");
+    P2_ALLOC(btotal, sizeof(int64_t) * (nb + 1), "scratch");
+    P2_ALLOC(bnsl, sizeof(int64_t) * (nb + 1), "scratch");
+    P2_ALLOC(idx_off, sizeof(int64_t) * (nb + 1), "scratch");
+    P2_ALLOC(meta_off, sizeof(int64_t) * (nb + 1), "scratch");
+    P2_ALLOC(dmax, sizeof(int64_t) * 2, "scratch");
+    P2_ALLOC(imax, sizeof(int32_t) * 2, "scratch");
+    P2_ALLOC(derr, sizeof(int), "scratch");
+    P2_ALLOC(bcount, sizeof(int32_t) * nb, "block cell counts");
+    P2_ALLOC(vcount, sizeof(int32_t) * nb, "block vertex counts");
+    cudaMemsetAsync(derr, 0, sizeof(int), s);
+    cudaMemcpyAsync(bstart, starts, sizeof(int64_t) * (nb + 1), cudaMemcpyHostToDevice, s);
+    // ---- cells of every block
+    block_candidates<<<GRID(nb, 256), 256, 0, s>>>(bstart, nb, e->adj_ptr, ncand);
+    int64_t maxcand = 0;
+    if ((rc = max_i64(ncand, nb, maxcand))) break;
+    int kpad = PLAN_THREADS;
+    while (kpad < maxcand) kpad <<= 1;
+    if (kpad > 32768) {
+      fdts_set_error("gather plan: a row block touches too many cells (use smaller / more compact row blocks)");
+      rc = 4;
+      break;
+    }
+    const size_t sm = sizeof(int32_t) * (size_t)kpad;
+    if (sm > 48 * 1024) {
+      cudaFuncSetAttribute(block_cells<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      cudaFuncSetAttribute(block_cells<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    }
+    block_cells<false><<<(unsigned)nb, PLAN_THREADS, sm, s>>>(bstart, e->adj_ptr, e->adj_cell, kpad, 0, bcount, nullptr);
+    int32_t cmax = 0;
+    if ((rc = max_i32(bcount, nb, cmax))) break;
+    p.cmax = cmax;
+    p.zaddr = (cmax * p.nep + 15) & ~15;  // 16 staged zeros, one per 8-byte bank
+    if (p.zaddr + 16 > 65535) {
+      fdts_set_error("gather plan: staged entries per row block exceed the 16-bit address space (use smaller row blocks)");
+      rc = 4;
+      break;
+    }
+    P2_ALLOC(bcells, sizeof(int32_t) * (size_t)nb * cmax, "block cell lists");
+    block_cells<true><<<(unsigned)nb, PLAN_THREADS, sm, s>>>(bstart, e->adj_ptr, e->adj_cell, kpad, cmax, nullptr, bcells);
+    // ---- contribution counts per slot, sector-grouped SELL layout
+    P2_ALLOC(cnt8, (size_t)nnz + 1, "slot counters");
+    P2_ALLOC(sellpos, sizeof(uint32_t) * (size_t)(nnz + 1), "slot positions");
+    cudaMemsetAsync(cnt8, 0, (size_t)nnz + 1, s);
+    slot_contributions<0><<<(unsigned)nb, 128, 0, s>>>(bstart, e->adj_ptr, e->adj_cell, e->cell_node, nc, nd, p.nep, e->pos8,
+                                                      e->isbc, e->nrowptr, cnt8, nullptr, nullptr, nullptr, nullptr, cmax,
+                                                      nullptr, derr);
+    cudaMemsetAsync(btotal, 0, sizeof(int64_t) * (nb + 1), s);
+    cudaMemsetAsync(bnsl, 0, sizeof(int64_t) * (nb + 1), s);
+    sell2_layout<false><<<(unsigned)nb, PLAN_THREADS, 0, s>>>(bstart, e->nrowptr, cnt8, G, nullptr, nullptr, nullptr, nullptr,
+                                                            btotal, bnsl, derr);
+    if ((rc = scan(btotal, idx_off, nb + 1)) || (rc = scan(bnsl, meta_off, nb + 1))) break;
+    int64_t total = 0, total_sl = 0, max_idx = 0, max_sl = 0;
+    cudaMemcpyAsync(&total, idx_off + nb, sizeof(int64_t), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(&total_sl, meta_off + nb, sizeof(int64_t), cudaMemcpyDeviceToHost, s);
+    if ((rc = max_i64(btotal, nb, max_idx)) || (rc = max_i64(bnsl, nb, max_sl))) break;
+    int herr = 0;
+    cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    if (herr == 7 || herr == 8) {
+      fdts_set_error("gather plan 2: a row block has too many CSR slots (at most 8192 store groups / 2048 slices; use smaller row blocks)");
+      rc = 4;
+      break;
+    }
+    p.total_idx = total;
+    p.max_nidx = (int32_t)max_idx;
+    p.max_nsl = (int32_t)max_sl;
+    P2_ALLOC(p.cidx, sizeof(uint16_t) * (size_t)(total + 64), "contribution lists");
+    P2_ALLOC(p.smeta, sizeof(uint32_t) * (size_t)(total_sl + 16), "slice table");
+    P2_ALLOC(p.gdst, sizeof(uint16_t) * (size_t)(total_sl + 16) * per_norm, "slice destinations");
+    fill_padding<<<GRID(total + 64, 256), 256, 0, s>>>(p.cidx, total + 64, p.zaddr);
+    cudaMemsetAsync(p.smeta, 0, sizeof(uint32_t) * (size_t)(total_sl + 16), s);
+    cudaMemsetAsync(p.gdst, 0xff, sizeof(uint16_t) * (size_t)(total_sl + 16) * per_norm, s);
+    // second pass writes the tables; the true (unpadded) slice counts land in ncand (reused)
+    sell2_layout<true><<<(unsigned)nb, PLAN_THREADS, 0, s>>>(bstart, e->nrowptr, cnt8, G, meta_off, p.smeta, p.gdst, sellpos,
+                                                           btotal, ncand, derr);
+    cudaMemsetAsync(cnt8, 0, (size_t)nnz + 1, s);
+    slot_contributions2<<<(unsigned)nb, 128, 0, s>>>(bstart, e->adj_ptr, e->adj_cell, e->cell_node, nc, nd, p.nep, e->pos8,
+                                                    e->isbc, e->nrowptr, cnt8, sellpos, idx_off, bcells, bcount, cmax,
+                                                    p.cidx, derr);
+    cudaStreamSynchronize(s);
+    cudaFree(sellpos);
+    sellpos = nullptr;
+    cudaFree(cnt8);
+    cnt8 = nullptr;
+    // ---- block vertex tables
+    int kpv = PLAN_THREADS;
+    while (kpv < cmax * (dim + 1)) kpv <<= 1;
+    const size_t smv = sizeof(int32_t) * 2 * (size_t)kpv;
+    if (smv > 48 * 1024) {
+      cudaFuncSetAttribute(block_vertices<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smv);
+      cudaFuncSetAttribute(block_vertices<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smv);
+    }
+    block_vertices<false><<<(unsigned)nb, PLAN_THREADS, smv, s>>>(bcells, bcount, cmax, e->cell_coord, nc, dim, e->coords, kpv,
+                                                                0, vcount, nullptr, nullptr, derr);
+    int32_t vmax = 0;
+    if ((rc = max_i32(vcount, nb, vmax))) break;
+    vmax = (vmax + 1) & ~1;  // keep vmax*dim*8 a multiple of 16 bytes
+    p.vmax = vmax;
+    if (vmax > 254) {
+      fdts_set_error("gather plan: a row block touches more than 254 coordinate nodes (use smaller row blocks)");
+      rc = 4;
+      break;
+    }
+    const int cmaxp = (cmax + 3) & ~3;
+    P2_ALLOC(p.bvcoords, sizeof(double) * (size_t)nb * vmax * dim + 64, "block vertex tables");
+    P2_ALLOC(p.bcc, sizeof(uint32_t) * ((size_t)nb * cmaxp + 16), "block cell vertices");
+    P2_ALLOC(p.bdesc, sizeof(BlockDesc2) * (size_t)(nb + 4), "block descriptors");
+    cudaMemsetAsync(p.bvcoords, 0, sizeof(double) * (size_t)nb * vmax * dim + 64, s);
+    cudaMemsetAsync(p.bcc, 0, sizeof(uint32_t) * ((size_t)nb * cmaxp + 16), s);
+    cudaMemsetAsync(p.bdesc, 0, sizeof(BlockDesc2) * (size_t)(nb + 4), s);
+    block_vertices<true><<<(unsigned)nb, PLAN_THREADS, smv, s>>>(bcells, bcount, cmax, e->cell_coord, nc, dim, e->coords, kpv,
+                                                               vmax, nullptr, p.bvcoords, p.bcc, derr);
+    block_descriptors2<<<GRID(nb, 256), 256, 0, s>>>(bstart, nb, e->nrowptr, idx_off, meta_off, ncand, bcount, vcount, cmaxp,
+                                                    vmax, dim, G, p.bdesc);
+    cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, s);
+    cudaError_t ce = cudaStreamSynchronize(s);
+    if (ce != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+      fdts_set_error(std::string("gather plan 2 kernels failed: ") + cudaGetErrorString(ce));
+      rc = 2;
+      break;
+    }
+    if (herr) {
+      fdts_set_error("gather plan 2: internal inconsistency (code " + std::to_string(herr) + ")");
+      rc = 5;
+      break;
+    }
+    // ---- pattern dictionary: blocks with identical index lists share the first copy
+    p.unique_patterns = nb;
+    p.shared_idx = total;
+    if (e->opt_dedup) {
+      P2_ALLOC(hash_d, sizeof(uint64_t) * 2 * (size_t)nb, "pattern hashes");
+      P2_ALLOC(rep_d, sizeof(int64_t) * (size_t)nb, "pattern representatives");
+      block_hash<<<(unsigned)nb, PLAN_THREADS, 0, s>>>(p.bdesc, p.cidx, p.smeta, p.gdst, p.bcc, per_norm, hash_d);
+      std::vector<uint64_t> h(2 * (size_t)nb);
+      std::vector<BlockDesc2> hd((size_t)nb);
+      cudaMemcpyAsync(h.data(), hash_d, sizeof(uint64_t) * 2 * (size_t)nb, cudaMemcpyDeviceToHost, s);
+      cudaMemcpyAsync(hd.data(), p.bdesc, sizeof(BlockDesc2) * (size_t)nb, cudaMemcpyDeviceToHost, s);
+      if (cudaStreamSynchronize(s) != cudaSuccess) {
+        fdts_set_error("gather plan 2: hashing failed");
+        rc = 2;
+        break;
+      }
+      std::unordered_map<std::pair<uint64_t, uint64_t>, int64_t, PairHash> first;
+      first.reserve((size_t)nb);
+      std::vector<int64_t> rep((size_t)nb);
+      int64_t uniq = 0, shared = 0;
+      for (int64_t b = 0; b < nb; ++b) {
+        auto key = std::make_pair(h[2 * b], h[2 * b + 1]);
+        auto it = first.find(key);
+        if (it == first.end()) {
+          first.emplace(key, b);
+          rep[b] = b;
+          ++uniq;
+          shared += hd[b].nidx;
+        } else {
+          rep[b] = it->second;
+        }
+      }
+      cudaMemcpyAsync(rep_d, rep.data(), sizeof(int64_t) * (size_t)nb, cudaMemcpyHostToDevice, s);
+      apply_representatives<<<GRID(nb, 256), 256, 0, s>>>(p.bdesc, rep_d, nb);
+      if (cudaStreamSynchronize(s) != cudaSuccess) {
+        fdts_set_error("gather plan 2: applying the pattern dictionary failed");
+        rc = 2;
+        break;
+      }
+      p.unique_patterns = uniq;
+      p.shared_idx = shared;
+      if (e->opt_optimize && uniq <= 4096) {
+        std::vector<uint32_t> hm;
+        std::vector<uint16_t> hi;
+        bool ok = true;
+        for (int64_t b = 0; b < nb && ok; ++b) {
+          if (rep[b] != b || hd[b].nsl == 0 || hd[b].nidx == 0) continue;
+          hm.resize((size_t)hd[b].nsl);
+          hi.resize((size_t)hd[b].nidx);
+          ok = cudaMemcpy(hm.data(), p.smeta + hd[b].meta_off, sizeof(uint32_t) * hm.size(), cudaMemcpyDeviceToHost) == cudaSuccess &&
+               cudaMemcpy(hi.data(), p.cidx + hd[b].idx_off, sizeof(uint16_t) * hi.size(), cudaMemcpyDeviceToHost) == cudaSuccess;
+          if (!ok) break;
+          optimize_pattern(hd[b], hm.data(), hi.data(), p.zaddr);
+          ok = cudaMemcpy(p.cidx + hd[b].idx_off, hi.data(), sizeof(uint16_t) * hi.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+        }
+        if (!ok) {
+          fdts_set_error("gather plan 2: pattern optimisation failed");
+          rc = 2;
+          break;
+        }
+        p.optimized = 1;
+      }
+    }
+    p.ready = true;
+  } while (0);
+  void *scratch[] = {tmp, bstart, ncand, btotal, bnsl, idx_off, meta_off, dmax, imax, derr, bcount, vcount, bcells, cnt8,
+                     sellpos, hash_d, rep_d};
+  for (void *q : scratch)
+    if (q) cudaFree(q);
+  if (rc) fdts_free_plan2(e);
+  return rc;
+}

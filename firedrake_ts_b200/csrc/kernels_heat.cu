@@ -434,6 +434,277 @@ int launch_gather(int which, GArgs a, const GatherPlan &p, cudaStream_t s) {
   return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 
+// ------------------------------------------------------------------ path 2, plan version 2
+// Persistent owner-computes Jacobian gather over the sector-grouped SELL plan (gather_plan.cu, v2).
+//   phase A  element matrices of the block's cells -> shared memory (symmetric packing, odd stride);
+//   phase B  one flat, barrier-free sweep over the block's slices: lane l of a slice sums the staged
+//            contributions of one CSR slot (16-bit addresses, column-major => conflict-free index
+//            loads) and stores it itself; the 4 lanes of a lane group own one 32-byte sector, so
+//            every store instruction writes full sectors and every CSR value is written exactly once
+//            (no atomics, no zero-fill, no transposition buffer, bitwise reproducible).  Slots with
+//            more than 8 contributions (vertex diagonals) are summed by 4 lanes + 2 shuffles.
+// All inputs of a block arrive through TMA bulk copies issued one phase ahead: phase-B tables
+// (addresses, slice table, sector ids) while phase A computes, phase-A tables (vertex coordinates,
+// per-cell local vertex ids) of the next block while phase B sweeps.  With the pattern dictionary the
+// index tables of a structured mesh are a few hundred KB in total and stay L2 resident.
+struct G2Args {
+  const BlockDesc2 *bdesc;
+  const uint16_t *cidx, *gdst;
+  const uint32_t *smeta, *bcc;
+  const double *bvcoords;
+  double *out;
+  int64_t nblocks;
+  double shift;
+  int32_t off_idx, off_meta, off_gdst, off_vtab, off_lcc, off_bar, zaddr, sector;
+  int32_t dbg;  // development only: bit0 skips phase A, bit1 skips phase B (timing experiments; results are wrong)
+};
+
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+
+// sums W staged contributions of one slot; ip = shared address of the lane's first 32-bit pair of
+// 16-bit staging addresses (units of 8 bytes), sbase = shared address of the staging area
+template <int W>
+__device__ __forceinline__ double sum_columns(uint32_t ip, uint32_t sbase) {
+  uint32_t pr[(W + 1) / 2];
+#pragma unroll
+  for (int q = 0; q < (W + 1) / 2; ++q) pr[q] = lds_u32(ip + q * 128);
+  double v[W];
+#pragma unroll
+  for (int k = 0; k < W; ++k)
+    v[k] = lds_f64(__byte_perm(pr[k >> 1], 0u, (k & 1) ? 0x4432u : 0x4410u) * 8u + sbase);
+  if constexpr (W == 1) return v[0];
+  double a0 = v[0], a1 = v[1];
+#pragma unroll
+  for (int k = 2; k < W; ++k) {
+    if (k & 1) a1 += v[k]; else a0 += v[k];
+  }
+  return a0 + a1;
+}
+
+// reference tensors in the constant bank: the unrolled element kernel reads them as DFMA operands
+// (c[3][imm]) instead of materialising 64-bit immediates through the uniform datapath
+template <int DIM, int DEG, int VAR>
+struct HeatTab {
+  using T = RefT<DIM, DEG, VAR>;
+  double R00[T::ND][T::ND];
+  double S[T::NP][T::ND][T::ND];
+  constexpr HeatTab() : R00{}, S{} {
+    for (int i = 0; i < T::ND; ++i)
+      for (int j = 0; j < T::ND; ++j) {
+        R00[i][j] = T::R00[i][j];
+        for (int p = 0; p < T::NP; ++p) S[p][i][j] = T::S[p][i][j];
+      }
+  }
+};
+template <int DIM, int DEG, int VAR>
+__constant__ HeatTab<DIM, DEG, VAR> c_heat_tab{};
+
+template <int DIM, int DEG, int VAR, int I, int J, int NP>
+__device__ __forceinline__ double heat_entry_c(double m, const double (&gm)[NP]) {
+  using T = RefT<DIM, DEG, VAR>;
+  double v = 0.0;
+  constexpr double r = T::R00[I][J];
+  if constexpr (r != 0.0) v = m * c_heat_tab<DIM, DEG, VAR>.R00[I][J];
+  static_for<NP>([&](auto P) {
+    constexpr int p = decltype(P)::value;
+    constexpr double sv = T::S[p][I][J];
+    if constexpr (sv != 0.0) v = fma(gm[p], c_heat_tab<DIM, DEG, VAR>.S[p][I][J], v);
+  });
+  return v;
+}
+
+template <int DIM, int DEG, int VAR, int NT, int G>
+__global__ void __launch_bounds__(NT, NT <= 512 ? 2 : 1) heat_jacobian_gather2(const G2Args a) {
+  using T = RefT<DIM, DEG, VAR>;
+  constexpr int ND = T::ND, NP = T::NP, NEP = (ND * (ND + 1) / 2) | 1;
+  constexpr int NWARPS = NT / 32;
+  constexpr int LG = G == 4 ? 2 : (G == 2 ? 1 : 0), PER_NORM = 32 / G;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smraw + a.off_bar);
+  const uint32_t sbase = smem_u32(smraw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // per-thread shared addresses of the phase-B tables (slice `warp`), advanced by NWARPS slices per step
+  const uint32_t meta0 = sbase + a.off_meta + warp * 4;
+  const uint32_t idx0 = sbase + a.off_idx + lane * 4;
+  // lane -> (store group, slot inside the group); split slices use four lanes per slot
+  const uint32_t gd_norm0 = sbase + a.off_gdst + (warp * PER_NORM + (lane >> LG)) * 2;
+  const uint32_t gd_split0 = sbase + a.off_gdst + (warp * PER_NORM + (lane >> (LG + 2))) * 2;
+  const int sub_norm = lane & (G - 1), sub_split = (lane >> 2) & (G - 1);
+  const bool lead = (lane & 3) == 0;
+
+  auto issue_A = [&](const BlockDesc2 &d) {  // vertex table + local vertex ids
+    const uint32_t vb = (uint32_t)(((d.nvert * DIM + 1) & ~1) * 8);
+    const uint32_t cb = (uint32_t)(((d.ncell + 3) & ~3) * 4);
+    mbar_expect_tx(&bars[0], vb + cb);
+    if (vb) bulk_g2s(smraw + a.off_vtab, a.bvcoords + d.vc_off, vb, &bars[0]);
+    if (cb) bulk_g2s(smraw + a.off_lcc, a.bcc + d.cc_off, cb, &bars[0]);
+  };
+  auto issue_B = [&](const BlockDesc2 &d) {  // SELL addresses, slice table, sector ids
+    const uint32_t nslp = (uint32_t)((d.nsl + 3) & ~3);
+    const uint32_t ib = (uint32_t)d.nidx * 2u, mb = nslp * 4u, gb = nslp * 2u * (uint32_t)PER_NORM;
+    mbar_expect_tx(&bars[1], ib + mb + gb);
+    if (ib) bulk_g2s(smraw + a.off_idx, a.cidx + d.idx_off, ib, &bars[1]);
+    if (mb) bulk_g2s(smraw + a.off_meta, a.smeta + d.meta_off, mb, &bars[1]);
+    if (gb) bulk_g2s(smraw + a.off_gdst, a.gdst + d.meta_off * PER_NORM, gb, &bars[1]);
+  };
+
+  const int64_t stride = gridDim.x;
+  int64_t b = blockIdx.x;
+  if (b >= a.nblocks) return;
+  BlockDesc2 d = a.bdesc[b];
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    issue_A(d);
+  }
+  if (threadIdx.x < 16) sts_f64(sbase + (a.zaddr + threadIdx.x) * 8, 0.0);  // one staged zero per 8-byte bank
+  __syncthreads();
+  for (int it = 0; b < a.nblocks; ++it, b += stride) {
+    const int64_t bn = b + stride;
+    const bool more = bn < a.nblocks;
+    if (threadIdx.x == 0) issue_B(d);
+    const BlockDesc2 dn = a.bdesc[more ? bn : b];
+    // ---- phase A
+    mbar_wait(&bars[0], (uint32_t)(it & 1));
+    const int ncell = (a.dbg & 1) ? 0 : d.ncell;
+    for (int k = threadIdx.x; k < ncell; k += NT) {
+      const uint32_t packed = lds_u32(sbase + a.off_lcc + k * 4);
+      double X[DIM + 1][DIM];
+#pragma unroll
+      for (int v = 0; v <= DIM; ++v) {
+        const uint32_t va = sbase + a.off_vtab + ((packed >> (8 * v)) & 255u) * (DIM * 8);
+#pragma unroll
+        for (int q = 0; q < DIM; ++q) X[v][q] = lds_f64(va + q * 8);
+      }
+      Geom<DIM> g;
+      geometry_from_vertices<DIM>(X, g);
+      double gm[NP];
+      metric<DIM>(g, gm);
+      const double m = a.shift * g.adet;
+      const uint32_t st = sbase + k * (NEP * 8);
+      static_for<ND>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        static_for<ND - i>([&](auto JJ) {
+          constexpr int j = i + decltype(JJ)::value;
+          constexpr int e = i * ND - (i * (i - 1)) / 2 + (j - i);
+          sts_f64(st + e * 8, heat_entry<T, i, j, NP>(m, gm));
+        });
+      });
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && more) issue_A(dn);
+    // ---- phase B
+    mbar_wait(&bars[1], (uint32_t)(it & 1));
+    double *__restrict__ out = a.out + (d.s0 - d.s_align);
+    const uint32_t lo = (uint32_t)d.s_align, span = (uint32_t)d.nslots;
+    const int nsl = (a.dbg & 2) ? 0 : d.nsl;
+    uint32_t mp = meta0, gn = gd_norm0, gp = gd_split0;
+    for (int sl = warp; sl < nsl; sl += NWARPS, mp += NWARPS * 4, gn += NWARPS * PER_NORM * 2, gp += NWARPS * PER_NORM * 2) {
+      const uint32_t meta = lds_u32(mp);
+      const uint32_t w = (meta >> 16) & 0xffu;
+      const bool split = meta >= 0x1000000u;
+      const uint32_t gs = lds_u16(split ? gp : gn);
+      const uint32_t ip = idx0 + (meta & 0xffffu) * 128u;
+      double acc;
+      switch (w) {
+        case 0: acc = 0.0; break;
+        case 1: acc = sum_columns<1>(ip, sbase); break;
+        case 2: acc = sum_columns<2>(ip, sbase); break;
+        case 3: acc = sum_columns<3>(ip, sbase); break;
+        case 4: acc = sum_columns<4>(ip, sbase); break;
+        case 5: acc = sum_columns<5>(ip, sbase); break;
+        case 6: acc = sum_columns<6>(ip, sbase); break;
+        case 7: acc = sum_columns<7>(ip, sbase); break;
+        case 8: acc = sum_columns<8>(ip, sbase); break;
+        default: {
+          double a0 = 0.0, a1 = 0.0;
+          for (uint32_t q = 0; 2 * q < w; ++q) {
+            const uint32_t pr = lds_u32(ip + q * 128);
+            a0 += lds_f64(sbase + (pr & 0xffffu) * 8u);
+            if (2 * q + 1 < w) a1 += lds_f64(sbase + (pr >> 16) * 8u);
+          }
+          acc = a0 + a1;
+        }
+      }
+      uint32_t slot = gs * G + sub_norm;
+      bool wr = true;
+      if (split) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        slot = gs * G + sub_split;
+        wr = lead;
+      }
+      // sector id 0xffff (no sector) lands far outside [lo, lo + span)
+      if (wr && slot - lo < span) out[slot] = acc;
+    }
+    __syncthreads();
+    d = dn;
+  }
+}
+
+template <int DIM, int DEG, int VAR, int NT>
+int launch_gather2_nt(G2Args a, const GatherPlan2 &p, cudaStream_t s) {
+  using T = RefT<DIM, DEG, VAR>;
+  constexpr int ND = T::ND, NEP = (ND * (ND + 1) / 2) | 1;
+  auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  if (p.nep != NEP) return 3;
+  size_t off = up16(sizeof(double) * ((size_t)p.zaddr + 16));
+  a.off_idx = (int)off;
+  off += up16(2 * (size_t)p.max_nidx + 64);
+  a.off_meta = (int)off;
+  off += up16(4 * (size_t)p.max_nsl + 16);
+  a.off_gdst = (int)off;
+  off += up16(2 * (size_t)(32 / p.sector) * (size_t)p.max_nsl + 16);
+  a.sector = p.sector;
+  a.off_vtab = (int)off;
+  off += up16(8 * (size_t)p.vmax * DIM + 16);
+  a.off_lcc = (int)off;
+  off += up16(4 * (size_t)p.cmax + 16);
+  a.off_bar = (int)off;
+  off += 32;
+  a.zaddr = p.zaddr;
+  const size_t smem = off;
+  if (smem > 227 * 1024) return 4;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  auto launch = [&](auto kern) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem) != cudaSuccess || occ < 1) occ = 1;
+    const int64_t slots = (int64_t)sms * occ;
+    const int64_t grid = p.nblocks < slots ? p.nblocks : slots;
+    kern<<<(unsigned)grid, NT, smem, s>>>(a);
+    return cudaGetLastError() == cudaSuccess ? 0 : 2;
+  };
+  if (p.sector == 4) return launch(heat_jacobian_gather2<DIM, DEG, VAR, NT, 4>);
+  if (p.sector == 2) return launch(heat_jacobian_gather2<DIM, DEG, VAR, NT, 2>);
+  return launch(heat_jacobian_gather2<DIM, DEG, VAR, NT, 1>);
+}
+
+template <int DIM, int DEG, int VAR>
+int launch_gather2(G2Args a, const GatherPlan2 &p, int threads, cudaStream_t s) {
+  if (threads == 512) return launch_gather2_nt<DIM, DEG, VAR, 512>(a, p, s);
+  return launch_gather2_nt<DIM, DEG, VAR, 1024>(a, p, s);
+}
+
 __global__ void set_values_k(double *__restrict__ v, const int64_t *__restrict__ slots, int64_t n, double val) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n && slots[t] >= 0) v[slots[t]] = val;
@@ -482,7 +753,40 @@ int fdts_launch_heat(fdts_engine *e, int which, const double *x, const double *x
   }
   KArgs a = fdts_make_kargs(e, x, xdot, shift, out, c0, c1);
   const int dim = e->cfg.dim, deg = e->cfg.degree, var = e->variant;
-  if (e->opt_scatter == 2 && (which == 1 || e->opt_gather_residual)) {
+  if (e->opt_scatter == 2 && var < 0) {
+    fdts_set_error("closed-form heat path: run-time reference tensors do not match the compiled tables");
+    return 3;
+  }
+  if (e->opt_scatter == 2 && which == 1 && !e->plan2.ready && !e->plan.ready) {
+    fdts_set_error("gather path requested but no gather plan is built (fdts_set_row_blocks)");
+    return 3;
+  }
+  if (e->opt_scatter == 2 && which == 1 && e->plan2.ready) {
+    const GatherPlan2 &p = e->plan2;
+    G2Args g;
+    g.bdesc = p.bdesc; g.cidx = p.cidx; g.gdst = p.gdst; g.smeta = p.smeta; g.bcc = p.bcc; g.bvcoords = p.bvcoords;
+    g.out = out; g.nblocks = p.nblocks; g.shift = shift; g.dbg = (int32_t)e->opt_debug;
+    int rc = 3;
+#define G2CASE(D, K, V) \
+  if (dim == D && deg == K && (K < 3 || var == V)) rc = launch_gather2<D, K, V>(g, p, (int)e->opt_threads, s);
+    G2CASE(1, 1, 1) G2CASE(1, 2, 1) G2CASE(1, 3, 0) G2CASE(1, 3, 1)
+    G2CASE(2, 1, 1) G2CASE(2, 2, 1) G2CASE(2, 3, 0) G2CASE(2, 3, 1)
+    G2CASE(3, 1, 1) G2CASE(3, 2, 1) G2CASE(3, 3, 0) G2CASE(3, 3, 1)
+#undef G2CASE
+    if (rc == 4) fdts_set_error("gather path: a row block needs more shared memory than one SM has (use smaller row blocks)");
+    if (rc == 3) fdts_set_error("gather path: unsupported dimension/degree");
+    if (rc == 2) fdts_set_error(std::string("gather kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    if (rc) return rc;
+    e->launches++;
+    if (e->cfg.num_bc_nodes > 0) {
+      const int64_t n = e->cfg.num_bc_nodes;
+      set_values_k<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, e->bc_diag_slot, n, 1.0);
+      e->launches++;
+    }
+    FDTS_CHECK(cudaGetLastError());
+    return 0;
+  }
+  if (e->opt_scatter == 2 && (which == 1 || e->opt_gather_residual) && e->plan.ready) {
     if (!e->plan.ready) {
       fdts_set_error("gather path requested but no gather plan is built (fdts_set_row_blocks)");
       return 3;

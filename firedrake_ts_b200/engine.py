@@ -111,7 +111,7 @@ class Engine:
     / ``_assemble_jac`` of the reference's ``_TSContext``,
     firedrake_ts/solving_utils.py:258,305)."""
 
-    def __init__(self, form, bcs=(), device=None, scatter=None):
+    def __init__(self, form, bcs=(), device=None, scatter=None, plan_version=None, dedup=None, options=None):
         if not torch.cuda.is_available():
             raise EngineError("no CUDA device: the B200 assembly engine has no CPU fallback")
         lib = load_library()
@@ -157,6 +157,12 @@ class Engine:
         self.max_row_nodes, self.max_degree = s.max_row_nodes, s.reserved
         self.num_cells, self.num_interior_cells = m.num_cells, m.num_interior_cells
         self._lib = lib
+        if plan_version is not None:
+            self.set_option("plan_version", plan_version)
+        if dedup is not None:
+            self.set_option("dedup", dedup)
+        for k, v in (options or {}).items():  # plan options must be set before the plan is built
+            self.set_option(k, v)
         if scatter is not None:
             if int(scatter) == 2:
                 starts = V.row_block_starts()

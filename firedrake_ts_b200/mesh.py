@@ -60,21 +60,35 @@ def _tile_sizes(n, tile, offset):
     return out
 
 
+def _tile_tuple(tile, dim):
+    """normalise a tile spec (None, int or per-dimension sequence) to a tuple of ints (0 = untiled)."""
+    if tile is None:
+        return (0,) * dim
+    if isinstance(tile, (int, np.integer)):
+        return (max(int(tile), 0),) * dim
+    t = tuple(max(int(x), 0) for x in tile)
+    assert len(t) == dim, "tile must be an int or one entry per dimension"
+    if any(x == 0 for x in t):
+        return (0,) * dim
+    return t
+
+
 def _tiled_index(p, dims, tile, offset=0):
     """Bijective numbering of the integer box prod(range(dims[a])) that walks
-    tile by tile (tile edge ``tile``; tile boundaries at offset + k*tile; first
+    tile by tile (tile edges ``tile[a]``; tile boundaries at offset + k*tile[a]; first
     and last tiles ragged), x fastest inside a tile.  ``p``: (..., dim) int64
     tensor.  tile <= 0 means lexicographic."""
     dim = len(dims)
-    if tile is None or tile <= 0:
+    tt = _tile_tuple(tile, dim)
+    if tt[0] <= 0:
         idx = p[..., dim - 1]
         for a in range(dim - 2, -1, -1):
             idx = idx * dims[a] + p[..., a]
         return idx
-    T = int(tile)
-    sh = (T - int(offset) % T) % T  # shift so that tiles are uniform on x' = x + sh
     start, l, s = [], [], []
     for a in range(dim):
+        T = tt[a]
+        sh = (T - int(offset) % T) % T  # shift so that tiles are uniform on x' = x + sh
         xs = p[..., a] + sh
         t = torch.div(xs, T, rounding_mode="floor")
         st = torch.clamp(t * T, min=sh)
@@ -161,7 +175,7 @@ class SimplexMesh:
         assert not self.periodic or self.dim == 1, "periodic meshes: 1-D only"
         self.partition = partition or Partition((1,) * self.dim, 0)
         assert not (self.periodic and self.partition.size > 1)
-        self.tile = int(tile)
+        self.tile = _tile_tuple(tile, len(self.shape))
         self.device = torch.device(device)
         dim = self.dim
         pc = self.partition.coords_of(self.partition.rank)
@@ -183,8 +197,7 @@ class SimplexMesh:
         axes = [torch.arange(dims[a], device=dev, dtype=torch.int64) for a in range(dim)]
         grids = torch.meshgrid(*axes, indexing="ij")
         p = torch.stack([g.reshape(-1) for g in grids], dim=-1)  # local cube coords
-        ct = max(self.tile, 0)
-        key = _tiled_index(p, dims, ct)
+        key = _tiled_index(p, dims, self.tile)
         p = p[torch.argsort(key)]
         cube = p + torch.tensor(self.box_lo, device=dev, dtype=torch.int64)
         # a cube touches ghost nodes iff it lies in the halo layer or at the
@@ -213,8 +226,7 @@ class SimplexMesh:
         lo = torch.tensor(self.box_lo, device=dev, dtype=torch.int64)
         vdims = [self.box_hi[a] - self.box_lo[a] + 1 for a in range(dim)]
         self._vdims = vdims
-        vt = max(self.tile, 0)
-        self.cell_coord_map = _tiled_index(self.cell_vlat - lo, vdims, vt).to(torch.int32).contiguous()
+        self.cell_coord_map = _tiled_index(self.cell_vlat - lo, vdims, self.tile).to(torch.int32).contiguous()
         nv = int(np.prod(vdims))
         self.num_coord_nodes = nv
         coords = torch.zeros((nv, dim), dtype=torch.float64, device=dev)
@@ -247,7 +259,7 @@ class FunctionSpace:
         assert layout in ("interleaved", "blocked")
         self.mesh, self.degree, self.ncomp, self.layout, self.variant = mesh, degree, ncomp, layout, variant
         self.dim = mesh.dim
-        self.tile = mesh.tile * degree if tile is None else int(tile)
+        self.tile = (tuple(t * degree for t in mesh.tile) if tile is None else _tile_tuple(tile, mesh.dim))
         self.tile_offset = int(tile_offset)
         self.nd = fem.num_nodes(self.dim, degree)
         self._build()
@@ -469,9 +481,9 @@ class FunctionSpace:
         in the numbering): int64 tensor of nblocks+1 offsets.  The gather kernels
         use them as row blocks (one CTA per tile)."""
         dims = [self.owned_hi[a] - self.owned_lo[a] for a in range(self.dim)]
-        if self.tile <= 0:
+        if self.tile[0] <= 0:
             return None
-        per_dim = [_tile_sizes(dims[a], self.tile, self.tile_offset) for a in range(self.dim)]
+        per_dim = [_tile_sizes(dims[a], self.tile[a], self.tile_offset) for a in range(self.dim)]
         sizes = torch.tensor(per_dim[self.dim - 1], dtype=torch.int64)
         # order: slowest dimension outermost; tile (t_{d-1}, ..., t_0) has prod of sizes
         out = torch.ones(1, dtype=torch.int64)

@@ -41,40 +41,73 @@ def test_engine_matches_oracle(family, dim, degree, n, tile):
     shift = 10.0
     Fo = orc.ifunction(0.0, u.data, udot.data)
     Jo = orc.ijacobian(0.0, u.data, udot.data, shift)
-    for path in paths:  # 0: generic quadrature, 1: closed form + atomics, 2: closed form + owner-computes gather
+    # 0: generic quadrature, 1: closed form + atomics, 2: closed form + owner-computes gather (plan 1 / plan 2)
+    for path, plan in [(p, 0) for p in paths if p < 2] + ([(2, 1), (2, 2)] if 2 in paths else []):
         if path == 2:
             starts = form.space.row_block_starts()
             if starts is None:
                 starts = torch.unique(torch.arange(0, eng.num_rows + 50, 50).clamp(max=eng.num_rows))
+            eng.set_option("plan_version", plan)
             eng.set_row_blocks(starts)
+            assert eng.get_option("plan_version") == plan
             eng.set_option("gather_residual", 1)
         eng.set_option("scatter", path)
         F = eng.ifunction(0.0, x, xd).cpu().numpy()
-        assert rel_err(F, Fo) < TOL, (path, rel_err(F, Fo))
+        assert rel_err(F, Fo) < TOL, (path, plan, rel_err(F, Fo))
         Jv = eng.ijacobian(0.0, x, xd, shift).cpu().numpy()
-        assert rel_err(Jv, Jo) < TOL, (path, rel_err(Jv, Jo))
+        assert rel_err(Jv, Jo) < TOL, (path, plan, rel_err(Jv, Jo))
     assert eng.launch_count > 0
 
 
+@pytest.mark.parametrize("plan", [1, 2])
 @pytest.mark.parametrize("dim,degree,n,ftile,foffset", [(3, 2, 6, 5, 1), (3, 2, 5, 6, 0), (2, 2, 9, 5, 1), (3, 1, 7, 3, 1),
-                                                        (3, 3, 3, 4, 1), (2, 3, 5, 7, 2), (1, 2, 20, 5, 1)])
-def test_gather_path_tiled_numbering(dim, degree, n, ftile, foffset):
-    """owner-computes gather (write-once, deterministic) on tile-numbered spaces with offset tiles;
-    also checks run-to-run bitwise reproducibility."""
+                                                        (3, 3, 3, 4, 1), (2, 3, 5, 7, 2), (1, 2, 20, 5, 1),
+                                                        (3, 2, 8, (8, 6, 4), 0), (3, 2, 7, (4, 6, 8), 3),
+                                                        (2, 2, 12, (8, 4), 0)])
+def test_gather_path_tiled_numbering(dim, degree, n, ftile, foffset, plan):
+    """owner-computes gather (write-once, deterministic) on tile-numbered spaces with offset and
+    anisotropic tiles, both plan versions; also checks run-to-run bitwise reproducibility."""
     from firedrake_ts_b200.engine import Engine
     from oracle import Oracle
 
     form, bcs, u, udot = make_problem("heat", dim, degree, n, tile=2, ftile=ftile, foffset=foffset)
     orc = Oracle.from_form(form, bcs)
-    eng = Engine(form, bcs, device="cuda:0", scatter=2)
+    eng = Engine(form, bcs, device="cuda:0", scatter=2, plan_version=plan)
     eng.set_option("gather_residual", 1)
     assert eng.get_option("scatter") == 2 and eng.get_option("plan_blocks") > 0
+    assert eng.get_option("plan_version") == plan
     x, xd = u.data.cuda(), udot.data.cuda()
     J1 = eng.ijacobian(0.0, x, xd, 7.5)
     J2 = eng.ijacobian(0.0, x, xd, 7.5)
     assert torch.equal(J1, J2)
     F1 = eng.ifunction(0.0, x, xd)
     F2 = eng.ifunction(0.0, x, xd)
-    assert torch.equal(F1, F2)
+    if plan == 1:  # plan 2 has no residual lists: the residual stays on the atomic path (order not fixed)
+        assert torch.equal(F1, F2)
     assert rel_err(J1.cpu().numpy(), orc.ijacobian(0.0, u.data, udot.data, 7.5)) < TOL
     assert rel_err(F1.cpu().numpy(), orc.ifunction(0.0, u.data, udot.data)) < TOL
+
+
+@pytest.mark.parametrize("n,ftile", [(12, (8, 6, 4)), (13, 6)])
+def test_pattern_dictionary(n, ftile):
+    """plan 2: blocks with identical index lists share one copy; sharing must not change any value
+    (bitwise) and must actually find the repeated interior blocks of a structured mesh."""
+    from firedrake_ts_b200.engine import Engine
+
+    mt = tuple(t // 2 for t in ftile) if isinstance(ftile, tuple) else ftile // 2
+    form, bcs, u, udot = make_problem("heat", 3, 2, n, tile=mt, ftile=ftile)
+    x, xd = u.data.cuda(), udot.data.cuda()
+    e1 = Engine(form, bcs, device="cuda:0", scatter=2, plan_version=2, dedup=1, options={"optimize": 0})
+    e0 = Engine(form, bcs, device="cuda:0", scatter=2, plan_version=2, dedup=0)
+    nb = e1.get_option("plan_blocks")
+    assert e0.get_option("plan_patterns") == nb
+    assert e1.get_option("plan_patterns") < nb
+    assert e1.get_option("plan_shared_contributions") < e1.get_option("plan_contributions")
+    J0 = e0.ijacobian(0.0, x, xd, 10.0)
+    assert torch.equal(e1.ijacobian(0.0, x, xd, 10.0), J0)
+    # bank-conflict-aware column order and 16-byte store groups only change the summation order
+    for opts in ({"optimize": 1}, {"optimize": 1, "sector": 2}, {"optimize": 0, "sector": 2}):
+        e2 = Engine(form, bcs, device="cuda:0", scatter=2, plan_version=2, dedup=1, options=opts)
+        J2 = e2.ijacobian(0.0, x, xd, 10.0)
+        assert rel_err(J2.cpu().numpy(), J0.cpu().numpy()) < TOL
+        assert torch.equal(J2, e2.ijacobian(0.0, x, xd, 10.0))

@@ -16,28 +16,47 @@ ap.add_argument("--family", default="heat")
 ap.add_argument("--dim", type=int, default=3)
 ap.add_argument("--degree", type=int, default=2)
 ap.add_argument("-n", type=int, default=184)
-ap.add_argument("--tile", type=int, default=4)
+ap.add_argument("--tile", default="4")
 ap.add_argument("--scatter", type=int, default=0)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--peak", action="store_true")
-ap.add_argument("--ftile", type=int, default=None)
+ap.add_argument("--ftile", default=None)
+ap.add_argument("--plan", type=int, default=2)
+ap.add_argument("--debug", type=int, default=0)
+ap.add_argument("--sector", type=int, default=4)
+ap.add_argument("--optimize", type=int, default=1)
+ap.add_argument("--threads", type=int, default=1024)
+ap.add_argument("--dedup", type=int, default=1)
 ap.add_argument("--foffset", type=int, default=0)
 a = ap.parse_args()
 
 if a.peak:
     print("fp64 DFMA GFLOP/s", measure_fp64_peak(0, False), "DMMA GFLOP/s", measure_fp64_peak(0, True), flush=True)
 t0 = time.time()
-form, bcs, u, udot = make_problem(a.family, a.dim, a.degree, a.n, tile=a.tile, device="cuda:0", ftile=a.ftile,
-                                  foffset=a.foffset)
+def _tile(v):
+    if v is None:
+        return None
+    t = tuple(int(x) for x in str(v).split(","))
+    return t[0] if len(t) == 1 else t
+
+
+form, bcs, u, udot = make_problem(a.family, a.dim, a.degree, a.n, tile=_tile(a.tile), device="cuda:0",
+                                  ftile=_tile(a.ftile), foffset=a.foffset)
 torch.cuda.synchronize()
 print("mesh+space", time.time() - t0, "s; cells", form.space.mesh.num_cells, "dofs", form.space.num_dofs, flush=True)
 t0 = time.time()
-eng = Engine(form, bcs, scatter=a.scatter)
+eng = Engine(form, bcs, scatter=a.scatter, plan_version=a.plan, dedup=a.dedup,
+             options={"sector": a.sector, "optimize": a.optimize, "threads": a.threads})
 torch.cuda.synchronize()
 print("engine create", time.time() - t0, "s; nnz", eng.nnz, "maxrow", eng.max_row_nodes, "maxdeg", eng.max_degree, flush=True)
 if a.scatter == 2:
-    print("plan: blocks", eng.get_option("plan_blocks"), "cells_max", eng.get_option("plan_cells_max"), "contrib", eng.get_option("plan_contributions"), flush=True)
+    print("plan: version", eng.get_option("plan_version"), "blocks", eng.get_option("plan_blocks"), "cells_max",
+          eng.get_option("plan_cells_max"), "contrib", eng.get_option("plan_contributions"), "patterns",
+          eng.get_option("plan_patterns"), "shared contrib", eng.get_option("plan_shared_contributions"),
+          "vmax", eng.get_option("plan_vertices_max"), flush=True)
 x, xd = u.data, udot.data
+if a.debug:
+    eng.set_option("debug", a.debug)
 F = torch.empty(eng.num_rows, dtype=torch.float64, device="cuda")
 J = eng.new_values()
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
