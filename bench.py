@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--cpu-n", type=int, default=40, help="mesh size of the bounded CPU-baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-nodict", action="store_true")
     return ap.parse_args()
 
 
@@ -289,12 +290,29 @@ def run_b200(a):
         tj = json.load(open(tpath))
         key = f"n{a.n}_p{a.degree}_g{world}"
         traffic = tj.get(key)
-    roofline = {"bound": "hbm", "kernel": "IJacobian (heat_jacobian_gather_persist)", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": "IJacobian (heat_jacobian_gather2)", "achieved": achieved,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": b_ij, "ms_per_launch": t_ij,
                 "pair": {"algorithmic_bytes": b_if + b_ij, "achieved": (b_if + b_ij) / (ms_per_step * 1e-3) / 1e9,
                          "frac": (b_if + b_ij) / (ms_per_step * 1e-3) / 1e9 / peak},
                 "ifunction": {"algorithmic_bytes": b_if, "ms": t_if, "frac": b_if / (t_if * 1e-3) / 1e9 / peak}}
+
+    # the same Jacobian with the pattern dictionary switched off: every row block reads its own index
+    # lists from HBM, which is what an unstructured mesh (no repeated blocks) would do
+    if world == 1 and ftile and not a.no_nodict:
+        eng_nd = Engine(form, bcs, device=dev, scatter=2, dedup=0)
+        for _ in range(2):
+            eng_nd.ijacobian(0.0, x, xd, shift, out=J)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            eng_nd.ijacobian(0.0, x, xd, shift, out=J)
+        e1.record()
+        torch.cuda.synchronize()
+        roofline["ijacobian_no_dictionary"] = {"ms": e0.elapsed_time(e1) / 5, "index_bytes_per_launch":
+                                               2 * eng_nd.get_option("plan_contributions")}
+        del eng_nd
+        torch.cuda.empty_cache()
 
     # end-to-end through the host-buffer C ABI (single rank only: host Vec/Mat of one process)
     e2e = None
@@ -329,7 +347,9 @@ def run_b200(a):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a.n, a.degree), "partition": "x".join(map(str, M.default_grid(world, 3))),
                        "l2": "inputs >> L2 (126 MB), no flush", "scatter": "closed-form residual + atomics, "
-                       "owner-computes gather Jacobian", "shift": shift},
+                       "owner-computes gather Jacobian (plan 2: sector SELL + pattern dictionary)", "shift": shift,
+                       "row_blocks": eng.get_option("plan_blocks") if ftile else 0,
+                       "index_patterns": eng.get_option("plan_patterns") if ftile else 0},
             "ms_ifunction": t_if, "ms_ijacobian": t_ij,
             "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": int(launches),
             "checksum": {"sum_F": chk[0], "sum_absF": chk[1], "sum_J": chk[2], "sum_absJ": chk[3]},

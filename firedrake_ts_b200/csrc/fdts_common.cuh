@@ -51,16 +51,20 @@ struct BlockDesc {              // 48 bytes, one per row block
 // that sum a sector also store it (full-sector writes, no transposition buffer, no barriers inside the
 // sweep).  Slots with more than SPLIT_CAP contributions are summed by 4 lanes each ("split" slices).
 // Blocks whose index lists are identical share one copy (pattern dictionary).
-struct BlockDesc2 {             // 64 bytes, one per row block
+struct BlockDesc2 {             // 80 bytes, one per row block
   int64_t s0;                   // first node-level CSR slot of the block
   int64_t idx_off;              // first entry of the block's pattern in cidx (uint16 units, multiple of 64)
-  int64_t meta_off;             // first slice of the pattern in smeta (multiple of 4); gdst holds 32/sector per slice
+  int64_t meta_off;             // first slice of the pattern in gdst (multiple of 4 slices; 32/sector ids per slice)
   int64_t cc_off;               // first entry of the pattern in bcc (multiple of 4)
   int64_t vc_off;               // first coordinate of the block's vertex table in bvcoords
-  int32_t nslots, nidx;         // CSR slots of the block; SELL entries (multiple of 32)
+  int64_t cls_off;              // first class of the pattern in cmeta (multiple of PLAN2_MAX_CLASSES)
+  int32_t nslots, nidx;         // CSR slots of the block; SELL entries (multiple of 64)
   int32_t ncell, nvert;
-  int32_t nsl, s_align;         // slices; s0 & 3
+  int32_t nsl, ncls;            // slices; slice classes (runs of slices with equal width / split flag)
+  int32_t pad0, pad1;
 };
+constexpr int PLAN2_MAX_CLASSES = 32;
+// slice class (8 bytes): lo = first slice | count << 16, hi = first offset (units of 64 entries) | width << 16 | split << 24
 
 struct GatherPlan2 {
   bool ready = false;
@@ -69,7 +73,7 @@ struct GatherPlan2 {
   int32_t max_nidx = 0, max_nsl = 0;  // per-block maxima (max_nsl padded to 4)
   int32_t sector = 4;           // slots per store group: 4 = 32-byte sectors, 2 = 16-byte half sectors
   uint16_t *cidx = nullptr;     // staged element-matrix addresses, SELL order
-  uint32_t *smeta = nullptr;    // per slice: (offset/64) | width << 16 | split << 24
+  uint2 *cmeta = nullptr;       // per block: PLAN2_MAX_CLASSES slice classes
   uint16_t *gdst = nullptr;     // per slice: 32/sector block-local sector ids (0xffff = none)
   uint32_t *bcc = nullptr;      // per cell: (dim+1) block-local vertex ids, one byte each
   double *bvcoords = nullptr;   // per block: vmax x dim vertex coordinates

@@ -633,7 +633,8 @@ __global__ void __launch_bounds__(PLAN_THREADS) sell2_layout(const int64_t *__re
                                                              const int64_t *__restrict__ nrp,
                                                              const uint8_t *__restrict__ cnt8, int G,
                                                              const int64_t *__restrict__ meta_off,
-                                                             uint32_t *__restrict__ smeta, uint16_t *__restrict__ gdst,
+                                                             uint2 *__restrict__ cmeta, int32_t *__restrict__ bncls,
+                                                             uint16_t *__restrict__ gdst,
                                                              uint32_t *__restrict__ sellpos,
                                                              int64_t *__restrict__ btotal, int64_t *__restrict__ bnsl,
                                                              int *__restrict__ err) {
@@ -703,22 +704,39 @@ __global__ void __launch_bounds__(PLAN_THREADS) sell2_layout(const int64_t *__re
   auto width_of = [&](uint32_t key) { return (int)((0x1ff - (key >> 16)) & 0xff); };
   if (threadIdx.x == 0) {
     uint32_t run = 0;
+    int ncls = 0, cfirst = 0;
+    uint32_t ckey = 0xffffffffu, coff = 0;
+    auto flush = [&](int jend) {
+      if (ckey == 0xffffffffu) return;
+      if (WRITE && ncls < PLAN2_MAX_CLASSES)
+        cmeta[b * PLAN2_MAX_CLASSES + ncls] =
+            make_uint2((uint32_t)cfirst | ((uint32_t)(jend - cfirst) << 16), (coff >> 6) | ((ckey & 0xffu) << 16) | ((ckey >> 8) << 24));
+      ++ncls;
+    };
     for (int j = 0; j < nsl; ++j) {
       woff[j] = run;
-      run += slice_entries(width_of(keys[first_sector(j)]));
+      const int wj = width_of(keys[first_sector(j)]);
+      const uint32_t key = (uint32_t)wj | (j < nslA ? 0x100u : 0u);
+      if (key != ckey) {
+        flush(j);
+        ckey = key;
+        cfirst = j;
+        coff = run;
+      }
+      run += slice_entries(wj);
     }
+    flush(nsl);
     woff[nsl] = run;
     btotal[b] = run;
     bnsl[b] = WRITE ? nsl : ((nsl + 3) & ~3);
     if ((run >> 6) > 65535u) atomicExch(err, 8);
+    if (ncls > PLAN2_MAX_CLASSES) atomicExch(err, 9);
+    if (WRITE) bncls[b] = ncls;
   }
   if (!WRITE) return;
   __syncthreads();
   const int64_t mo = meta_off[b];
   for (int j = threadIdx.x; j < ((nsl + 3) & ~3); j += PLAN_THREADS) {
-    uint32_t m = 0;
-    if (j < nsl) m = (woff[j] >> 6) | ((uint32_t)width_of(keys[first_sector(j)]) << 16) | (j < nslA ? 1u << 24 : 0u);
-    smeta[mo + j] = m;
     for (int g = 0; g < per_norm; ++g) {
       uint16_t v = 0xffff;
       if (j < nslA) {
@@ -797,9 +815,9 @@ __global__ void slot_contributions2(const int64_t *__restrict__ bstart, const in
 
 __global__ void block_descriptors2(const int64_t *__restrict__ bstart, int64_t nb, const int64_t *__restrict__ nrp,
                                    const int64_t *__restrict__ idx_off, const int64_t *__restrict__ meta_off,
-                                   const int64_t *__restrict__ bnsl_true, const int32_t *__restrict__ bcount,
-                                   const int32_t *__restrict__ vcount, int cmaxp, int vmax, int dim, int G,
-                                   BlockDesc2 *__restrict__ d) {
+                                   const int64_t *__restrict__ bnsl_true, const int32_t *__restrict__ bncls,
+                                   const int32_t *__restrict__ bcount, const int32_t *__restrict__ vcount, int cmaxp,
+                                   int vmax, int dim, BlockDesc2 *__restrict__ d) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   BlockDesc2 x;
@@ -813,7 +831,9 @@ __global__ void block_descriptors2(const int64_t *__restrict__ bstart, int64_t n
   x.ncell = bcount[b];
   x.nvert = vcount[b];
   x.nsl = (int32_t)bnsl_true[b];
-  x.s_align = (int32_t)(x.s0 & (G - 1));
+  x.ncls = bncls[b];
+  x.cls_off = b * (int64_t)PLAN2_MAX_CLASSES;
+  x.pad0 = x.pad1 = 0;
   d[b] = x;
 }
 
@@ -827,15 +847,15 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
 // 128-bit content hash of a block's pattern (position-keyed, order-independent sum => parallel)
 __global__ void __launch_bounds__(PLAN_THREADS) block_hash(const BlockDesc2 *__restrict__ d,
                                                            const uint16_t *__restrict__ cidx,
-                                                           const uint32_t *__restrict__ smeta,
-                                                           const uint16_t *__restrict__ gdst,
+                                                           const uint2 *__restrict__ cmeta,
+                                                           const uint16_t *__restrict__ gdst, int G,
                                                            const uint32_t *__restrict__ bcc, int per_norm,
                                                            uint64_t *__restrict__ hash2) {
   __shared__ unsigned long long h0, h1;
   const BlockDesc2 x = d[blockIdx.x];
   if (threadIdx.x == 0) {
     h0 = mix64(((uint64_t)x.nslots << 32) ^ (uint64_t)x.nidx) + mix64(((uint64_t)x.ncell << 32) ^ (uint64_t)x.nvert ^ 0x51ull << 60);
-    h1 = mix64(((uint64_t)x.nsl << 32) ^ (uint64_t)x.s_align ^ 0x7ull << 58);
+    h1 = mix64(((uint64_t)x.nsl << 32) ^ (uint64_t)(x.s0 & (G - 1)) ^ ((uint64_t)x.ncls << 8) ^ 0x7ull << 58);
   }
   __syncthreads();
   uint64_t a0 = 0, a1 = 0;
@@ -846,7 +866,10 @@ __global__ void __launch_bounds__(PLAN_THREADS) block_hash(const BlockDesc2 *__r
   };
   for (int t = threadIdx.x; t < x.nidx; t += PLAN_THREADS) add(1, t, cidx[x.idx_off + t]);
   const int nslp = (x.nsl + 3) & ~3;
-  for (int t = threadIdx.x; t < nslp; t += PLAN_THREADS) add(2, t, smeta[x.meta_off + t]);
+  for (int t = threadIdx.x; t < x.ncls; t += PLAN_THREADS) {
+    const uint2 c = cmeta[x.cls_off + t];
+    add(2, t, ((uint64_t)c.y << 32) | c.x);
+  }
   for (int t = threadIdx.x; t < nslp * per_norm; t += PLAN_THREADS) add(3, t, gdst[x.meta_off * per_norm + t]);
   for (int t = threadIdx.x; t < x.ncell; t += PLAN_THREADS) add(4, t, bcc[x.cc_off + t]);
   for (int o = 16; o > 0; o >>= 1) {
@@ -872,6 +895,7 @@ __global__ void apply_representatives(BlockDesc2 *__restrict__ d, const int64_t 
   d[b].idx_off = d[r].idx_off;
   d[b].meta_off = d[r].meta_off;
   d[b].cc_off = d[r].cc_off;
+  d[b].cls_off = d[r].cls_off;
 }
 
 struct PairHash {
@@ -880,135 +904,228 @@ struct PairHash {
 
 }  // namespace
 
-// Bank-conflict-aware column order (host side, unique patterns only).  The order in which a lane sums
-// its contributions is free, so each lane's address list is permuted to spread the 16 lanes of a
-// half-warp over the 16 eight-byte banks of every column; padding lanes then take a staged zero in
-// the least loaded bank.  Greedy lane by lane; exhaustive over the permutations of short lists.
-static void optimize_pattern(const BlockDesc2 &d, const uint32_t *meta, uint16_t *idx, int zaddr) {
+// Bank-conflict-aware layout of the unique patterns (host side).  Two degrees of freedom that do not
+// change any sum except for its order:
+//   * the order in which a lane adds its contributions (a permutation of its column entries);
+//   * which store groups (sectors) of one slice class share a half-warp (slices of a class are
+//     interchangeable; a group moves together with its sector id).
+// Goal: the 16 lanes of a half-warp hit 16 different 8-byte banks in every column.  Greedy packing of
+// half-warps for narrow classes (few permutations per lane => the choice of neighbours matters most),
+// then a few refinement sweeps over the lanes of every slice; padding lanes finally take a staged zero
+// in the least loaded bank.
+namespace {
+struct BankLoad {
+  struct Ent {
+    uint16_t addr, n;
+  };
+  int w = 0;
+  std::vector<std::vector<Ent>> cells;  // [column][half][bank]
+  void reset(int width) {
+    w = width;
+    cells.assign((size_t)w * 2 * 16, {});
+  }
+  std::vector<Ent> &at(int k, int half, int bank) { return cells[((size_t)k * 2 + half) * 16 + bank]; }
+  void add(int k, int half, uint16_t x) {
+    auto &v = at(k, half, x & 15);
+    for (auto &e : v)
+      if (e.addr == x) {
+        ++e.n;
+        return;
+      }
+    v.push_back({x, 1});
+  }
+  void remove(int k, int half, uint16_t x) {
+    auto &v = at(k, half, x & 15);
+    for (size_t i = 0; i < v.size(); ++i)
+      if (v[i].addr == x) {
+        if (--v[i].n == 0) v.erase(v.begin() + (long)i);
+        return;
+      }
+  }
+  int cost(int k, int half, uint16_t x) {
+    const auto &v = at(k, half, x & 15);
+    for (const auto &e : v)
+      if (e.addr == x) return 0;  // same address: broadcast
+    return 2 * (int)v.size() + 1;
+  }
+};
+
+struct LaneOrder {
   uint64_t rng = 0x243f6a8885a308d3ull;
-  auto next = [&]() {
+  std::vector<int> best, cand, ident;
+  uint32_t next() {
     rng = rng * 6364136223846793005ull + 1442695040888963407ull;
     return (uint32_t)(rng >> 33);
-  };
-  struct Ent {
-    uint16_t addr;
-    uint16_t n;
-  };
-  std::vector<int> best, cand, ident;
-  for (int sl = 0; sl < d.nsl; ++sl) {
-    const uint32_t m = meta[sl];
-    const int w = (int)((m >> 16) & 0xffu);
-    if (w < 1) continue;
-    uint16_t *base = idx + (size_t)(m & 0xffffu) * 64;
-    auto at = [&](int k, int lane) -> uint16_t & { return base[(size_t)(k >> 1) * 64 + 2 * lane + (k & 1)]; };
-    // load[k][half][bank]: distinct addresses placed there, with multiplicity
-    std::vector<std::vector<Ent>> load((size_t)w * 2 * 16);
-    auto cell = [&](int k, int half, int bank) -> std::vector<Ent> & { return load[((size_t)k * 2 + half) * 16 + bank]; };
-    auto add = [&](int k, int half, uint16_t x) {
-      auto &v = cell(k, half, x & 15);
-      for (auto &e : v)
-        if (e.addr == x) {
-          ++e.n;
-          return;
-        }
-      v.push_back({x, 1});
-    };
-    auto remove = [&](int k, int half, uint16_t x) {
-      auto &v = cell(k, half, x & 15);
-      for (size_t i = 0; i < v.size(); ++i)
-        if (v[i].addr == x) {
-          if (--v[i].n == 0) v.erase(v.begin() + (long)i);
-          return;
-        }
-    };
-    auto cost_of = [&](int k, int half, uint16_t x) {
-      const auto &v = cell(k, half, x & 15);
-      for (const auto &e : v)
-        if (e.addr == x) return 0;  // same address: broadcast
-      return 2 * (int)v.size() + 1;
-    };
-    std::vector<std::vector<uint16_t>> cur(32);
+  }
+  // best order of `vals` (entries >= zaddr are padding) against `load`; returns its cost
+  int choose(BankLoad &load, int half, const std::vector<uint16_t> &vals, int zaddr, std::vector<uint16_t> &out,
+             bool quick = false) {
+    const int w = (int)vals.size();
     ident.resize(w);
     for (int k = 0; k < w; ++k) ident[k] = k;
-    for (int sweep = 0; sweep < 4; ++sweep) {
-      bool changed = false;
-      for (int lane = 0; lane < 32; ++lane) {
-        const int half = lane >> 4;
-        auto &vals = cur[lane];
-        if (sweep == 0) {
-          vals.resize(w);
-          for (int k = 0; k < w; ++k) vals[k] = at(k, lane);
-        } else {
-          for (int k = 0; k < w; ++k)
-            if (vals[k] < zaddr) remove(k, half, vals[k]);
-        }
-        int nreal = 0;
-        for (int k = 0; k < w; ++k) nreal += vals[k] < zaddr;
-        if (nreal == 0) continue;
-        int bestc = -1;
-        auto consider = [&](const std::vector<int> &pm) {
-          int c = 0;
-          for (int k = 0; k < w; ++k)
-            if (vals[pm[k]] < zaddr) c += cost_of(k, half, vals[pm[k]]);
-          if (bestc < 0 || c < bestc) {
-            bestc = c;
-            best = pm;
-          }
-        };
-        consider(ident);  // keep the current order on ties
-        if (w <= 5) {
-          cand = ident;
-          do consider(cand); while (std::next_permutation(cand.begin(), cand.end()));
-        } else {
-          for (int r = 0; r < w; ++r) {
-            cand.resize(w);
-            for (int k = 0; k < w; ++k) cand[k] = (k + r) % w;
-            consider(cand);
-            std::reverse(cand.begin(), cand.end());
-            consider(cand);
-          }
-          for (int t = 0; t < 128 && bestc > 0; ++t) {
-            cand = ident;
-            for (int k = w - 1; k > 0; --k) std::swap(cand[k], cand[next() % (uint32_t)(k + 1)]);
-            consider(cand);
-          }
-        }
-        std::vector<uint16_t> out(w);
-        for (int k = 0; k < w; ++k) out[k] = vals[best[k]];
-        changed |= out != vals;
-        vals = out;
-        for (int k = 0; k < w; ++k)
-          if (vals[k] < zaddr) add(k, half, vals[k]);
+    int bestc = -1;
+    auto consider = [&](const std::vector<int> &pm) {
+      int c = 0;
+      for (int k = 0; k < w; ++k)
+        if (vals[pm[k]] < zaddr) c += load.cost(k, half, vals[pm[k]]);
+      if (bestc < 0 || c < bestc) {
+        bestc = c;
+        best = pm;
       }
-      if (sweep > 0 && !changed) break;
+    };
+    consider(ident);  // keep the current order on ties
+    if (w <= 5) {
+      cand = ident;
+      do consider(cand); while (bestc > 0 && std::next_permutation(cand.begin(), cand.end()));
+    } else {
+      for (int r = 0; r < w && bestc > 0; ++r) {
+        cand.resize(w);
+        for (int k = 0; k < w; ++k) cand[k] = (k + r) % w;
+        consider(cand);
+        std::reverse(cand.begin(), cand.end());
+        consider(cand);
+      }
+      for (int t = 0; t < 128 && bestc > 0 && !quick; ++t) {
+        cand = ident;
+        for (int k = w - 1; k > 0; --k) std::swap(cand[k], cand[next() % (uint32_t)(k + 1)]);
+        consider(cand);
+      }
     }
-    for (int lane = 0; lane < 32; ++lane)
-      for (int k = 0; k < w; ++k) at(k, lane) = cur[lane][k];
-    for (int lane = 0; lane < 32; ++lane)  // padding: a staged zero in the least loaded bank
-      for (int k = 0; k < w; ++k) {
-        if (at(k, lane) < zaddr) continue;
-        const int half = lane >> 4;
-        int bb = 0;
-        size_t bl = (size_t)-1;
-        for (int bk = 0; bk < 16; ++bk) {
-          const auto &v = cell(k, half, bk);
-          size_t l = v.size();
-          for (const auto &e : v)
-            if (e.addr == (uint16_t)(zaddr + bk)) --l;  // the zero of this bank is already there: free
-          if (l < bl) {
-            bl = l;
-            bb = bk;
-          }
+    out.resize(w);
+    for (int k = 0; k < w; ++k) out[k] = vals[best[k]];
+    return bestc;
+  }
+};
+}  // namespace
+
+static void optimize_pattern(const BlockDesc2 &d, const uint2 *cls, uint16_t *idx, uint16_t *gdst, int G, int zaddr) {
+  const int per_norm = 32 / G;
+  LaneOrder lo;
+  BankLoad load;
+  std::vector<uint16_t> tmp;
+  for (int c = 0; c < d.ncls; ++c) {
+    const int first = (int)(cls[c].x & 0xffffu), count = (int)(cls[c].x >> 16);
+    const int w = (int)((cls[c].y >> 16) & 0xffu);
+    const bool split = (cls[c].y >> 24) != 0;
+    if (w < 1 || count < 1) continue;
+    const size_t pairs = (size_t)((w + 1) >> 1);
+    uint16_t *cbase = idx + (size_t)(cls[c].y & 0xffffu) * 64;
+    auto at = [&](int sl, int k, int lane) -> uint16_t & { return cbase[((size_t)sl * pairs + (size_t)(k >> 1)) * 64 + 2 * lane + (k & 1)]; };
+    // ---- regroup the store groups of narrow, non-split classes
+    if (!split && w <= 8 && count >= 2) {
+      struct Unit {
+        uint16_t gd;
+        std::vector<std::vector<uint16_t>> lanes;  // [G][w]
+      };
+      std::vector<Unit> pool, pads, order;
+      for (int sl = 0; sl < count; ++sl)
+        for (int g = 0; g < per_norm; ++g) {
+          Unit u;
+          u.gd = gdst[(size_t)(first + sl) * per_norm + g];
+          u.lanes.assign(G, std::vector<uint16_t>(w));
+          for (int q = 0; q < G; ++q)
+            for (int k = 0; k < w; ++k) u.lanes[q][k] = at(sl, k, g * G + q);
+          (u.gd == 0xffff ? pads : pool).push_back(std::move(u));
         }
-        at(k, lane) = (uint16_t)(zaddr + bb);
-        add(k, half, (uint16_t)(zaddr + bb));
+      const int gph = per_norm / 2;  // groups per half-warp
+      std::vector<char> used(pool.size(), 0);
+      size_t remaining = pool.size(), head = 0;
+      while (remaining > 0) {
+        load.reset(w);
+        for (int slot = 0; slot < gph && remaining > 0; ++slot) {
+          while (used[head]) ++head;
+          size_t pick = head;
+          if (slot > 0) {
+            int bestc = -1;
+            size_t seen = 0;
+            for (size_t u = head; u < pool.size() && seen < 256; ++u) {
+              if (used[u]) continue;
+              ++seen;
+              int cst = 0;
+              for (int q = 0; q < G; ++q) cst += lo.choose(load, 0, pool[u].lanes[q], zaddr, tmp, true);
+              if (bestc < 0 || cst < bestc) {
+                bestc = cst;
+                pick = u;
+              }
+              if (bestc == 0) break;
+            }
+          }
+          Unit u = pool[pick];
+          used[pick] = 1;
+          --remaining;
+          for (int q = 0; q < G; ++q) {
+            lo.choose(load, 0, u.lanes[q], zaddr, tmp);
+            u.lanes[q] = tmp;
+            for (int k = 0; k < w; ++k)
+              if (tmp[k] < zaddr) load.add(k, 0, tmp[k]);
+          }
+          order.push_back(std::move(u));
+        }
       }
+      for (auto &u : pads) order.push_back(std::move(u));
+      size_t n = 0;
+      for (int sl = 0; sl < count; ++sl)
+        for (int g = 0; g < per_norm; ++g, ++n) {
+          const Unit &u = order[n];
+          gdst[(size_t)(first + sl) * per_norm + g] = u.gd;
+          for (int q = 0; q < G; ++q)
+            for (int k = 0; k < w; ++k) at(sl, k, g * G + q) = u.lanes[q][k];
+        }
+    }
+    // ---- per-slice refinement of the lane orders, then padding
+    for (int sl = 0; sl < count; ++sl) {
+      load.reset(w);
+      std::vector<std::vector<uint16_t>> cur(32, std::vector<uint16_t>(w));
+      for (int lane = 0; lane < 32; ++lane)
+        for (int k = 0; k < w; ++k) cur[lane][k] = at(sl, k, lane);
+      for (int sweep = 0; sweep < 4; ++sweep) {
+        bool changed = false;
+        for (int lane = 0; lane < 32; ++lane) {
+          const int half = lane >> 4;
+          auto &vals = cur[lane];
+          int nreal = 0;
+          for (int k = 0; k < w; ++k) nreal += vals[k] < zaddr;
+          if (nreal == 0) continue;
+          if (sweep > 0)
+            for (int k = 0; k < w; ++k)
+              if (vals[k] < zaddr) load.remove(k, half, vals[k]);
+          lo.choose(load, half, vals, zaddr, tmp);
+          changed |= tmp != vals;
+          vals = tmp;
+          for (int k = 0; k < w; ++k)
+            if (vals[k] < zaddr) load.add(k, half, vals[k]);
+        }
+        if (sweep > 0 && !changed) break;
+      }
+      for (int lane = 0; lane < 32; ++lane)
+        for (int k = 0; k < w; ++k) {
+          uint16_t v = cur[lane][k];
+          if (v >= zaddr) {  // padding: a staged zero in the least loaded bank
+            const int half = lane >> 4;
+            int bb = 0;
+            size_t bl = (size_t)-1;
+            for (int bk = 0; bk < 16; ++bk) {
+              const auto &cellv = load.at(k, half, bk);
+              size_t l = cellv.size();
+              for (const auto &e : cellv)
+                if (e.addr == (uint16_t)(zaddr + bk)) --l;  // the zero of this bank is already there: free
+              if (l < bl) {
+                bl = l;
+                bb = bk;
+              }
+            }
+            v = (uint16_t)(zaddr + bb);
+            load.add(k, half, v);
+          }
+          at(sl, k, lane) = v;
+        }
+    }
   }
 }
 
 void fdts_free_plan2(fdts_engine *e) {
   GatherPlan2 &p = e->plan2;
-  void *ptrs[] = {p.cidx, p.smeta, p.gdst, p.bcc, p.bvcoords, p.bdesc};
+  void *ptrs[] = {p.cidx, p.cmeta, p.gdst, p.bcc, p.bvcoords, p.bdesc};
   for (void *q : ptrs)
     if (q) cudaFree(q);
   p = GatherPlan2();
@@ -1042,7 +1159,7 @@ int fdts_build_plan2(fdts_engine *e, const int64_t *starts, int64_t nb) {
   p.sector = G;
   int64_t *bstart = nullptr, *ncand = nullptr, *btotal = nullptr, *bnsl = nullptr, *idx_off = nullptr, *meta_off = nullptr,
           *dmax = nullptr, *rep_d = nullptr;
-  int32_t *bcount = nullptr, *bcells = nullptr, *vcount = nullptr, *imax = nullptr;
+  int32_t *bcount = nullptr, *bcells = nullptr, *vcount = nullptr, *imax = nullptr, *bncls = nullptr;
   uint8_t *cnt8 = nullptr;
   uint32_t *sellpos = nullptr;
   uint64_t *hash_d = nullptr;
@@ -1092,6 +1209,7 @@ int fdts_build_plan2(fdts_engine *e, const int64_t *starts, int64_t nb) {
     P2_ALLOC(derr, sizeof(int), "scratch");
     P2_ALLOC(bcount, sizeof(int32_t) * nb, "block cell counts");
     P2_ALLOC(vcount, sizeof(int32_t) * nb, "block vertex counts");
+    P2_ALLOC(bncls, sizeof(int32_t) * nb, "block class counts");
     cudaMemsetAsync(derr, 0, sizeof(int), s);
     cudaMemcpyAsync(bstart, starts, sizeof(int64_t) * (nb + 1), cudaMemcpyHostToDevice, s);
     // ---- cells of every block
@@ -1131,7 +1249,7 @@ int fdts_build_plan2(fdts_engine *e, const int64_t *starts, int64_t nb) {
                                                       nullptr, derr);
     cudaMemsetAsync(btotal, 0, sizeof(int64_t) * (nb + 1), s);
     cudaMemsetAsync(bnsl, 0, sizeof(int64_t) * (nb + 1), s);
-    sell2_layout<false><<<(unsigned)nb, PLAN_THREADS, 0, s>>>(bstart, e->nrowptr, cnt8, G, nullptr, nullptr, nullptr, nullptr,
+    sell2_layout<false><<<(unsigned)nb, PLAN_THREADS, 0, s>>>(bstart, e->nrowptr, cnt8, G, nullptr, nullptr, nullptr, nullptr, nullptr,
                                                             btotal, bnsl, derr);
     if ((rc = scan(btotal, idx_off, nb + 1)) || (rc = scan(bnsl, meta_off, nb + 1))) break;
     int64_t total = 0, total_sl = 0, max_idx = 0, max_sl = 0;
@@ -1141,6 +1259,11 @@ int fdts_build_plan2(fdts_engine *e, const int64_t *starts, int64_t nb) {
     int herr = 0;
     cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, s);
     cudaStreamSynchronize(s);
+    if (herr == 9) {
+      fdts_set_error("gather plan 2: a row block has more than 32 distinct slice widths");
+      rc = 4;
+      break;
+    }
     if (herr == 7 || herr == 8) {
       fdts_set_error("gather plan 2: a row block has too many CSR slots (at most 8192 store groups / 2048 slices; use smaller row blocks)");
       rc = 4;
@@ -1150,13 +1273,13 @@ int fdts_build_plan2(fdts_engine *e, const int64_t *starts, int64_t nb) {
     p.max_nidx = (int32_t)max_idx;
     p.max_nsl = (int32_t)max_sl;
     P2_ALLOC(p.cidx, sizeof(uint16_t) * (size_t)(total + 64), "contribution lists");
-    P2_ALLOC(p.smeta, sizeof(uint32_t) * (size_t)(total_sl + 16), "slice table");
+    P2_ALLOC(p.cmeta, sizeof(uint2) * ((size_t)nb + 1) * PLAN2_MAX_CLASSES, "slice class table");
     P2_ALLOC(p.gdst, sizeof(uint16_t) * (size_t)(total_sl + 16) * per_norm, "slice destinations");
     fill_padding<<<GRID(total + 64, 256), 256, 0, s>>>(p.cidx, total + 64, p.zaddr);
-    cudaMemsetAsync(p.smeta, 0, sizeof(uint32_t) * (size_t)(total_sl + 16), s);
+    cudaMemsetAsync(p.cmeta, 0, sizeof(uint2) * ((size_t)nb + 1) * PLAN2_MAX_CLASSES, s);
     cudaMemsetAsync(p.gdst, 0xff, sizeof(uint16_t) * (size_t)(total_sl + 16) * per_norm, s);
     // second pass writes the tables; the true (unpadded) slice counts land in ncand (reused)
-    sell2_layout<true><<<(unsigned)nb, PLAN_THREADS, 0, s>>>(bstart, e->nrowptr, cnt8, G, meta_off, p.smeta, p.gdst, sellpos,
+    sell2_layout<true><<<(unsigned)nb, PLAN_THREADS, 0, s>>>(bstart, e->nrowptr, cnt8, G, meta_off, p.cmeta, bncls, p.gdst, sellpos,
                                                            btotal, ncand, derr);
     cudaMemsetAsync(cnt8, 0, (size_t)nnz + 1, s);
     slot_contributions2<<<(unsigned)nb, 128, 0, s>>>(bstart, e->adj_ptr, e->adj_cell, e->cell_node, nc, nd, p.nep, e->pos8,
@@ -1195,8 +1318,8 @@ int fdts_build_plan2(fdts_engine *e, const int64_t *starts, int64_t nb) {
     cudaMemsetAsync(p.bdesc, 0, sizeof(BlockDesc2) * (size_t)(nb + 4), s);
     block_vertices<true><<<(unsigned)nb, PLAN_THREADS, smv, s>>>(bcells, bcount, cmax, e->cell_coord, nc, dim, e->coords, kpv,
                                                                vmax, nullptr, p.bvcoords, p.bcc, derr);
-    block_descriptors2<<<GRID(nb, 256), 256, 0, s>>>(bstart, nb, e->nrowptr, idx_off, meta_off, ncand, bcount, vcount, cmaxp,
-                                                    vmax, dim, G, p.bdesc);
+    block_descriptors2<<<GRID(nb, 256), 256, 0, s>>>(bstart, nb, e->nrowptr, idx_off, meta_off, ncand, bncls, bcount, vcount, cmaxp,
+                                                    vmax, dim, p.bdesc);
     cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, s);
     cudaError_t ce = cudaStreamSynchronize(s);
     if (ce != cudaSuccess || cudaGetLastError() != cudaSuccess) {
@@ -1215,7 +1338,7 @@ int fdts_build_plan2(fdts_engine *e, const int64_t *starts, int64_t nb) {
     if (e->opt_dedup) {
       P2_ALLOC(hash_d, sizeof(uint64_t) * 2 * (size_t)nb, "pattern hashes");
       P2_ALLOC(rep_d, sizeof(int64_t) * (size_t)nb, "pattern representatives");
-      block_hash<<<(unsigned)nb, PLAN_THREADS, 0, s>>>(p.bdesc, p.cidx, p.smeta, p.gdst, p.bcc, per_norm, hash_d);
+      block_hash<<<(unsigned)nb, PLAN_THREADS, 0, s>>>(p.bdesc, p.cidx, p.cmeta, p.gdst, G, p.bcc, per_norm, hash_d);
       std::vector<uint64_t> h(2 * (size_t)nb);
       std::vector<BlockDesc2> hd((size_t)nb);
       cudaMemcpyAsync(h.data(), hash_d, sizeof(uint64_t) * 2 * (size_t)nb, cudaMemcpyDeviceToHost, s);
@@ -1251,18 +1374,21 @@ int fdts_build_plan2(fdts_engine *e, const int64_t *starts, int64_t nb) {
       p.unique_patterns = uniq;
       p.shared_idx = shared;
       if (e->opt_optimize && uniq <= 4096) {
-        std::vector<uint32_t> hm;
-        std::vector<uint16_t> hi;
+        std::vector<uint2> hm;
+        std::vector<uint16_t> hi, hg;
         bool ok = true;
         for (int64_t b = 0; b < nb && ok; ++b) {
           if (rep[b] != b || hd[b].nsl == 0 || hd[b].nidx == 0) continue;
-          hm.resize((size_t)hd[b].nsl);
+          hm.resize((size_t)hd[b].ncls);
           hi.resize((size_t)hd[b].nidx);
-          ok = cudaMemcpy(hm.data(), p.smeta + hd[b].meta_off, sizeof(uint32_t) * hm.size(), cudaMemcpyDeviceToHost) == cudaSuccess &&
-               cudaMemcpy(hi.data(), p.cidx + hd[b].idx_off, sizeof(uint16_t) * hi.size(), cudaMemcpyDeviceToHost) == cudaSuccess;
+          hg.resize((size_t)hd[b].nsl * per_norm);
+          ok = cudaMemcpy(hm.data(), p.cmeta + hd[b].cls_off, sizeof(uint2) * hm.size(), cudaMemcpyDeviceToHost) == cudaSuccess &&
+               cudaMemcpy(hi.data(), p.cidx + hd[b].idx_off, sizeof(uint16_t) * hi.size(), cudaMemcpyDeviceToHost) == cudaSuccess &&
+               cudaMemcpy(hg.data(), p.gdst + hd[b].meta_off * per_norm, sizeof(uint16_t) * hg.size(), cudaMemcpyDeviceToHost) == cudaSuccess;
           if (!ok) break;
-          optimize_pattern(hd[b], hm.data(), hi.data(), p.zaddr);
-          ok = cudaMemcpy(p.cidx + hd[b].idx_off, hi.data(), sizeof(uint16_t) * hi.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+          optimize_pattern(hd[b], hm.data(), hi.data(), hg.data(), G, p.zaddr);
+          ok = cudaMemcpy(p.cidx + hd[b].idx_off, hi.data(), sizeof(uint16_t) * hi.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+               cudaMemcpy(p.gdst + hd[b].meta_off * per_norm, hg.data(), sizeof(uint16_t) * hg.size(), cudaMemcpyHostToDevice) == cudaSuccess;
         }
         if (!ok) {
           fdts_set_error("gather plan 2: pattern optimisation failed");
@@ -1274,7 +1400,7 @@ int fdts_build_plan2(fdts_engine *e, const int64_t *starts, int64_t nb) {
     }
     p.ready = true;
   } while (0);
-  void *scratch[] = {tmp, bstart, ncand, btotal, bnsl, idx_off, meta_off, dmax, imax, derr, bcount, vcount, bcells, cnt8,
+  void *scratch[] = {tmp, bstart, ncand, btotal, bnsl, idx_off, meta_off, dmax, imax, derr, bcount, vcount, bncls, bcells, cnt8,
                      sellpos, hash_d, rep_d};
   for (void *q : scratch)
     if (q) cudaFree(q);

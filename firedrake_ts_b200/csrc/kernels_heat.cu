@@ -450,12 +450,13 @@ int launch_gather(int which, GArgs a, const GatherPlan &p, cudaStream_t s) {
 struct G2Args {
   const BlockDesc2 *bdesc;
   const uint16_t *cidx, *gdst;
-  const uint32_t *smeta, *bcc;
+  const uint2 *cmeta;
+  const uint32_t *bcc;
   const double *bvcoords;
   double *out;
   int64_t nblocks;
   double shift;
-  int32_t off_idx, off_meta, off_gdst, off_vtab, off_lcc, off_bar, zaddr, sector;
+  int32_t off_idx, off_meta, off_gdst, off_vtab, off_lcc, off_bar, off_desc, zaddr, sector;
   int32_t dbg;  // development only: bit0 skips phase A, bit1 skips phase B (timing experiments; results are wrong)
 };
 
@@ -498,36 +499,45 @@ __device__ __forceinline__ double sum_columns(uint32_t ip, uint32_t sbase) {
   return a0 + a1;
 }
 
-// reference tensors in the constant bank: the unrolled element kernel reads them as DFMA operands
-// (c[3][imm]) instead of materialising 64-bit immediates through the uniform datapath
-template <int DIM, int DEG, int VAR>
-struct HeatTab {
-  using T = RefT<DIM, DEG, VAR>;
-  double R00[T::ND][T::ND];
-  double S[T::NP][T::ND][T::ND];
-  constexpr HeatTab() : R00{}, S{} {
-    for (int i = 0; i < T::ND; ++i)
-      for (int j = 0; j < T::ND; ++j) {
-        R00[i][j] = T::R00[i][j];
-        for (int p = 0; p < T::NP; ++p) S[p][i][j] = T::S[p][i][j];
-      }
-  }
-};
-template <int DIM, int DEG, int VAR>
-__constant__ HeatTab<DIM, DEG, VAR> c_heat_tab{};
-
-template <int DIM, int DEG, int VAR, int I, int J, int NP>
-__device__ __forceinline__ double heat_entry_c(double m, const double (&gm)[NP]) {
-  using T = RefT<DIM, DEG, VAR>;
+// element-matrix entry from the integer form of the reference tensors (ref_tables.cuh):
+//   A_ij = ms * IR_ij + sum_p gs_p * IS_pij,   ms = shift |detJ| / RDEN,  gs_p = |detJ| G_p / SDEN.
+// The handful of distinct integer multipliers stay in uniform registers; the plain tables would cost one
+// 64-bit immediate (two UMOVs) per use.
+template <class T, int I, int J, int NP>
+__device__ __forceinline__ double heat_entry_i(double ms, const double (&gs)[NP]) {
   double v = 0.0;
-  constexpr double r = T::R00[I][J];
-  if constexpr (r != 0.0) v = m * c_heat_tab<DIM, DEG, VAR>.R00[I][J];
+  constexpr int r = T::IR[I][J];
+  if constexpr (r != 0) v = ms * (double)r;
   static_for<NP>([&](auto P) {
     constexpr int p = decltype(P)::value;
-    constexpr double sv = T::S[p][I][J];
-    if constexpr (sv != 0.0) v = fma(gm[p], c_heat_tab<DIM, DEG, VAR>.S[p][I][J], v);
+    constexpr int c = T::IS[p][I][J];
+    if constexpr (c != 0) v = fma(gs[p], (double)c, v);
   });
   return v;
+}
+
+// one class of slices (equal width W, equal split flag): warp `warp` takes the slices congruent to it
+template <int W, int G, int NWARPS>
+__device__ __forceinline__ void sweep_class(uint32_t first, uint32_t count, uint32_t off64, bool split, int warp, int lane,
+                                            uint32_t idx0, uint32_t gd0, uint32_t sbase, double *__restrict__ out,
+                                            uint32_t lo, uint32_t span) {
+  constexpr int LG = G == 4 ? 2 : (G == 2 ? 1 : 0), PER_NORM = 32 / G, PAIRS = (W + 1) / 2;
+  uint32_t i = (uint32_t)(warp - (int)first) & (NWARPS - 1);
+  const uint32_t gsel = split ? (uint32_t)(lane >> (LG + 2)) : (uint32_t)(lane >> LG);
+  const uint32_t sub = split ? (uint32_t)((lane >> 2) & (G - 1)) : (uint32_t)(lane & (G - 1));
+  const bool wr = split ? (lane & 3) == 0 : true;
+  uint32_t ip = idx0 + (off64 + i * PAIRS) * 128u;
+  uint32_t gd = gd0 + ((first + i) * PER_NORM + gsel) * 2u;
+  for (; i < count; i += NWARPS, ip += NWARPS * PAIRS * 128u, gd += NWARPS * PER_NORM * 2u) {
+    const uint32_t gs = lds_u16(gd);
+    double acc = sum_columns<W>(ip, sbase);
+    if (split) {
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    }
+    const uint32_t slot = gs * G + sub;  // sector id 0xffff (none) lands far outside [lo, lo + span)
+    if (wr && slot - lo < span) out[slot] = acc;
+  }
 }
 
 template <int DIM, int DEG, int VAR, int NT, int G>
@@ -535,19 +545,15 @@ __global__ void __launch_bounds__(NT, NT <= 512 ? 2 : 1) heat_jacobian_gather2(c
   using T = RefT<DIM, DEG, VAR>;
   constexpr int ND = T::ND, NP = T::NP, NEP = (ND * (ND + 1) / 2) | 1;
   constexpr int NWARPS = NT / 32;
-  constexpr int LG = G == 4 ? 2 : (G == 2 ? 1 : 0), PER_NORM = 32 / G;
+  constexpr int PER_NORM = 32 / G;
   extern __shared__ __align__(16) unsigned char smraw[];
   uint64_t *bars = reinterpret_cast<uint64_t *>(smraw + a.off_bar);
+  BlockDesc2 *sdesc = reinterpret_cast<BlockDesc2 *>(smraw + a.off_desc);  // [2]: current / next block
   const uint32_t sbase = smem_u32(smraw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // per-thread shared addresses of the phase-B tables (slice `warp`), advanced by NWARPS slices per step
-  const uint32_t meta0 = sbase + a.off_meta + warp * 4;
   const uint32_t idx0 = sbase + a.off_idx + lane * 4;
-  // lane -> (store group, slot inside the group); split slices use four lanes per slot
-  const uint32_t gd_norm0 = sbase + a.off_gdst + (warp * PER_NORM + (lane >> LG)) * 2;
-  const uint32_t gd_split0 = sbase + a.off_gdst + (warp * PER_NORM + (lane >> (LG + 2))) * 2;
-  const int sub_norm = lane & (G - 1), sub_split = (lane >> 2) & (G - 1);
-  const bool lead = (lane & 3) == 0;
+  const uint32_t gd0 = sbase + a.off_gdst;
+  const uint32_t cls0 = sbase + a.off_meta;
 
   auto issue_A = [&](const BlockDesc2 &d) {  // vertex table + local vertex ids
     const uint32_t vb = (uint32_t)(((d.nvert * DIM + 1) & ~1) * 8);
@@ -556,31 +562,35 @@ __global__ void __launch_bounds__(NT, NT <= 512 ? 2 : 1) heat_jacobian_gather2(c
     if (vb) bulk_g2s(smraw + a.off_vtab, a.bvcoords + d.vc_off, vb, &bars[0]);
     if (cb) bulk_g2s(smraw + a.off_lcc, a.bcc + d.cc_off, cb, &bars[0]);
   };
-  auto issue_B = [&](const BlockDesc2 &d) {  // SELL addresses, slice table, sector ids
+  auto issue_B = [&](const BlockDesc2 &d) {  // SELL addresses, class table, sector ids
     const uint32_t nslp = (uint32_t)((d.nsl + 3) & ~3);
-    const uint32_t ib = (uint32_t)d.nidx * 2u, mb = nslp * 4u, gb = nslp * 2u * (uint32_t)PER_NORM;
+    const uint32_t ib = (uint32_t)d.nidx * 2u, mb = (uint32_t)((d.ncls + 1) & ~1) * 8u, gb = nslp * 2u * (uint32_t)PER_NORM;
     mbar_expect_tx(&bars[1], ib + mb + gb);
     if (ib) bulk_g2s(smraw + a.off_idx, a.cidx + d.idx_off, ib, &bars[1]);
-    if (mb) bulk_g2s(smraw + a.off_meta, a.smeta + d.meta_off, mb, &bars[1]);
+    if (mb) bulk_g2s(smraw + a.off_meta, a.cmeta + d.cls_off, mb, &bars[1]);
     if (gb) bulk_g2s(smraw + a.off_gdst, a.gdst + d.meta_off * PER_NORM, gb, &bars[1]);
   };
 
   const int64_t stride = gridDim.x;
   int64_t b = blockIdx.x;
   if (b >= a.nblocks) return;
-  BlockDesc2 d = a.bdesc[b];
   if (threadIdx.x == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
-    issue_A(d);
+    sdesc[0] = a.bdesc[b];
+    issue_A(sdesc[0]);
   }
   if (threadIdx.x < 16) sts_f64(sbase + (a.zaddr + threadIdx.x) * 8, 0.0);  // one staged zero per 8-byte bank
   __syncthreads();
   for (int it = 0; b < a.nblocks; ++it, b += stride) {
     const int64_t bn = b + stride;
     const bool more = bn < a.nblocks;
-    if (threadIdx.x == 0) issue_B(d);
-    const BlockDesc2 dn = a.bdesc[more ? bn : b];
+    const BlockDesc2 &d = sdesc[it & 1];
+    BlockDesc2 dn;
+    if (threadIdx.x == 0) {
+      issue_B(d);
+      if (more) dn = a.bdesc[bn];
+    }
     // ---- phase A
     mbar_wait(&bars[0], (uint32_t)(it & 1));
     const int ncell = (a.dbg & 1) ? 0 : d.ncell;
@@ -597,65 +607,88 @@ __global__ void __launch_bounds__(NT, NT <= 512 ? 2 : 1) heat_jacobian_gather2(c
       geometry_from_vertices<DIM>(X, g);
       double gm[NP];
       metric<DIM>(g, gm);
-      const double m = a.shift * g.adet;
       const uint32_t st = sbase + k * (NEP * 8);
-      static_for<ND>([&](auto I) {
-        constexpr int i = decltype(I)::value;
-        static_for<ND - i>([&](auto JJ) {
-          constexpr int j = i + decltype(JJ)::value;
-          constexpr int e = i * ND - (i * (i - 1)) / 2 + (j - i);
-          sts_f64(st + e * 8, heat_entry<T, i, j, NP>(m, gm));
+      if constexpr (T::INT) {
+        const double ms = a.shift * g.adet * (1.0 / T::RDEN);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) gm[p] *= (1.0 / T::SDEN);
+        static_for<ND>([&](auto I) {
+          constexpr int i = decltype(I)::value;
+          static_for<ND - i>([&](auto JJ) {
+            constexpr int j = i + decltype(JJ)::value;
+            constexpr int e = i * ND - (i * (i - 1)) / 2 + (j - i);
+            sts_f64(st + e * 8, heat_entry_i<T, i, j, NP>(ms, gm));
+          });
         });
-      });
+      } else {
+        const double m = a.shift * g.adet;
+        static_for<ND>([&](auto I) {
+          constexpr int i = decltype(I)::value;
+          static_for<ND - i>([&](auto JJ) {
+            constexpr int j = i + decltype(JJ)::value;
+            constexpr int e = i * ND - (i * (i - 1)) / 2 + (j - i);
+            sts_f64(st + e * 8, heat_entry<T, i, j, NP>(m, gm));
+          });
+        });
+      }
     }
+    if (threadIdx.x == 0 && more) sdesc[(it + 1) & 1] = dn;
     __syncthreads();
     if (threadIdx.x == 0 && more) issue_A(dn);
-    // ---- phase B
+    // ---- phase B: class by class, no barrier in between
     mbar_wait(&bars[1], (uint32_t)(it & 1));
-    double *__restrict__ out = a.out + (d.s0 - d.s_align);
-    const uint32_t lo = (uint32_t)d.s_align, span = (uint32_t)d.nslots;
-    const int nsl = (a.dbg & 2) ? 0 : d.nsl;
-    uint32_t mp = meta0, gn = gd_norm0, gp = gd_split0;
-    for (int sl = warp; sl < nsl; sl += NWARPS, mp += NWARPS * 4, gn += NWARPS * PER_NORM * 2, gp += NWARPS * PER_NORM * 2) {
-      const uint32_t meta = lds_u32(mp);
-      const uint32_t w = (meta >> 16) & 0xffu;
-      const bool split = meta >= 0x1000000u;
-      const uint32_t gs = lds_u16(split ? gp : gn);
-      const uint32_t ip = idx0 + (meta & 0xffffu) * 128u;
-      double acc;
+    const uint32_t lo = (uint32_t)(d.s0 & (G - 1)), span = (uint32_t)d.nslots;
+    double *__restrict__ out = a.out + (d.s0 - lo);
+    const int ncls = (a.dbg & 2) ? 0 : d.ncls;
+    for (int c = 0; c < ncls; ++c) {
+      uint32_t c0, c1;
+      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(c0), "=r"(c1) : "r"(cls0 + c * 8));
+      const uint32_t first = c0 & 0xffffu, count = c0 >> 16, off64 = c1 & 0xffffu, w = (c1 >> 16) & 0xffu;
+      const bool split = c1 >= 0x1000000u;
+#define SWEEP(W) sweep_class<W, G, NWARPS>(first, count, off64, split, warp, lane, idx0, gd0, sbase, out, lo, span)
       switch (w) {
-        case 0: acc = 0.0; break;
-        case 1: acc = sum_columns<1>(ip, sbase); break;
-        case 2: acc = sum_columns<2>(ip, sbase); break;
-        case 3: acc = sum_columns<3>(ip, sbase); break;
-        case 4: acc = sum_columns<4>(ip, sbase); break;
-        case 5: acc = sum_columns<5>(ip, sbase); break;
-        case 6: acc = sum_columns<6>(ip, sbase); break;
-        case 7: acc = sum_columns<7>(ip, sbase); break;
-        case 8: acc = sum_columns<8>(ip, sbase); break;
-        default: {
-          double a0 = 0.0, a1 = 0.0;
-          for (uint32_t q = 0; 2 * q < w; ++q) {
-            const uint32_t pr = lds_u32(ip + q * 128);
-            a0 += lds_f64(sbase + (pr & 0xffffu) * 8u);
-            if (2 * q + 1 < w) a1 += lds_f64(sbase + (pr >> 16) * 8u);
+        case 0: {  // slots without contributions (Dirichlet rows/columns): write zeros
+          constexpr int LG = G == 4 ? 2 : (G == 2 ? 1 : 0);
+          for (uint32_t i = (uint32_t)(warp - (int)first) & (NWARPS - 1); i < count; i += NWARPS) {
+            const uint32_t gs = lds_u16(gd0 + ((first + i) * PER_NORM + (split ? (lane >> (LG + 2)) : (lane >> LG))) * 2u);
+            const uint32_t slot = gs * G + (split ? ((lane >> 2) & (G - 1)) : (lane & (G - 1)));
+            if ((!split || (lane & 3) == 0) && slot - lo < span) out[slot] = 0.0;
           }
-          acc = a0 + a1;
+          break;
+        }
+        case 1: SWEEP(1); break;
+        case 2: SWEEP(2); break;
+        case 3: SWEEP(3); break;
+        case 4: SWEEP(4); break;
+        case 5: SWEEP(5); break;
+        case 6: SWEEP(6); break;
+        case 7: SWEEP(7); break;
+        case 8: SWEEP(8); break;
+        default: {  // wider classes (high-valence vertices of unstructured meshes): generic loop
+          constexpr int LG = G == 4 ? 2 : (G == 2 ? 1 : 0);
+          const uint32_t pairs = (w + 1) >> 1;
+          for (uint32_t i = (uint32_t)(warp - (int)first) & (NWARPS - 1); i < count; i += NWARPS) {
+            const uint32_t ip = idx0 + (off64 + i * pairs) * 128u;
+            const uint32_t gs = lds_u16(gd0 + ((first + i) * PER_NORM + (split ? (lane >> (LG + 2)) : (lane >> LG))) * 2u);
+            double a0 = 0.0, a1 = 0.0;
+            for (uint32_t q = 0; q < pairs; ++q) {
+              const uint32_t pr = lds_u32(ip + q * 128);
+              a0 += lds_f64(sbase + (pr & 0xffffu) * 8u);
+              if (2 * q + 1 < w) a1 += lds_f64(sbase + (pr >> 16) * 8u);
+            }
+            double acc = a0 + a1;
+            if (split) {
+              acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+              acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            }
+            const uint32_t slot = gs * G + (split ? ((lane >> 2) & (G - 1)) : (lane & (G - 1)));
+            if ((!split || (lane & 3) == 0) && slot - lo < span) out[slot] = acc;
+          }
         }
       }
-      uint32_t slot = gs * G + sub_norm;
-      bool wr = true;
-      if (split) {
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        slot = gs * G + sub_split;
-        wr = lead;
-      }
-      // sector id 0xffff (no sector) lands far outside [lo, lo + span)
-      if (wr && slot - lo < span) out[slot] = acc;
+#undef SWEEP
     }
     __syncthreads();
-    d = dn;
   }
 }
 
@@ -669,7 +702,7 @@ int launch_gather2_nt(G2Args a, const GatherPlan2 &p, cudaStream_t s) {
   a.off_idx = (int)off;
   off += up16(2 * (size_t)p.max_nidx + 64);
   a.off_meta = (int)off;
-  off += up16(4 * (size_t)p.max_nsl + 16);
+  off += up16(8 * (size_t)PLAN2_MAX_CLASSES + 16);
   a.off_gdst = (int)off;
   off += up16(2 * (size_t)(32 / p.sector) * (size_t)p.max_nsl + 16);
   a.sector = p.sector;
@@ -679,6 +712,8 @@ int launch_gather2_nt(G2Args a, const GatherPlan2 &p, cudaStream_t s) {
   off += up16(4 * (size_t)p.cmax + 16);
   a.off_bar = (int)off;
   off += 32;
+  a.off_desc = (int)off;
+  off += 2 * sizeof(BlockDesc2);
   a.zaddr = p.zaddr;
   const size_t smem = off;
   if (smem > 227 * 1024) return 4;
@@ -764,7 +799,7 @@ int fdts_launch_heat(fdts_engine *e, int which, const double *x, const double *x
   if (e->opt_scatter == 2 && which == 1 && e->plan2.ready) {
     const GatherPlan2 &p = e->plan2;
     G2Args g;
-    g.bdesc = p.bdesc; g.cidx = p.cidx; g.gdst = p.gdst; g.smeta = p.smeta; g.bcc = p.bcc; g.bvcoords = p.bvcoords;
+    g.bdesc = p.bdesc; g.cidx = p.cidx; g.gdst = p.gdst; g.cmeta = p.cmeta; g.bcc = p.bcc; g.bvcoords = p.bvcoords;
     g.out = out; g.nblocks = p.nblocks; g.shift = shift; g.dbg = (int32_t)e->opt_debug;
     int rc = 3;
 #define G2CASE(D, K, V) \
