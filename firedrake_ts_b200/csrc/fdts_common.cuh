@@ -61,7 +61,7 @@ struct BlockDesc2 {             // 80 bytes, one per row block
   int32_t nslots, nidx;         // CSR slots of the block; SELL entries (multiple of 64)
   int32_t ncell, nvert;
   int32_t nsl, ncls;            // slices; slice classes (runs of slices with equal width / split flag)
-  int32_t pad0, pad1;
+  int32_t pattern, pad1;        // pattern id (first block with identical tables)
 };
 constexpr int PLAN2_MAX_CLASSES = 32;
 // slice class (8 bytes): lo = first slice | count << 16, hi = first offset (units of 64 entries) | width << 16 | split << 24
@@ -116,7 +116,7 @@ struct fdts_engine {
   int64_t opt_dedup = 1;         // plan 2: share identical block patterns
   int64_t opt_sector = 4;        // plan 2: slots per store group (4 or 2)
   int64_t opt_optimize = 1;      // plan 2: bank-conflict-aware column order for the unique patterns
-  int64_t opt_threads = 1024;    // plan 2: threads per persistent CTA (512 or 1024)
+  int64_t opt_threads = 512;     // plan 2: threads per persistent CTA (512: 128 registers per thread, or 1024)
   int64_t opt_debug = 0;         // development only (timing experiments with phases switched off)
   int variant = -1;              // which baked RefT table matches cfg.R (-1: none, closed-form path off)
   // scratch

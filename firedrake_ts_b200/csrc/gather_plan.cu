@@ -833,7 +833,8 @@ __global__ void block_descriptors2(const int64_t *__restrict__ bstart, int64_t n
   x.nsl = (int32_t)bnsl_true[b];
   x.ncls = bncls[b];
   x.cls_off = b * (int64_t)PLAN2_MAX_CLASSES;
-  x.pad0 = x.pad1 = 0;
+  x.pattern = (int32_t)b;
+  x.pad1 = 0;
   d[b] = x;
 }
 
@@ -896,6 +897,7 @@ __global__ void apply_representatives(BlockDesc2 *__restrict__ d, const int64_t 
   d[b].meta_off = d[r].meta_off;
   d[b].cc_off = d[r].cc_off;
   d[b].cls_off = d[r].cls_off;
+  d[b].pattern = (int32_t)r;
 }
 
 struct PairHash {

@@ -479,13 +479,17 @@ __device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
   asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
 
-// sums W staged contributions of one slot; ip = shared address of the lane's first 32-bit pair of
-// 16-bit staging addresses (units of 8 bytes), sbase = shared address of the staging area
+// loads the W 16-bit staging addresses of one slot (two per 32-bit word); ip = shared address of the
+// lane's first word
 template <int W>
-__device__ __forceinline__ double sum_columns(uint32_t ip, uint32_t sbase) {
-  uint32_t pr[(W + 1) / 2];
+__device__ __forceinline__ void load_pairs(uint32_t ip, uint32_t (&pr)[(W + 1) / 2]) {
 #pragma unroll
   for (int q = 0; q < (W + 1) / 2; ++q) pr[q] = lds_u32(ip + q * 128);
+}
+
+// sums the W staged contributions addressed by pr (units of 8 bytes from sbase)
+template <int W>
+__device__ __forceinline__ double sum_pairs(const uint32_t (&pr)[(W + 1) / 2], uint32_t sbase) {
   double v[W];
 #pragma unroll
   for (int k = 0; k < W; ++k)
@@ -528,20 +532,39 @@ __device__ __forceinline__ void sweep_class(uint32_t first, uint32_t count, uint
   const bool wr = split ? (lane & 3) == 0 : true;
   uint32_t ip = idx0 + (off64 + i * PAIRS) * 128u;
   uint32_t gd = gd0 + ((first + i) * PER_NORM + gsel) * 2u;
-  for (; i < count; i += NWARPS, ip += NWARPS * PAIRS * 128u, gd += NWARPS * PER_NORM * 2u) {
-    const uint32_t gs = lds_u16(gd);
-    double acc = sum_columns<W>(ip, sbase);
+  if (i >= count) return;
+  // software pipeline: the addresses and the sector id of the warp's next slice are fetched while the
+  // current slice is summed
+  uint32_t pr[PAIRS];
+  load_pairs<W>(ip, pr);
+  uint32_t gs = lds_u16(gd);
+  for (;;) {
+    const uint32_t in = i + NWARPS;
+    const bool has_next = in < count;
+    uint32_t prn[PAIRS], gsn = 0;
+    ip += NWARPS * PAIRS * 128u;
+    gd += NWARPS * PER_NORM * 2u;
+    if (has_next) {
+      load_pairs<W>(ip, prn);
+      gsn = lds_u16(gd);
+    }
+    double acc = sum_pairs<W>(pr, sbase);
     if (split) {
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     }
     const uint32_t slot = gs * G + sub;  // sector id 0xffff (none) lands far outside [lo, lo + span)
     if (wr && slot - lo < span) out[slot] = acc;
+    if (!has_next) break;
+#pragma unroll
+    for (int q = 0; q < PAIRS; ++q) pr[q] = prn[q];
+    gs = gsn;
+    i = in;
   }
 }
 
 template <int DIM, int DEG, int VAR, int NT, int G>
-__global__ void __launch_bounds__(NT, NT <= 512 ? 2 : 1) heat_jacobian_gather2(const G2Args a) {
+__global__ void __launch_bounds__(NT, 1) heat_jacobian_gather2(const G2Args a) {
   using T = RefT<DIM, DEG, VAR>;
   constexpr int ND = T::ND, NP = T::NP, NEP = (ND * (ND + 1) / 2) | 1;
   constexpr int NWARPS = NT / 32;
@@ -555,9 +578,10 @@ __global__ void __launch_bounds__(NT, NT <= 512 ? 2 : 1) heat_jacobian_gather2(c
   const uint32_t gd0 = sbase + a.off_gdst;
   const uint32_t cls0 = sbase + a.off_meta;
 
-  auto issue_A = [&](const BlockDesc2 &d) {  // vertex table + local vertex ids
+  // phase-A inputs: vertex table (always) + local vertex ids (only when the pattern changes)
+  auto issue_A = [&](const BlockDesc2 &d, bool with_cells) {
     const uint32_t vb = (uint32_t)(((d.nvert * DIM + 1) & ~1) * 8);
-    const uint32_t cb = (uint32_t)(((d.ncell + 3) & ~3) * 4);
+    const uint32_t cb = with_cells ? (uint32_t)(((d.ncell + 3) & ~3) * 4) : 0u;
     mbar_expect_tx(&bars[0], vb + cb);
     if (vb) bulk_g2s(smraw + a.off_vtab, a.bvcoords + d.vc_off, vb, &bars[0]);
     if (cb) bulk_g2s(smraw + a.off_lcc, a.bcc + d.cc_off, cb, &bars[0]);
@@ -578,18 +602,28 @@ __global__ void __launch_bounds__(NT, NT <= 512 ? 2 : 1) heat_jacobian_gather2(c
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     sdesc[0] = a.bdesc[b];
-    issue_A(sdesc[0]);
+    issue_A(sdesc[0], true);
   }
   if (threadIdx.x < 16) sts_f64(sbase + (a.zaddr + threadIdx.x) * 8, 0.0);  // one staged zero per 8-byte bank
   __syncthreads();
+  // Pattern residency: consecutive blocks of a structured mesh mostly share one pattern, so the index
+  // tables already in shared memory are reused and only reloaded when the pattern id changes.
+  int resident = -1;
+  uint32_t nloadB = 0;
   for (int it = 0; b < a.nblocks; ++it, b += stride) {
     const int64_t bn = b + stride;
     const bool more = bn < a.nblocks;
     const BlockDesc2 &d = sdesc[it & 1];
+    const int pattern = d.pattern;
+    const bool loadB = pattern != resident;
     BlockDesc2 dn;
     if (threadIdx.x == 0) {
-      issue_B(d);
+      if (loadB) issue_B(d);
       if (more) dn = a.bdesc[bn];
+    }
+    if (loadB) {
+      resident = pattern;
+      ++nloadB;
     }
     // ---- phase A
     mbar_wait(&bars[0], (uint32_t)(it & 1));
@@ -634,10 +668,10 @@ __global__ void __launch_bounds__(NT, NT <= 512 ? 2 : 1) heat_jacobian_gather2(c
     }
     if (threadIdx.x == 0 && more) sdesc[(it + 1) & 1] = dn;
     __syncthreads();
-    if (threadIdx.x == 0 && more) issue_A(dn);
+    if (threadIdx.x == 0 && more) issue_A(dn, dn.pattern != pattern);
     // ---- phase B: class by class, no barrier in between
-    mbar_wait(&bars[1], (uint32_t)(it & 1));
-    const uint32_t lo = (uint32_t)(d.s0 & (G - 1)), span = (uint32_t)d.nslots;
+    if (loadB) mbar_wait(&bars[1], (nloadB - 1u) & 1u);
+    const uint32_t lo = (uint32_t)(d.s0 & (G - 1)), span = (a.dbg & 8) ? 0u : (uint32_t)d.nslots;
     double *__restrict__ out = a.out + (d.s0 - lo);
     const int ncls = (a.dbg & 2) ? 0 : d.ncls;
     for (int c = 0; c < ncls; ++c) {

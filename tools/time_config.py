@@ -25,7 +25,7 @@ ap.add_argument("--plan", type=int, default=2)
 ap.add_argument("--debug", type=int, default=0)
 ap.add_argument("--sector", type=int, default=4)
 ap.add_argument("--optimize", type=int, default=1)
-ap.add_argument("--threads", type=int, default=1024)
+ap.add_argument("--threads", type=int, default=512)
 ap.add_argument("--dedup", type=int, default=1)
 ap.add_argument("--foffset", type=int, default=0)
 a = ap.parse_args()
