@@ -120,6 +120,7 @@ KArgs fdts_make_kargs(fdts_engine *e, const double *x, const double *xdot, doubl
   a.xdot = xdot;
   a.out = out;
   a.isbc = e->isbc;
+  a.rowmask = e->cell_rowmask;
   a.nrowptr = e->nrowptr;
   a.pos8_t = e->pos8;
   a.ncells_total = e->cfg.num_cells;
@@ -251,7 +252,7 @@ extern "C" int fdts_destroy(fdts_handle e) {
   cudaSetDevice(e->device);
   void *ptrs[] = {e->coords, e->cell_coord, e->cell_node, e->B, e->w, e->R, e->M0, e->isbc, e->bc_nodes,
                   e->bc_diag_slot, e->nrowptr, e->ncolidx, e->pos8, e->adj_ptr, e->adj_cell, e->h2d_x, e->h2d_xdot,
-                  e->d_f, e->d_vals};
+                  e->d_f, e->d_vals, e->cell_rowmask};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   fdts_free_plan(e);
@@ -347,8 +348,8 @@ extern "C" int fdts_set_option(fdts_handle e, const char *key, int64_t value) {
     return 0;
   }
   if (!strcmp(key, "threads")) {
-    if (value != 512 && value != 1024) {
-      fdts_set_error("threads must be 512 or 1024");
+    if (value != 384 && value != 512 && value != 768 && value != 1024) {
+      fdts_set_error("threads must be 384, 512, 768 or 1024");
       return 1;
     }
     e->opt_threads = value;

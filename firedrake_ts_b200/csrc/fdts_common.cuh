@@ -93,6 +93,7 @@ struct fdts_engine {
   double *B = nullptr, *w = nullptr, *R = nullptr, *M0 = nullptr;
   // boundary conditions
   uint8_t *isbc = nullptr;       // per local node
+  uint32_t *cell_rowmask = nullptr;  // per cell: bit i = local node i is an owned non-Dirichlet row
   int32_t *bc_nodes = nullptr;   // owned Dirichlet nodes
   int64_t num_bc_owned = 0;
   int64_t *bc_diag_slot = nullptr;  // dof-level slot of the diagonal entry, per (bc node, comp)

@@ -23,6 +23,7 @@ struct KArgs {
   const double *x, *xdot;
   double *out;
   const uint8_t *isbc;
+  const uint32_t *rowmask;      // per cell: owned non-Dirichlet rows (bit per local node)
   const int64_t *nrowptr;
   const uint8_t *pos8_t;        // (ND*ND) x ncells_total
   int64_t ncells_total, c0, c1, nown, nnodes, node_nnz;

@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(128) heat_residual_atomic(const KArgs a) {
   for (int v = 0; v <= DIM; ++v) cc[v] = a.cell_coord_t[v * a.ncells_total + c];
 #pragma unroll
   for (int i = 0; i < ND; ++i) nodes[i] = a.cell_node_t[i * a.ncells_total + c];
+  const uint32_t rowok = a.rowmask[c];
   Geom<DIM> g;
   compute_geometry<DIM>(a.coords, cc, g);
   double gm[NP];
@@ -133,8 +134,7 @@ __global__ void __launch_bounds__(128) heat_residual_atomic(const KArgs a) {
       });
       f = fma(gm[p], s, f);
     });
-    const int64_t n = nodes[i];
-    if (n < a.nown && !a.isbc[n]) red_add_f64(a.out + n, f);
+    if ((rowok >> i) & 1u) red_add_f64(a.out + nodes[i], f);
   });
 }
 
@@ -520,13 +520,22 @@ __device__ __forceinline__ double heat_entry_i(double ms, const double (&gs)[NP]
   return v;
 }
 
+// slices are dealt round-robin over the whole block (slice s -> warp s mod NWARPS): index inside the
+// class of the first slice that belongs to `warp`
+template <int NWARPS>
+__device__ __forceinline__ uint32_t first_slice_of(int warp, uint32_t first) {
+  if constexpr ((NWARPS & (NWARPS - 1)) == 0) return (uint32_t)(warp - (int)first) & (NWARPS - 1);
+  const int r = (warp - (int)(first % NWARPS)) % NWARPS;
+  return (uint32_t)(r < 0 ? r + NWARPS : r);
+}
+
 // one class of slices (equal width W, equal split flag): warp `warp` takes the slices congruent to it
 template <int W, int G, int NWARPS>
 __device__ __forceinline__ void sweep_class(uint32_t first, uint32_t count, uint32_t off64, bool split, int warp, int lane,
                                             uint32_t idx0, uint32_t gd0, uint32_t sbase, double *__restrict__ out,
                                             uint32_t lo, uint32_t span) {
   constexpr int LG = G == 4 ? 2 : (G == 2 ? 1 : 0), PER_NORM = 32 / G, PAIRS = (W + 1) / 2;
-  uint32_t i = (uint32_t)(warp - (int)first) & (NWARPS - 1);
+  uint32_t i = first_slice_of<NWARPS>(warp, first);
   const uint32_t gsel = split ? (uint32_t)(lane >> (LG + 2)) : (uint32_t)(lane >> LG);
   const uint32_t sub = split ? (uint32_t)((lane >> 2) & (G - 1)) : (uint32_t)(lane & (G - 1));
   const bool wr = split ? (lane & 3) == 0 : true;
@@ -683,7 +692,7 @@ __global__ void __launch_bounds__(NT, 1) heat_jacobian_gather2(const G2Args a) {
       switch (w) {
         case 0: {  // slots without contributions (Dirichlet rows/columns): write zeros
           constexpr int LG = G == 4 ? 2 : (G == 2 ? 1 : 0);
-          for (uint32_t i = (uint32_t)(warp - (int)first) & (NWARPS - 1); i < count; i += NWARPS) {
+          for (uint32_t i = first_slice_of<NWARPS>(warp, first); i < count; i += NWARPS) {
             const uint32_t gs = lds_u16(gd0 + ((first + i) * PER_NORM + (split ? (lane >> (LG + 2)) : (lane >> LG))) * 2u);
             const uint32_t slot = gs * G + (split ? ((lane >> 2) & (G - 1)) : (lane & (G - 1)));
             if ((!split || (lane & 3) == 0) && slot - lo < span) out[slot] = 0.0;
@@ -701,7 +710,7 @@ __global__ void __launch_bounds__(NT, 1) heat_jacobian_gather2(const G2Args a) {
         default: {  // wider classes (high-valence vertices of unstructured meshes): generic loop
           constexpr int LG = G == 4 ? 2 : (G == 2 ? 1 : 0);
           const uint32_t pairs = (w + 1) >> 1;
-          for (uint32_t i = (uint32_t)(warp - (int)first) & (NWARPS - 1); i < count; i += NWARPS) {
+          for (uint32_t i = first_slice_of<NWARPS>(warp, first); i < count; i += NWARPS) {
             const uint32_t ip = idx0 + (off64 + i * pairs) * 128u;
             const uint32_t gs = lds_u16(gd0 + ((first + i) * PER_NORM + (split ? (lane >> (LG + 2)) : (lane >> LG))) * 2u);
             double a0 = 0.0, a1 = 0.0;
@@ -771,6 +780,8 @@ int launch_gather2_nt(G2Args a, const GatherPlan2 &p, cudaStream_t s) {
 template <int DIM, int DEG, int VAR>
 int launch_gather2(G2Args a, const GatherPlan2 &p, int threads, cudaStream_t s) {
   if (threads == 512) return launch_gather2_nt<DIM, DEG, VAR, 512>(a, p, s);
+  if (threads == 768) return launch_gather2_nt<DIM, DEG, VAR, 768>(a, p, s);
+  if (threads == 384) return launch_gather2_nt<DIM, DEG, VAR, 384>(a, p, s);
   return launch_gather2_nt<DIM, DEG, VAR, 1024>(a, p, s);
 }
 

@@ -140,6 +140,20 @@ __global__ void slot_positions(const int32_t *__restrict__ cell_node_t, int64_t 
   }
 }
 
+// per cell: bit i set iff local node i is an owned, non-Dirichlet row (one coalesced 32-bit load in the
+// scatter kernels instead of nd dependent byte loads of isbc)
+__global__ void cell_row_masks(const int32_t *__restrict__ cell_node_t, int64_t nc, int nd, int64_t nown,
+                               const uint8_t *__restrict__ isbc, uint32_t *__restrict__ rowmask) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  uint32_t m = 0;
+  for (int i = 0; i < nd; ++i) {
+    const int32_t n = cell_node_t[(int64_t)i * nc + c];
+    if (n < nown && !isbc[n]) m |= 1u << i;
+  }
+  rowmask[c] = m;
+}
+
 __global__ void mark_bc(const int32_t *__restrict__ bc_nodes, int64_t nbc, uint8_t *__restrict__ isbc) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < nbc) isbc[bc_nodes[t]] = 1;
@@ -264,6 +278,8 @@ int fdts_build_pattern(fdts_engine *e, cudaStream_t s) {
     bc_diag_slots<<<GRID(nbc, 256), 256, 0, s>>>(e->bc_nodes, nbc, e->cfg.ncomp, e->cfg.layout, nown, e->node_nnz,
                                                   e->nrowptr, e->ncolidx, e->bc_diag_slot);
   }
+  FDTS_CHECK(cudaMalloc(&e->cell_rowmask, sizeof(uint32_t) * (size_t)(nc > 0 ? nc : 1)));
+  if (nc > 0) cell_row_masks<<<GRID(nc, 256), 256, 0, s>>>(e->cell_node, nc, nd, nown, e->isbc, e->cell_rowmask);
   int herr = 0;
   FDTS_CHECK(cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, s));
   FDTS_CHECK(cudaStreamSynchronize(s));
