@@ -456,7 +456,7 @@ struct G2Args {
   double *out;
   int64_t nblocks;
   double shift;
-  int32_t off_idx, off_meta, off_gdst, off_vtab, off_lcc, off_bar, off_desc, zaddr, sector;
+  int32_t off_idx, off_meta, off_gdst, off_vtab, off_lcc, off_bar, off_desc, zaddr, sector, inA_bytes;
   int32_t dbg;  // development only: bit0 skips phase A, bit1 skips phase B (timing experiments; results are wrong)
 };
 
@@ -573,27 +573,31 @@ __device__ __forceinline__ void sweep_class(uint32_t first, uint32_t count, uint
 }
 
 template <int DIM, int DEG, int VAR, int NT, int G>
-__global__ void __launch_bounds__(NT, 1) heat_jacobian_gather2(const G2Args a) {
+__global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) heat_jacobian_gather2(const G2Args a) {
   using T = RefT<DIM, DEG, VAR>;
   constexpr int ND = T::ND, NP = T::NP, NEP = (ND * (ND + 1) / 2) | 1;
   constexpr int NWARPS = NT / 32;
   constexpr int PER_NORM = 32 / G;
   extern __shared__ __align__(16) unsigned char smraw[];
   uint64_t *bars = reinterpret_cast<uint64_t *>(smraw + a.off_bar);
-  BlockDesc2 *sdesc = reinterpret_cast<BlockDesc2 *>(smraw + a.off_desc);  // [2]: current / next block
+  BlockDesc2 *sdesc = reinterpret_cast<BlockDesc2 *>(smraw + a.off_desc);  // ring of 4 blocks
   const uint32_t sbase = smem_u32(smraw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // bulk copies and descriptor fetches are issued by lane 0 of the LAST warp: phase A fills the warps from
+  // the front (one cell per thread), so this warp is normally idle there and the issue latency of the
+  // copies (~1000 cycles measured) stays off the critical path
+  const bool producer = threadIdx.x == NT - 32;
   const uint32_t idx0 = sbase + a.off_idx + lane * 4;
   const uint32_t gd0 = sbase + a.off_gdst;
   const uint32_t cls0 = sbase + a.off_meta;
 
-  // phase-A inputs: vertex table (always) + local vertex ids (only when the pattern changes)
-  auto issue_A = [&](const BlockDesc2 &d, bool with_cells) {
+  // phase-A inputs (vertex table + local vertex ids), double buffered: issued one block ahead
+  auto issue_A = [&](const BlockDesc2 &d, int buf) {
     const uint32_t vb = (uint32_t)(((d.nvert * DIM + 1) & ~1) * 8);
-    const uint32_t cb = with_cells ? (uint32_t)(((d.ncell + 3) & ~3) * 4) : 0u;
-    mbar_expect_tx(&bars[0], vb + cb);
-    if (vb) bulk_g2s(smraw + a.off_vtab, a.bvcoords + d.vc_off, vb, &bars[0]);
-    if (cb) bulk_g2s(smraw + a.off_lcc, a.bcc + d.cc_off, cb, &bars[0]);
+    const uint32_t cb = (uint32_t)(((d.ncell + 3) & ~3) * 4);
+    mbar_expect_tx(&bars[2 + buf], vb + cb);
+    if (vb) bulk_g2s(smraw + a.off_vtab + buf * a.inA_bytes, a.bvcoords + d.vc_off, vb, &bars[2 + buf]);
+    if (cb) bulk_g2s(smraw + a.off_lcc + buf * a.inA_bytes, a.bcc + d.cc_off, cb, &bars[2 + buf]);
   };
   auto issue_B = [&](const BlockDesc2 &d) {  // SELL addresses, class table, sector ids
     const uint32_t nslp = (uint32_t)((d.nsl + 3) & ~3);
@@ -607,11 +611,15 @@ __global__ void __launch_bounds__(NT, 1) heat_jacobian_gather2(const G2Args a) {
   const int64_t stride = gridDim.x;
   int64_t b = blockIdx.x;
   if (b >= a.nblocks) return;
-  if (threadIdx.x == 0) {
-    mbar_init(&bars[0], 1);
+  // descriptors are fetched two blocks ahead (ring of four in shared memory), phase-A inputs one block
+  // ahead, so no dependent global access sits on a block's critical path
+  if (producer) {
     mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    mbar_init(&bars[3], 1);
     sdesc[0] = a.bdesc[b];
-    issue_A(sdesc[0], true);
+    if (b + stride < a.nblocks) sdesc[1] = a.bdesc[b + stride];
+    issue_A(sdesc[0], 0);
   }
   if (threadIdx.x < 16) sts_f64(sbase + (a.zaddr + threadIdx.x) * 8, 0.0);  // one staged zero per 8-byte bank
   __syncthreads();
@@ -620,29 +628,30 @@ __global__ void __launch_bounds__(NT, 1) heat_jacobian_gather2(const G2Args a) {
   int resident = -1;
   uint32_t nloadB = 0;
   for (int it = 0; b < a.nblocks; ++it, b += stride) {
-    const int64_t bn = b + stride;
-    const bool more = bn < a.nblocks;
-    const BlockDesc2 &d = sdesc[it & 1];
+    const int64_t bn = b + stride, bnn = bn + stride;
+    const BlockDesc2 &d = sdesc[it & 3];
     const int pattern = d.pattern;
     const bool loadB = pattern != resident;
-    BlockDesc2 dn;
-    if (threadIdx.x == 0) {
+    BlockDesc2 dnn;
+    if (producer) {
       if (loadB) issue_B(d);
-      if (more) dn = a.bdesc[bn];
+      if (bn < a.nblocks) issue_A(sdesc[(it + 1) & 3], (it + 1) & 1);
+      if (bnn < a.nblocks) dnn = a.bdesc[bnn];
     }
     if (loadB) {
       resident = pattern;
       ++nloadB;
     }
     // ---- phase A
-    mbar_wait(&bars[0], (uint32_t)(it & 1));
+    mbar_wait(&bars[2 + (it & 1)], (uint32_t)((it >> 1) & 1));
     const int ncell = (a.dbg & 1) ? 0 : d.ncell;
+    const uint32_t lcc0 = sbase + a.off_lcc + (it & 1) * a.inA_bytes, vt0 = sbase + a.off_vtab + (it & 1) * a.inA_bytes;
     for (int k = threadIdx.x; k < ncell; k += NT) {
-      const uint32_t packed = lds_u32(sbase + a.off_lcc + k * 4);
+      const uint32_t packed = lds_u32(lcc0 + k * 4);
       double X[DIM + 1][DIM];
 #pragma unroll
       for (int v = 0; v <= DIM; ++v) {
-        const uint32_t va = sbase + a.off_vtab + ((packed >> (8 * v)) & 255u) * (DIM * 8);
+        const uint32_t va = vt0 + ((packed >> (8 * v)) & 255u) * (DIM * 8);
 #pragma unroll
         for (int q = 0; q < DIM; ++q) X[v][q] = lds_f64(va + q * 8);
       }
@@ -675,9 +684,8 @@ __global__ void __launch_bounds__(NT, 1) heat_jacobian_gather2(const G2Args a) {
         });
       }
     }
-    if (threadIdx.x == 0 && more) sdesc[(it + 1) & 1] = dn;
+    if (producer && bnn < a.nblocks) sdesc[(it + 2) & 3] = dnn;
     __syncthreads();
-    if (threadIdx.x == 0 && more) issue_A(dn, dn.pattern != pattern);
     // ---- phase B: class by class, no barrier in between
     if (loadB) mbar_wait(&bars[1], (nloadB - 1u) & 1u);
     const uint32_t lo = (uint32_t)(d.s0 & (G - 1)), span = (a.dbg & 8) ? 0u : (uint32_t)d.nslots;
@@ -749,14 +757,15 @@ int launch_gather2_nt(G2Args a, const GatherPlan2 &p, cudaStream_t s) {
   a.off_gdst = (int)off;
   off += up16(2 * (size_t)(32 / p.sector) * (size_t)p.max_nsl + 16);
   a.sector = p.sector;
+  // phase-A inputs: two buffers of (vertex table, local vertex ids)
+  a.inA_bytes = (int)(up16(8 * (size_t)p.vmax * DIM + 16) + up16(4 * (size_t)p.cmax + 16));
   a.off_vtab = (int)off;
-  off += up16(8 * (size_t)p.vmax * DIM + 16);
-  a.off_lcc = (int)off;
-  off += up16(4 * (size_t)p.cmax + 16);
+  a.off_lcc = (int)(off + up16(8 * (size_t)p.vmax * DIM + 16));
+  off += 2 * (size_t)a.inA_bytes;
   a.off_bar = (int)off;
   off += 32;
   a.off_desc = (int)off;
-  off += 2 * sizeof(BlockDesc2);
+  off += 4 * sizeof(BlockDesc2);
   a.zaddr = p.zaddr;
   const size_t smem = off;
   if (smem > 227 * 1024) return 4;
@@ -782,6 +791,7 @@ int launch_gather2(G2Args a, const GatherPlan2 &p, int threads, cudaStream_t s) 
   if (threads == 512) return launch_gather2_nt<DIM, DEG, VAR, 512>(a, p, s);
   if (threads == 768) return launch_gather2_nt<DIM, DEG, VAR, 768>(a, p, s);
   if (threads == 384) return launch_gather2_nt<DIM, DEG, VAR, 384>(a, p, s);
+  if (threads == 256) return launch_gather2_nt<DIM, DEG, VAR, 256>(a, p, s);
   return launch_gather2_nt<DIM, DEG, VAR, 1024>(a, p, s);
 }
 
