@@ -347,6 +347,10 @@ extern "C" int fdts_set_option(fdts_handle e, const char *key, int64_t value) {
     e->opt_optimize = value ? 1 : 0;
     return 0;
   }
+  if (!strcmp(key, "overlap")) {
+    e->opt_overlap = value ? 1 : 0;
+    return 0;
+  }
   if (!strcmp(key, "threads")) {
     if (value != 256 && value != 384 && value != 512 && value != 768 && value != 1024) {
       fdts_set_error("threads must be 256, 384, 512, 768 or 1024");

@@ -117,6 +117,7 @@ struct fdts_engine {
   int64_t opt_dedup = 1;         // plan 2: share identical block patterns
   int64_t opt_sector = 4;        // plan 2: slots per store group (4 or 2)
   int64_t opt_optimize = 1;      // plan 2: bank-conflict-aware column order for the unique patterns
+  int64_t opt_overlap = 0;       // plan 2: warp-specialised kernel (element matrices of block b+1 overlap the gather of block b; needs two staging buffers in smem; slower than the two-phase kernel on every block shape measured so far)
   int64_t opt_threads = 512;     // plan 2: threads per persistent CTA (512: 128 registers per thread, or 1024)
   int64_t opt_debug = 0;         // development only (timing experiments with phases switched off)
   int variant = -1;              // which baked RefT table matches cfg.R (-1: none, closed-form path off)
@@ -225,6 +226,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(

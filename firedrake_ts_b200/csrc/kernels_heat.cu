@@ -456,7 +456,7 @@ struct G2Args {
   double *out;
   int64_t nblocks;
   double shift;
-  int32_t off_idx, off_meta, off_gdst, off_vtab, off_lcc, off_bar, off_desc, zaddr, sector, inA_bytes;
+  int32_t off_idx, off_meta, off_gdst, off_vtab, off_lcc, off_bar, off_desc, zaddr, sector, inA_bytes, stage_bytes;
   int32_t dbg;  // development only: bit0 skips phase A, bit1 skips phase B (timing experiments; results are wrong)
 };
 
@@ -530,7 +530,7 @@ __device__ __forceinline__ uint32_t first_slice_of(int warp, uint32_t first) {
 }
 
 // one class of slices (equal width W, equal split flag): warp `warp` takes the slices congruent to it
-template <int W, int G, int NWARPS>
+template <int W, int G, int NWARPS, bool PIPE = true>
 __device__ __forceinline__ void sweep_class(uint32_t first, uint32_t count, uint32_t off64, bool split, int warp, int lane,
                                             uint32_t idx0, uint32_t gd0, uint32_t sbase, double *__restrict__ out,
                                             uint32_t lo, uint32_t span) {
@@ -542,6 +542,21 @@ __device__ __forceinline__ void sweep_class(uint32_t first, uint32_t count, uint
   uint32_t ip = idx0 + (off64 + i * PAIRS) * 128u;
   uint32_t gd = gd0 + ((first + i) * PER_NORM + gsel) * 2u;
   if (i >= count) return;
+  if constexpr (!PIPE) {  // plain loop (fits 64 registers: used when the CTA runs 32 warps)
+    for (; i < count; i += NWARPS, ip += NWARPS * PAIRS * 128u, gd += NWARPS * PER_NORM * 2u) {
+      uint32_t pr[PAIRS];
+      load_pairs<W>(ip, pr);
+      const uint32_t gs = lds_u16(gd);
+      double acc = sum_pairs<W>(pr, sbase);
+      if (split) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      }
+      const uint32_t slot = gs * G + sub;
+      if (wr && slot - lo < span) out[slot] = acc;
+    }
+    return;
+  }
   // software pipeline: the addresses and the sector id of the warp's next slice are fetched while the
   // current slice is summed
   uint32_t pr[PAIRS];
@@ -743,6 +758,264 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) heat_jacobian_gather2(c
   }
 }
 
+// ------------------------------------------------------------------ path 2, plan 2, warp-specialised
+// Same plan, same arithmetic, same summation order as heat_jacobian_gather2, but the two phases run
+// concurrently on different warps of one persistent CTA with two staging buffers:
+//   NPW producer warps   element matrices of block b+1 -> stage[(b+1)&1]        (fp64 pipe)
+//   NCW consumer warps   gather/sum/store of block b from stage[b&1]            (shared-memory pipe)
+//   1 copy warp          lane 0 issues every TMA bulk copy and fetches the block descriptors
+// Hand-over through mbarriers: full[s] (producers -> consumers), empty[s] (consumers -> producers),
+// inA[s] (copy warp -> producers); no CTA-wide barrier after the prologue.  The index tables of the
+// resident pattern are only reloaded (by the consumers themselves) when the pattern changes.
+template <int DIM, int DEG, int VAR, int NPW, int NCW, int G>
+__global__ void __launch_bounds__((NPW + NCW + 1) * 32, 1) heat_jacobian_gather3(const G2Args a) {
+  using T = RefT<DIM, DEG, VAR>;
+  constexpr int ND = T::ND, NP = T::NP, NEP = (ND * (ND + 1) / 2) | 1;
+  constexpr int PER_NORM = 32 / G;
+  constexpr int NDESC = 8;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smraw + a.off_bar);
+  constexpr int NA = 4;  // ring of phase-A input buffers: copies run three blocks ahead of the producers
+  uint64_t *inA = bars, *freeA = bars + NA, *full = bars + 2 * NA, *empty = bars + 2 * NA + 2, *barB = bars + 2 * NA + 4;
+  BlockDesc2 *sdesc = reinterpret_cast<BlockDesc2 *>(smraw + a.off_desc);  // ring of NDESC blocks
+  const uint32_t sbase = smem_u32(smraw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t stride = gridDim.x;
+  const int64_t b0 = blockIdx.x;
+  if (b0 >= a.nblocks) return;
+  const int64_t nmine = (a.nblocks - b0 + stride - 1) / stride;  // blocks of this CTA
+
+  auto issue_A = [&](const BlockDesc2 &d, int buf) {
+    const uint32_t vb = (uint32_t)(((d.nvert * DIM + 1) & ~1) * 8);
+    const uint32_t cb = (uint32_t)(((d.ncell + 3) & ~3) * 4);
+    mbar_expect_tx(&inA[buf], vb + cb);
+    if (vb) bulk_g2s(smraw + a.off_vtab + buf * a.inA_bytes, a.bvcoords + d.vc_off, vb, &inA[buf]);
+    if (cb) bulk_g2s(smraw + a.off_lcc + buf * a.inA_bytes, a.bcc + d.cc_off, cb, &inA[buf]);
+  };
+
+  // ---- prologue (the only CTA-wide barrier)
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < NA; ++q) {
+      mbar_init(&inA[q], 1);
+      mbar_init(&freeA[q], NPW);
+    }
+    mbar_init(&full[0], NPW);
+    mbar_init(&full[1], NPW);
+    mbar_init(&empty[0], NCW);
+    mbar_init(&empty[1], NCW);
+    mbar_init(barB, 1);
+    for (int q = 0; q < NA && q < nmine; ++q) {
+      sdesc[q] = a.bdesc[b0 + q * stride];
+      if (q < NA - 1) issue_A(sdesc[q], q);
+    }
+  }
+  if (threadIdx.x < 32) {  // one staged zero per 8-byte bank, in both staging buffers
+    const int q = threadIdx.x & 15, buf = threadIdx.x >> 4;
+    sts_f64(sbase + buf * a.stage_bytes + (a.zaddr + q) * 8, 0.0);
+  }
+  __syncthreads();
+
+  if (warp == NPW + NCW) {
+    // ================= copy warp
+    if (lane == 0) {
+      for (int64_t it = 0; it < nmine; ++it) {
+        // the phase-A inputs of block it+NA-1 reuse the buffer of block it-1: wait until the producers have
+        // released it (freeA cannot run ahead of this wait: its next phase needs the refill issued here);
+        // the copy is issued first, the (slow, dependent) descriptor fetch for block it+NA afterwards
+        if (it >= 1) mbar_wait(&freeA[(it - 1) % NA], (uint32_t)(((it - 1) / NA) & 1));
+        if (it + NA - 1 < nmine) issue_A(sdesc[(it + NA - 1) % NDESC], (int)((it + NA - 1) % NA));
+        if (it + NA < nmine) sdesc[(it + NA) % NDESC] = a.bdesc[b0 + (it + NA) * stride];
+      }
+    }
+  } else if (warp < NPW) {
+    // ================= producers: element matrices
+    const int tid = threadIdx.x;  // 0 .. NPW*32-1
+    for (int64_t it = 0; it < nmine; ++it) {
+      const int s = (int)(it & 1);
+      if (it >= 2) mbar_wait(&empty[s], (uint32_t)((((it >> 1) - 1)) & 1));
+      const int qa = (int)(it % NA);
+      mbar_wait(&inA[qa], (uint32_t)((it / NA) & 1));
+      const BlockDesc2 &d = sdesc[it % NDESC];
+      const int ncell = (a.dbg & 1) ? 0 : d.ncell;
+      const uint32_t lcc0 = sbase + a.off_lcc + qa * a.inA_bytes, vt0 = sbase + a.off_vtab + qa * a.inA_bytes;
+      const uint32_t stb = sbase + s * a.stage_bytes;
+      for (int k = tid; k < ncell; k += NPW * 32) {
+        const uint32_t packed = lds_u32(lcc0 + k * 4);
+        double X[DIM + 1][DIM];
+#pragma unroll
+        for (int v = 0; v <= DIM; ++v) {
+          const uint32_t va = vt0 + ((packed >> (8 * v)) & 255u) * (DIM * 8);
+#pragma unroll
+          for (int q = 0; q < DIM; ++q) X[v][q] = lds_f64(va + q * 8);
+        }
+        Geom<DIM> g;
+        geometry_from_vertices<DIM>(X, g);
+        double gm[NP];
+        metric<DIM>(g, gm);
+        const uint32_t st = stb + k * (NEP * 8);
+        if constexpr (T::INT) {
+          const double ms = a.shift * g.adet * (1.0 / T::RDEN);
+#pragma unroll
+          for (int p = 0; p < NP; ++p) gm[p] *= (1.0 / T::SDEN);
+          static_for<ND>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            static_for<ND - i>([&](auto JJ) {
+              constexpr int j = i + decltype(JJ)::value;
+              constexpr int e = i * ND - (i * (i - 1)) / 2 + (j - i);
+              sts_f64(st + e * 8, heat_entry_i<T, i, j, NP>(ms, gm));
+            });
+          });
+        } else {
+          const double m = a.shift * g.adet;
+          static_for<ND>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            static_for<ND - i>([&](auto JJ) {
+              constexpr int j = i + decltype(JJ)::value;
+              constexpr int e = i * ND - (i * (i - 1)) / 2 + (j - i);
+              sts_f64(st + e * 8, heat_entry<T, i, j, NP>(m, gm));
+            });
+          });
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&freeA[qa]);
+        mbar_arrive(&full[s]);
+      }
+    }
+  } else {
+    // ================= consumers: gather, sum, store
+    const int cw = warp - NPW;  // consumer warp id
+    const uint32_t idx0 = sbase + a.off_idx + lane * 4;
+    const uint32_t gd0 = sbase + a.off_gdst;
+    const uint32_t cls0 = sbase + a.off_meta;
+    int resident = -1;
+    uint32_t nloadB = 0;
+    for (int64_t it = 0; it < nmine; ++it) {
+      const int s = (int)(it & 1);
+      mbar_wait(&full[s], (uint32_t)((it >> 1) & 1));  // also orders the descriptor written by the copy warp
+      const BlockDesc2 &d = sdesc[it % NDESC];
+      const int pattern = d.pattern;
+      if (pattern != resident) {
+        // all consumers are done with the old tables (named barrier), then one of them reloads
+        asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");
+        if (cw == 0 && lane == 0) {
+          const uint32_t nslp = (uint32_t)((d.nsl + 3) & ~3);
+          const uint32_t ib = (uint32_t)d.nidx * 2u, mb = (uint32_t)((d.ncls + 1) & ~1) * 8u, gb = nslp * 2u * (uint32_t)PER_NORM;
+          mbar_expect_tx(barB, ib + mb + gb);
+          if (ib) bulk_g2s(smraw + a.off_idx, a.cidx + d.idx_off, ib, barB);
+          if (mb) bulk_g2s(smraw + a.off_meta, a.cmeta + d.cls_off, mb, barB);
+          if (gb) bulk_g2s(smraw + a.off_gdst, a.gdst + d.meta_off * PER_NORM, gb, barB);
+        }
+        mbar_wait(barB, nloadB & 1u);
+        ++nloadB;
+        resident = pattern;
+      }
+      const uint32_t lo = (uint32_t)(d.s0 & (G - 1)), span = (a.dbg & 8) ? 0u : (uint32_t)d.nslots;
+      double *__restrict__ out = a.out + (d.s0 - lo);
+      const uint32_t stb = sbase + s * a.stage_bytes;
+      const int ncls = (a.dbg & 2) ? 0 : d.ncls;
+      for (int c = 0; c < ncls; ++c) {
+        uint32_t c0, c1;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(c0), "=r"(c1) : "r"(cls0 + c * 8));
+        const uint32_t first = c0 & 0xffffu, count = c0 >> 16, off64 = c1 & 0xffffu, w = (c1 >> 16) & 0xffu;
+        const bool split = c1 >= 0x1000000u;
+#define SWEEP(W) sweep_class<W, G, NCW, (NCW <= 16)>(first, count, off64, split, cw, lane, idx0, gd0, stb, out, lo, span)
+        switch (w) {
+          case 0: {  // slots without contributions (Dirichlet rows/columns): write zeros
+            constexpr int LG = G == 4 ? 2 : (G == 2 ? 1 : 0);
+            for (uint32_t i = first_slice_of<NCW>(cw, first); i < count; i += NCW) {
+              const uint32_t gs = lds_u16(gd0 + ((first + i) * PER_NORM + (split ? (lane >> (LG + 2)) : (lane >> LG))) * 2u);
+              const uint32_t slot = gs * G + (split ? ((lane >> 2) & (G - 1)) : (lane & (G - 1)));
+              if ((!split || (lane & 3) == 0) && slot - lo < span) out[slot] = 0.0;
+            }
+            break;
+          }
+          case 1: SWEEP(1); break;
+          case 2: SWEEP(2); break;
+          case 3: SWEEP(3); break;
+          case 4: SWEEP(4); break;
+          case 5: SWEEP(5); break;
+          case 6: SWEEP(6); break;
+          case 7: SWEEP(7); break;
+          case 8: SWEEP(8); break;
+          default: {  // wider classes (high-valence vertices of unstructured meshes): generic loop
+            constexpr int LG = G == 4 ? 2 : (G == 2 ? 1 : 0);
+            const uint32_t pairs = (w + 1) >> 1;
+            for (uint32_t i = first_slice_of<NCW>(cw, first); i < count; i += NCW) {
+              const uint32_t ip = idx0 + (off64 + i * pairs) * 128u;
+              const uint32_t gs = lds_u16(gd0 + ((first + i) * PER_NORM + (split ? (lane >> (LG + 2)) : (lane >> LG))) * 2u);
+              double a0 = 0.0, a1 = 0.0;
+              for (uint32_t q = 0; q < pairs; ++q) {
+                const uint32_t pr = lds_u32(ip + q * 128);
+                a0 += lds_f64(stb + (pr & 0xffffu) * 8u);
+                if (2 * q + 1 < w) a1 += lds_f64(stb + (pr >> 16) * 8u);
+              }
+              double acc = a0 + a1;
+              if (split) {
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+              }
+              const uint32_t slot = gs * G + (split ? ((lane >> 2) & (G - 1)) : (lane & (G - 1)));
+              if ((!split || (lane & 3) == 0) && slot - lo < span) out[slot] = acc;
+            }
+          }
+        }
+#undef SWEEP
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+  }
+}
+
+// shared-memory layout of the warp-specialised kernel; returns the total size (0: does not fit)
+template <int DIM>
+size_t layout_gather3(G2Args &a, const GatherPlan2 &p) {
+  auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  a.stage_bytes = (int)up16(sizeof(double) * ((size_t)p.zaddr + 16));
+  size_t off = 2 * (size_t)a.stage_bytes;
+  a.off_idx = (int)off;
+  off += up16(2 * (size_t)p.max_nidx + 64);
+  a.off_meta = (int)off;
+  off += up16(8 * (size_t)PLAN2_MAX_CLASSES + 16);
+  a.off_gdst = (int)off;
+  off += up16(2 * (size_t)(32 / p.sector) * (size_t)p.max_nsl + 16);
+  a.sector = p.sector;
+  a.inA_bytes = (int)(up16(8 * (size_t)p.vmax * DIM + 16) + up16(4 * (size_t)p.cmax + 16));
+  a.off_vtab = (int)off;
+  a.off_lcc = (int)(off + up16(8 * (size_t)p.vmax * DIM + 16));
+  off += 4 * (size_t)a.inA_bytes;
+  a.off_bar = (int)off;
+  off += 128;
+  a.off_desc = (int)off;
+  off += 8 * sizeof(BlockDesc2);
+  a.zaddr = p.zaddr;
+  return off <= 227 * 1024 ? off : 0;
+}
+
+template <int DIM, int DEG, int VAR>
+int launch_gather3(G2Args a, const GatherPlan2 &p, cudaStream_t s) {
+  using T = RefT<DIM, DEG, VAR>;
+  constexpr int ND = T::ND, NEP = (ND * (ND + 1) / 2) | 1;
+  constexpr int NPW = 6, NCW = 25;  // 192 cells per pass of the producers; 32 warps, 64 registers each
+  if (p.nep != NEP) return 3;
+  const size_t smem = layout_gather3<DIM>(a, p);
+  if (smem == 0) return 4;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t grid = p.nblocks < sms ? p.nblocks : sms;
+  auto launch = [&](auto kern) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
+    kern<<<(unsigned)grid, (NPW + NCW + 1) * 32, smem, s>>>(a);
+    return cudaGetLastError() == cudaSuccess ? 0 : 2;
+  };
+  if (p.sector == 4) return launch(heat_jacobian_gather3<DIM, DEG, VAR, NPW, NCW, 4>);
+  if (p.sector == 2) return launch(heat_jacobian_gather3<DIM, DEG, VAR, NPW, NCW, 2>);
+  return launch(heat_jacobian_gather3<DIM, DEG, VAR, NPW, NCW, 1>);
+}
+
 template <int DIM, int DEG, int VAR, int NT>
 int launch_gather2_nt(G2Args a, const GatherPlan2 &p, cudaStream_t s) {
   using T = RefT<DIM, DEG, VAR>;
@@ -857,8 +1130,11 @@ int fdts_launch_heat(fdts_engine *e, int which, const double *x, const double *x
     g.bdesc = p.bdesc; g.cidx = p.cidx; g.gdst = p.gdst; g.cmeta = p.cmeta; g.bcc = p.bcc; g.bvcoords = p.bvcoords;
     g.out = out; g.nblocks = p.nblocks; g.shift = shift; g.dbg = (int32_t)e->opt_debug;
     int rc = 3;
-#define G2CASE(D, K, V) \
-  if (dim == D && deg == K && (K < 3 || var == V)) rc = launch_gather2<D, K, V>(g, p, (int)e->opt_threads, s);
+#define G2CASE(D, K, V)                                                      \
+  if (dim == D && deg == K && (K < 3 || var == V)) {                         \
+    rc = e->opt_overlap ? launch_gather3<D, K, V>(g, p, s) : 4;              \
+    if (rc == 4) rc = launch_gather2<D, K, V>(g, p, (int)e->opt_threads, s); \
+  }
     G2CASE(1, 1, 1) G2CASE(1, 2, 1) G2CASE(1, 3, 0) G2CASE(1, 3, 1)
     G2CASE(2, 1, 1) G2CASE(2, 2, 1) G2CASE(2, 3, 0) G2CASE(2, 3, 1)
     G2CASE(3, 1, 1) G2CASE(3, 2, 1) G2CASE(3, 3, 0) G2CASE(3, 3, 1)

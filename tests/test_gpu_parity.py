@@ -105,9 +105,29 @@ def test_pattern_dictionary(n, ftile):
     assert e1.get_option("plan_shared_contributions") < e1.get_option("plan_contributions")
     J0 = e0.ijacobian(0.0, x, xd, 10.0)
     assert torch.equal(e1.ijacobian(0.0, x, xd, 10.0), J0)
-    # bank-conflict-aware column order and 16-byte store groups only change the summation order
-    for opts in ({"optimize": 1}, {"optimize": 1, "sector": 2}, {"optimize": 0, "sector": 2}):
+    # bank-conflict-aware column order, 16/8-byte store groups, CTA sizes and the warp-specialised
+    # (overlapped) kernel only change the summation order / the schedule, never a value beyond rounding
+    for opts in ({"optimize": 1}, {"optimize": 1, "sector": 2}, {"optimize": 0, "sector": 2}, {"sector": 1},
+                 {"threads": 1024}, {"threads": 256}, {"overlap": 1}, {"overlap": 1, "sector": 2}):
         e2 = Engine(form, bcs, device="cuda:0", scatter=2, plan_version=2, dedup=1, options=opts)
         J2 = e2.ijacobian(0.0, x, xd, 10.0)
         assert rel_err(J2.cpu().numpy(), J0.cpu().numpy()) < TOL
         assert torch.equal(J2, e2.ijacobian(0.0, x, xd, 10.0))
+
+
+@pytest.mark.parametrize("dim,degree,n,ftile", [(3, 2, 8, (6, 4, 4)), (3, 2, 6, 4), (2, 2, 12, (8, 4)), (3, 1, 9, 4),
+                                                (2, 3, 6, 4), (1, 2, 30, 6)])
+def test_overlapped_kernel_bitwise_equal(dim, degree, n, ftile):
+    """warp-specialised Jacobian kernel (producer / consumer / copy warps, mbarrier hand-over) against the
+    two-phase kernel on the same plan: identical summation order => identical bits; plus the oracle."""
+    from firedrake_ts_b200.engine import Engine
+    from oracle import Oracle
+
+    form, bcs, u, udot = make_problem("heat", dim, degree, n, tile=2, ftile=ftile)
+    x, xd = u.data.cuda(), udot.data.cuda()
+    e0 = Engine(form, bcs, device="cuda:0", scatter=2, options={"overlap": 0})
+    e1 = Engine(form, bcs, device="cuda:0", scatter=2, options={"overlap": 1})
+    J0 = e0.ijacobian(0.0, x, xd, 3.0)
+    for _ in range(3):  # repeated launches: the hand-over barriers must not depend on timing
+        assert torch.equal(e1.ijacobian(0.0, x, xd, 3.0), J0)
+    assert rel_err(J0.cpu().numpy(), Oracle.from_form(form, bcs).ijacobian(0.0, u.data, udot.data, 3.0)) < TOL
