@@ -13,7 +13,8 @@ resident in HBM; `e2e` is the same pair through the host-buffer C ABI (fdts_*_ho
 x, xdot in, F and the CSR values out, copies inside the timed region).  Inputs are far larger
 than L2 (126 MB), so no flush between iterations is needed.  N > 1: strong scaling, the same
 global problem box-partitioned over the ranks (2x1x1 / 2x2x1 / 2x2x2), one halo exchange of
-u and udot per step over NCCL send/recv inside the timed region, max over ranks.
+u and udot per step over NCCL send/recv inside the timed region (hidden behind the interior
+cells of the residual; ms_ifunction includes it), max over ranks.
 """
 from __future__ import annotations
 
@@ -221,12 +222,10 @@ def run_b200(a):
     shift = 10.0  # 1/dt with PETSc's default dt = 0.1
 
     def step():
-        if halo is not None:
-            r1 = halo.start(x, 0)
-            r2 = halo.start(xd, 1)
-            halo.finish(x, r1, 0)
-            halo.finish(xd, r2, 1)
-        eng.ifunction(0.0, x, xd, out=F)
+        if halo is not None:  # ghost exchange hidden behind the interior cells of the residual
+            eng.ifunction_overlapped(0.0, x, xd, halo, out=F)
+        else:
+            eng.ifunction(0.0, x, xd, out=F)
         eng.ijacobian(0.0, x, xd, shift, out=J)
 
     for _ in range(a.warmup):
@@ -243,13 +242,11 @@ def run_b200(a):
     e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_beg.record()
     for k in range(a.steps):
-        if halo is not None:
-            r1 = halo.start(x, 0)
-            r2 = halo.start(xd, 1)
-            halo.finish(x, r1, 0)
-            halo.finish(xd, r2, 1)
         ev[k][0].record()
-        eng.ifunction(0.0, x, xd, out=F)
+        if halo is not None:
+            eng.ifunction_overlapped(0.0, x, xd, halo, out=F)
+        else:
+            eng.ifunction(0.0, x, xd, out=F)
         ev[k][1].record()
         eng.ijacobian(0.0, x, xd, shift, out=J)
         ev[k][2].record()
@@ -348,11 +345,7 @@ def run_b200(a):
         def e2e_step():
             x[:nown].copy_(xh, non_blocking=True)
             xd[:nown].copy_(xdh, non_blocking=True)
-            r1 = halo.start(x, 0)
-            r2 = halo.start(xd, 1)
-            halo.finish(x, r1, 0)
-            halo.finish(xd, r2, 1)
-            eng.ifunction(0.0, x, xd, out=F)
+            eng.ifunction_overlapped(0.0, x, xd, halo, out=F)
             Fh.copy_(F, non_blocking=True)
             eng.ijacobian(0.0, x, xd, shift, out=J)
             Jh.copy_(J, non_blocking=True)

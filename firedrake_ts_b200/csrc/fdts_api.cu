@@ -433,6 +433,8 @@ extern "C" int fdts_ifunction_range(fdts_handle e, double t, const double *x, co
     return 1;
   }
   cudaStream_t s = (cudaStream_t)stream;
+  if (use_fast_heat(e) && !(e->opt_scatter == 2 && e->opt_gather_residual && e->plan.ready))
+    return fdts_launch_heat(e, 0, x, xdot, 0.0, f, c0, c1, flags & 1, s);  // closed form + atomics on [c0, c1)
   if (flags & 1) FDTS_CHECK(cudaMemsetAsync(f, 0, sizeof(double) * e->cfg.num_owned_nodes * e->cfg.ncomp, s));
   RET_IF(fdts_launch_residual(e, x, xdot, f, c0, c1, s));
   return 0;
@@ -460,14 +462,14 @@ extern "C" int fdts_ijacobian_range(fdts_handle e, double t, const double *x, co
 
 extern "C" int fdts_ifunction(fdts_handle e, double t, const double *x, const double *xdot, double *f, void *stream) {
   if (!e) return 1;
-  if (use_fast_heat(e)) return fdts_launch_heat(e, 0, x, xdot, 0.0, f, 0, e->cfg.num_cells, (cudaStream_t)stream);
+  if (use_fast_heat(e)) return fdts_launch_heat(e, 0, x, xdot, 0.0, f, 0, e->cfg.num_cells, 3, (cudaStream_t)stream);
   return fdts_ifunction_range(e, t, x, xdot, f, 0, e->cfg.num_cells, 1, stream);
 }
 
 extern "C" int fdts_ijacobian(fdts_handle e, double t, const double *x, const double *xdot, double shift, double *vals,
                               void *stream) {
   if (!e) return 1;
-  if (use_fast_heat(e)) return fdts_launch_heat(e, 1, x, xdot, shift, vals, 0, e->cfg.num_cells, (cudaStream_t)stream);
+  if (use_fast_heat(e)) return fdts_launch_heat(e, 1, x, xdot, shift, vals, 0, e->cfg.num_cells, 3, (cudaStream_t)stream);
   return fdts_ijacobian_range(e, t, x, xdot, shift, vals, 0, e->cfg.num_cells, 3, stream);
 }
 

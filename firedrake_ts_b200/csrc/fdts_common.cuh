@@ -144,7 +144,7 @@ int fdts_launch_residual(fdts_engine *e, const double *x, const double *xdot, do
 int fdts_launch_jacobian(fdts_engine *e, const double *x, const double *xdot, double shift, double *vals, int64_t c0,
                          int64_t c1, cudaStream_t s);
 int fdts_launch_heat(fdts_engine *e, int which, const double *x, const double *xdot, double shift, double *out,
-                     int64_t c0, int64_t c1, cudaStream_t s);
+                     int64_t c0, int64_t c1, int flags, cudaStream_t s);
 int fdts_build_pattern(fdts_engine *e, cudaStream_t s);
 int fdts_heat_match_tables(int dim, int deg, const double *R_host);
 int fdts_build_plan(fdts_engine *e, const int64_t *starts_host, int64_t nblocks);

@@ -1108,8 +1108,9 @@ int fdts_heat_match_tables(int dim, int deg, const double *R) {
 }
 
 // which: 0 residual, 1 Jacobian.  Full call: zero, assemble, boundary fix-up.
+// flags: bit0 zero the output first (atomic paths), bit1 apply the Dirichlet diagonal afterwards (Jacobian)
 int fdts_launch_heat(fdts_engine *e, int which, const double *x, const double *xdot, double shift, double *out,
-                     int64_t c0, int64_t c1, cudaStream_t s) {
+                     int64_t c0, int64_t c1, int flags, cudaStream_t s) {
   if (e->cfg.family != FDTS_HEAT || e->cfg.ncomp != 1) {
     fdts_set_error("closed-form path: heat family only");
     return 3;
@@ -1190,10 +1191,12 @@ int fdts_launch_heat(fdts_engine *e, int which, const double *x, const double *x
     fdts_set_error("closed-form heat path: run-time reference tensors do not match the compiled tables");
     return 3;
   }
-  if (which == 0)
-    FDTS_CHECK(cudaMemsetAsync(out, 0, sizeof(double) * e->cfg.num_owned_nodes, s));
-  else
-    FDTS_CHECK(cudaMemsetAsync(out, 0, sizeof(double) * e->node_nnz, s));
+  if (flags & 1) {
+    if (which == 0)
+      FDTS_CHECK(cudaMemsetAsync(out, 0, sizeof(double) * e->cfg.num_owned_nodes, s));
+    else
+      FDTS_CHECK(cudaMemsetAsync(out, 0, sizeof(double) * e->node_nnz, s));
+  }
   int rc = 3;
 #define CASE(D, K, V) \
   if (dim == D && deg == K && (K < 3 || var == V)) rc = launch_atomic<D, K, V>(which, a, s);
@@ -1205,7 +1208,7 @@ int fdts_launch_heat(fdts_engine *e, int which, const double *x, const double *x
   if (rc == 2) fdts_set_error(std::string("heat kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
   if (rc) return rc;
   e->launches++;
-  if (which == 1 && e->cfg.num_bc_nodes > 0) {
+  if (which == 1 && (flags & 2) && e->cfg.num_bc_nodes > 0) {
     const int64_t n = e->cfg.num_bc_nodes;
     set_values_k<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, e->bc_diag_slot, n, 1.0);
     e->launches++;

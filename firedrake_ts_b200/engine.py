@@ -258,6 +258,23 @@ class Engine:
             _check(self._lib.fdts_ifunction_range(self._h, float(t), x.data_ptr(), xdot.data_ptr(), out.data_ptr(),
                                                   c0, c1, flags, _stream()), "fdts_ifunction_range")
 
+    def ifunction_overlapped(self, t, x, xdot, halo, out=None):
+        """IFunction with the ghost exchange of x / xdot hidden behind the interior cells (the cells
+        that touch no ghost node are listed first): pack + NCCL send/recv are posted, the interior
+        range is assembled meanwhile, the remaining cells after the receives completed.  Same split as
+        PyOP2's core / owned+exec-halo parloop halves around ``global_to_local_begin/end``."""
+        if out is None:
+            out = torch.empty(self.num_rows, dtype=torch.float64, device=self.device)
+        r1 = halo.start(x, 0)
+        r2 = halo.start(xdot, 1)
+        ni = self.num_interior_cells
+        self.ifunction_range(t, x, xdot, out, 0, ni, 1)
+        halo.finish(x, r1, 0)
+        halo.finish(xdot, r2, 1)
+        if ni < self.num_cells:
+            self.ifunction_range(t, x, xdot, out, ni, self.num_cells, 0)
+        return out
+
     def ijacobian_range(self, t, x, xdot, shift, out, c0, c1, flags):
         with torch.cuda.device(self.device):
             _check(self._lib.fdts_ijacobian_range(self._h, float(t), x.data_ptr(), xdot.data_ptr(), float(shift),
