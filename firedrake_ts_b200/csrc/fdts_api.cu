@@ -257,6 +257,7 @@ extern "C" int fdts_destroy(fdts_handle e) {
     if (p) cudaFree(p);
   fdts_free_plan(e);
   fdts_free_plan2(e);
+  fdts_free_rplan(e);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
   return 0;
@@ -347,6 +348,10 @@ extern "C" int fdts_set_option(fdts_handle e, const char *key, int64_t value) {
     e->opt_optimize = value ? 1 : 0;
     return 0;
   }
+  if (!strcmp(key, "residual_tiles")) {
+    e->opt_residual_tiles = value ? 1 : 0;
+    return 0;
+  }
   if (!strcmp(key, "overlap")) {
     e->opt_overlap = value ? 1 : 0;
     return 0;
@@ -382,6 +387,12 @@ extern "C" int fdts_set_row_blocks(fdts_handle e, const int64_t *starts_host, in
   return fdts_build_plan(e, starts_host, nblocks);
 }
 
+extern "C" int fdts_set_cell_tiles(fdts_handle e, const int64_t *starts_host, int64_t ntiles) {
+  if (!e || !starts_host) return 1;
+  FDTS_CHECK(cudaSetDevice(e->device));
+  return fdts_build_rplan(e, starts_host, ntiles);
+}
+
 extern "C" int fdts_get_option(fdts_handle e, const char *key, int64_t *value) {
   if (!e || !key || !value) return 1;
   if (!strcmp(key, "scatter")) {
@@ -403,6 +414,14 @@ extern "C" int fdts_get_option(fdts_handle e, const char *key, int64_t *value) {
   }
   if (!strcmp(key, "plan_version")) {
     *value = v2 ? 2 : (e->plan.ready ? 1 : 0);
+    return 0;
+  }
+  if (!strcmp(key, "residual_tiles")) {
+    *value = e->rplan.ready ? e->rplan.ntiles : 0;
+    return 0;
+  }
+  if (!strcmp(key, "residual_patterns")) {
+    *value = e->rplan.ready ? e->rplan.unique_patterns : 0;
     return 0;
   }
   if (!strcmp(key, "plan_patterns")) {

@@ -82,6 +82,28 @@ struct GatherPlan2 {
   int32_t optimized = 0;        // unique patterns went through the bank-conflict-aware column ordering
 };
 
+// residual tile plan (gather_plan.cu: fdts_build_rplan): cells are cut into contiguous tiles; a CTA
+// stages the tile's node values and vertex coordinates with coalesced loads, computes the element
+// vectors, pre-reduces them per unique node in shared memory (SELL lists, same machinery as plan 2)
+// and issues ONE atomic per (tile, node) instead of one per (cell, node).  Identical tiles share
+// their tables (pattern dictionary).
+struct ResidualPlan {
+  bool ready = false;
+  int64_t ntiles = 0;
+  int32_t cmax = 0, cmaxp = 0, vmax = 0, umaxp = 0, ndp = 0, zaddr = 0;
+  int32_t max_nidx = 0, max_nsl = 0;
+  uint16_t *cidx = nullptr;     // staged element-vector addresses, SELL order (pairs layout)
+  uint2 *cmeta = nullptr;       // slice classes per tile
+  uint16_t *gdst = nullptr;     // per slice: 32 tile-local node indices (0xffff = none)
+  uint32_t *bcc = nullptr;      // per cell: (dim+1) tile-local vertex ids, one byte each
+  double *bvcoords = nullptr;   // per tile: vmax x dim vertex coordinates
+  int32_t *tnode = nullptr;     // per tile: umaxp node ids relative to the tile's first node; bit 31 = no output
+  uint16_t *tlid = nullptr;     // per tile: [nd][cmaxp] tile-local node index of every cell
+  BlockDesc2 *tdesc = nullptr;  // s0 = first node id of the tile, nslots = unique nodes
+  int64_t *tstart_host = nullptr;  // ntiles+1 cell offsets (host copy, for cell-range calls)
+  int64_t unique_patterns = 0;
+};
+
 struct fdts_engine {
   fdts_config cfg;  // scalars only are meaningful after create; pointers below are device copies
   int device = 0;
@@ -113,10 +135,12 @@ struct fdts_engine {
   int64_t opt_persist = 1;       // gather path: persistent pipelined Jacobian kernel
   GatherPlan plan;
   GatherPlan2 plan2;
+  ResidualPlan rplan;
   int64_t opt_plan_version = 2;  // what fdts_set_row_blocks builds: 1 = windowed SELL (+ residual lists), 2 = sector SELL
   int64_t opt_dedup = 1;         // plan 2: share identical block patterns
   int64_t opt_sector = 4;        // plan 2: slots per store group (4 or 2)
   int64_t opt_optimize = 1;      // plan 2: bank-conflict-aware column order for the unique patterns
+  int64_t opt_residual_tiles = 1; // residual: tile kernel (pre-reduced atomics) when a cell-tile plan exists (fdts_set_cell_tiles; the Python layer only builds one on request: the kernel is slower than the per-cell one today)
   int64_t opt_overlap = 0;       // plan 2: warp-specialised kernel (element matrices of block b+1 overlap the gather of block b; needs two staging buffers in smem; slower than the two-phase kernel on every block shape measured so far)
   int64_t opt_threads = 512;     // plan 2: threads per persistent CTA (512: 128 registers per thread, or 1024)
   int64_t opt_debug = 0;         // development only (timing experiments with phases switched off)
@@ -151,6 +175,8 @@ int fdts_build_plan(fdts_engine *e, const int64_t *starts_host, int64_t nblocks)
 int fdts_build_plan2(fdts_engine *e, const int64_t *starts_host, int64_t nblocks);
 void fdts_free_plan(fdts_engine *e);
 void fdts_free_plan2(fdts_engine *e);
+int fdts_build_rplan(fdts_engine *e, const int64_t *tile_starts_host, int64_t ntiles);
+void fdts_free_rplan(fdts_engine *e);
 
 // ------------------------------------------------------------------ device helpers
 __device__ __forceinline__ void red_add_f64(double *addr, double v) {

@@ -1409,3 +1409,515 @@ int fdts_build_plan2(fdts_engine *e, const int64_t *starts, int64_t nb) {
   if (rc) fdts_free_plan2(e);
   return rc;
 }
+
+// =====================================================================================
+// Residual tile plan: per-tile pre-reduction of the element vectors before the atomics.
+// =====================================================================================
+namespace {
+
+constexpr int RT_KEYS = 4096;  // (cell, local node) pairs per tile handled by the in-smem sort
+
+__global__ void tile_cells(const int64_t *__restrict__ tstart, int64_t nt, int cmax, int32_t *__restrict__ bcount,
+                           int32_t *__restrict__ bcells) {
+  const int64_t t = blockIdx.x;
+  const int64_t c0 = tstart[t], n = tstart[t + 1] - c0;
+  if (threadIdx.x == 0) bcount[t] = (int32_t)n;
+  if (bcells)
+    for (int k = threadIdx.x; k < n; k += blockDim.x) bcells[t * cmax + k] = (int32_t)(c0 + k);
+}
+
+__global__ void widen_i32(const int32_t *__restrict__ in, int64_t n, int64_t *__restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t <= n) out[t] = t < n ? (int64_t)in[t] : 0;
+}
+
+__global__ void iota64(int64_t *p, int64_t n) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) p[t] = t;
+}
+
+__device__ __forceinline__ void bitonic_sort_u32(uint32_t *keys, int n) {  // n power of two, all threads of the CTA
+  for (int kk = 2; kk <= n; kk <<= 1)
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int q = t ^ j;
+        if (q > t) {
+          const uint32_t x = keys[t], y = keys[q];
+          const bool up = (t & kk) == 0;
+          if ((x > y) == up) {
+            keys[t] = y;
+            keys[q] = x;
+          }
+        }
+      }
+      __syncthreads();
+    }
+}
+
+// one CTA per tile: sorted unique nodes of its cells (relative ids, "no output" flag) and the
+// tile-local node index of every (cell, local node).  WRITE=false: count only.
+template <bool WRITE>
+__global__ void __launch_bounds__(PLAN_THREADS) tile_nodes(const int64_t *__restrict__ tstart,
+                                                           const int32_t *__restrict__ cell_node_t, int64_t nc, int nd,
+                                                           int64_t nown, const uint8_t *__restrict__ isbc, int umaxp,
+                                                           int cmaxp, int32_t *__restrict__ ucount,
+                                                           int64_t *__restrict__ tbase, int32_t *__restrict__ tnode,
+                                                           uint16_t *__restrict__ tlid, int *__restrict__ err) {
+  __shared__ uint32_t keys[RT_KEYS];
+  __shared__ int32_t uniq[RT_KEYS];
+  __shared__ int warp_tot[PLAN_THREADS / 32];
+  const int64_t t = blockIdx.x;
+  const int64_t c0 = tstart[t];
+  const int ncell = (int)(tstart[t + 1] - c0);
+  const int n = ncell * nd;
+  if (n > RT_KEYS) {
+    if (threadIdx.x == 0) {
+      atomicExch(err, 11);
+      ucount[t] = 0;
+    }
+    return;
+  }
+  for (int q = threadIdx.x; q < RT_KEYS; q += PLAN_THREADS) {
+    uint32_t v = 0xFFFFFFFFu;
+    if (q < n) {
+      const int i = q / ncell, k = q - i * ncell;
+      v = (uint32_t)cell_node_t[(int64_t)i * nc + c0 + k];
+    }
+    keys[q] = v;
+  }
+  __syncthreads();
+  bitonic_sort_u32(keys, RT_KEYS);
+  int base = 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t0 = 0; t0 < RT_KEYS; t0 += PLAN_THREADS) {
+    const int q = t0 + threadIdx.x;
+    const uint32_t v = keys[q];
+    const bool first = v != 0xFFFFFFFFu && (q == 0 || keys[q - 1] != v);
+    const unsigned m = __ballot_sync(0xffffffffu, first);
+    if (lane == 0) warp_tot[warp] = __popc(m);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    if (first) uniq[off + __popc(m & ((1u << lane) - 1u))] = (int32_t)v;
+    for (int w = 0; w < PLAN_THREADS / 32; ++w) base += warp_tot[w];
+    __syncthreads();
+  }
+  const int nu = base;
+  if (!WRITE) {
+    if (threadIdx.x == 0) ucount[t] = nu;
+    return;
+  }
+  if (nu > 65534 || nu > umaxp) {
+    if (threadIdx.x == 0) atomicExch(err, 12);
+    return;
+  }
+  const int32_t b0 = nu > 0 ? uniq[0] : 0;
+  if (threadIdx.x == 0) tbase[t] = b0;
+  for (int q = threadIdx.x; q < umaxp; q += PLAN_THREADS) {
+    int32_t v = (int32_t)0x80000000;
+    if (q < nu) {
+      const int32_t node = uniq[q];
+      v = node - b0;
+      if (node >= nown || isbc[node]) v |= (int32_t)0x80000000;  // ghost or Dirichlet row: no output
+    }
+    tnode[t * (int64_t)umaxp + q] = v;
+  }
+  for (int q = threadIdx.x; q < n; q += PLAN_THREADS) {
+    const int i = q / ncell, k = q - i * ncell;
+    const int32_t node = cell_node_t[(int64_t)i * nc + c0 + k];
+    const int l = find_cell(uniq, nu, node);
+    tlid[(t * nd + i) * (int64_t)cmaxp + k] = (uint16_t)l;
+  }
+}
+
+// MODE 0: contributions per unique node (cnt8).  MODE 1: staged addresses into their SELL positions,
+// contributions of a node in ascending (cell, local index) order.
+template <int MODE>
+__global__ void __launch_bounds__(PLAN_THREADS) tile_contributions(const int64_t *__restrict__ tstart, int nd, int ndp,
+                                                                   int cmaxp, const uint16_t *__restrict__ tlid,
+                                                                   const int64_t *__restrict__ tptr,
+                                                                   uint8_t *__restrict__ cnt8,
+                                                                   const uint32_t *__restrict__ sellpos,
+                                                                   const int64_t *__restrict__ idx_off,
+                                                                   uint16_t *__restrict__ cidx, int *__restrict__ err) {
+  __shared__ uint32_t keys[RT_KEYS];
+  const int64_t t = blockIdx.x;
+  const int ncell = (int)(tstart[t + 1] - tstart[t]);
+  const int n = ncell * nd;
+  if (n > RT_KEYS || ncell > 512) {
+    if (threadIdx.x == 0) atomicExch(err, 11);
+    return;
+  }
+  for (int q = threadIdx.x; q < RT_KEYS; q += PLAN_THREADS) {
+    uint32_t v = 0xFFFFFFFFu;
+    if (q < n) {
+      const int i = q / ncell, k = q - i * ncell;
+      v = ((uint32_t)tlid[(t * nd + i) * (int64_t)cmaxp + k] << 14) | ((uint32_t)k << 5) | (uint32_t)i;
+    }
+    keys[q] = v;
+  }
+  __syncthreads();
+  bitonic_sort_u32(keys, RT_KEYS);
+  for (int p = threadIdx.x; p < n; p += PLAN_THREADS) {
+    const uint32_t key = keys[p];
+    const uint32_t l = key >> 14;
+    int lo = 0, hi = p;  // first position of this node's segment
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if ((keys[mid] >> 14) < l) lo = mid + 1; else hi = mid;
+    }
+    const int kth = p - lo;
+    const int64_t slot = tptr[t] + l;
+    if (MODE == 0) {
+      if (p + 1 == n || (keys[p + 1] >> 14) != l) {
+        if (kth + 1 > 255) atomicExch(err, 3);
+        cnt8[slot] = (uint8_t)(kth + 1);
+      }
+    } else {
+      const uint32_t sp = sellpos[slot];
+      const int64_t base = (int64_t)((sp & ~SPLIT_FLAG) >> 8) * 64;
+      const int lane0 = (int)(sp & 0xffu);
+      const int64_t at = (sp & SPLIT_FLAG) ? base + sell_entry(kth >> 2, lane0 + (kth & 3)) : base + sell_entry(kth, lane0);
+      const int k = (int)((key >> 5) & 511u), i = (int)(key & 31u);
+      cidx[idx_off[t] + at] = (uint16_t)(k * ndp + i);
+    }
+  }
+}
+
+__global__ void tile_descriptors(int64_t nt, const int64_t *__restrict__ tbase, const int64_t *__restrict__ idx_off,
+                                 const int64_t *__restrict__ meta_off, const int64_t *__restrict__ nsl_true,
+                                 const int32_t *__restrict__ bncls, const int32_t *__restrict__ bcount,
+                                 const int32_t *__restrict__ vcount, const int32_t *__restrict__ ucount, int cmaxp,
+                                 int vmax, int dim, BlockDesc2 *__restrict__ d) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nt) return;
+  BlockDesc2 x;
+  x.s0 = tbase[t];
+  x.idx_off = idx_off[t];
+  x.meta_off = meta_off[t];
+  x.cc_off = t * (int64_t)cmaxp;
+  x.vc_off = t * (int64_t)vmax * dim;
+  x.cls_off = t * (int64_t)PLAN2_MAX_CLASSES;
+  x.nslots = ucount[t];
+  x.nidx = (int32_t)(idx_off[t + 1] - idx_off[t]);
+  x.ncell = bcount[t];
+  x.nvert = vcount[t];
+  x.nsl = (int32_t)nsl_true[t];
+  x.ncls = bncls[t];
+  x.pattern = (int32_t)t;
+  x.pad1 = 0;
+  d[t] = x;
+}
+
+__global__ void __launch_bounds__(PLAN_THREADS) tile_hash(const BlockDesc2 *__restrict__ d,
+                                                          const uint16_t *__restrict__ cidx,
+                                                          const uint2 *__restrict__ cmeta,
+                                                          const uint16_t *__restrict__ gdst,
+                                                          const uint32_t *__restrict__ bcc,
+                                                          const int32_t *__restrict__ tnode,
+                                                          const uint16_t *__restrict__ tlid, int umaxp, int cmaxp, int nd,
+                                                          int mask, uint64_t *__restrict__ hash2) {
+  __shared__ unsigned long long h0, h1;
+  const int64_t t = blockIdx.x;
+  const BlockDesc2 x = d[t];
+  if (threadIdx.x == 0) {
+    h0 = mix64(((uint64_t)x.nslots << 32) ^ (uint64_t)x.nidx) + mix64(((uint64_t)x.ncell << 32) ^ (uint64_t)x.nvert ^ 0x52ull << 60);
+    h1 = mix64(((uint64_t)x.nsl << 32) ^ ((uint64_t)x.ncls << 8) ^ 0x9ull << 58);
+  }
+  __syncthreads();
+  uint64_t a0 = 0, a1 = 0;
+  auto add = [&](uint64_t stream, uint64_t pos, uint64_t val) {
+    const uint64_t k = (stream << 56) ^ (pos << 24) ^ val;
+    a0 += mix64(k);
+    a1 += mix64(k ^ 0xa5a5a5a5deadbeefull);
+  };
+  if (mask & 1)
+    for (int q = threadIdx.x; q < x.nidx; q += PLAN_THREADS) add(1, q, cidx[x.idx_off + q]);
+  if (mask & 2)
+    for (int q = threadIdx.x; q < x.ncls; q += PLAN_THREADS) {
+      const uint2 c = cmeta[x.cls_off + q];
+      add(2, q, ((uint64_t)c.y << 32) | c.x);
+    }
+  const int nslp = (x.nsl + 3) & ~3;
+  if (mask & 4)
+    for (int q = threadIdx.x; q < nslp * 32; q += PLAN_THREADS) add(3, q, gdst[x.meta_off * 32 + q]);
+  if (mask & 8)
+    for (int q = threadIdx.x; q < x.ncell; q += PLAN_THREADS) add(4, q, bcc[x.cc_off + q]);
+  if (mask & 16)
+    for (int q = threadIdx.x; q < x.nslots; q += PLAN_THREADS) add(5, q, (uint32_t)tnode[t * umaxp + q]);
+  if (mask & 32)
+  for (int q = threadIdx.x; q < x.ncell * nd; q += PLAN_THREADS) {
+    const int i = q / x.ncell, k = q - i * x.ncell;
+    add(6, q, tlid[(t * nd + i) * (int64_t)cmaxp + k]);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&h0, (unsigned long long)a0);
+    atomicAdd(&h1, (unsigned long long)a1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    hash2[2 * t] = h0;
+    hash2[2 * t + 1] = h1;
+  }
+}
+
+}  // namespace
+
+void fdts_free_rplan(fdts_engine *e) {
+  ResidualPlan &p = e->rplan;
+  void *ptrs[] = {p.cidx, p.cmeta, p.gdst, p.bcc, p.bvcoords, p.tnode, p.tlid, p.tdesc};
+  for (void *q : ptrs)
+    if (q) cudaFree(q);
+  delete[] p.tstart_host;
+  p = ResidualPlan();
+}
+
+int fdts_build_rplan(fdts_engine *e, const int64_t *starts, int64_t nt) {
+  fdts_free_rplan(e);
+  ResidualPlan &p = e->rplan;
+  cudaStream_t s = e->own_stream;
+  const int64_t nc = e->cfg.num_cells, nown = e->cfg.num_owned_nodes;
+  const int nd = e->cfg.nd, dim = e->cfg.dim;
+  if (nt <= 0 || starts[0] != 0 || starts[nt] != nc) {
+    fdts_set_error("cell tiles must cover the cells [0, num_cells)");
+    return 1;
+  }
+  if (e->cfg.ncomp != 1) {
+    fdts_set_error("residual tile plan: scalar spaces only");
+    return 3;
+  }
+  p.ntiles = nt;
+  p.ndp = nd | 1;
+  int64_t *tstart = nullptr, *tbase = nullptr, *tptr = nullptr, *iota = nullptr, *btotal = nullptr, *bnsl = nullptr,
+          *idx_off = nullptr, *meta_off = nullptr, *nsl_true = nullptr, *dmax = nullptr, *rep_d = nullptr, *u64tmp = nullptr;
+  int32_t *bcount = nullptr, *bcells = nullptr, *vcount = nullptr, *ucount = nullptr, *bncls = nullptr, *imax = nullptr;
+  uint8_t *cnt8 = nullptr;
+  uint32_t *sellpos = nullptr;
+  uint64_t *hash_d = nullptr;
+  int *derr = nullptr;
+  void *tmp = nullptr;
+  size_t tb = 1 << 22;
+  int rc = 0;
+  auto max_i64 = [&](const int64_t *src, int64_t n, int64_t &out) {
+    size_t t2 = 0;
+    cub::DeviceReduce::Max(nullptr, t2, src, dmax, n, s);
+    if (t2 > tb) return 2;
+    cub::DeviceReduce::Max(tmp, t2, src, dmax, n, s);
+    cudaMemcpyAsync(&out, dmax, sizeof(int64_t), cudaMemcpyDeviceToHost, s);
+    return cudaStreamSynchronize(s) == cudaSuccess ? 0 : 2;
+  };
+  auto max_i32 = [&](const int32_t *src, int64_t n, int32_t &out) {
+    size_t t2 = 0;
+    cub::DeviceReduce::Max(nullptr, t2, src, imax, n, s);
+    if (t2 > tb) return 2;
+    cub::DeviceReduce::Max(tmp, t2, src, imax, n, s);
+    cudaMemcpyAsync(&out, imax, sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+    return cudaStreamSynchronize(s) == cudaSuccess ? 0 : 2;
+  };
+  auto scan = [&](const int64_t *src, int64_t *dst, int64_t n) {
+    size_t t2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, t2, src, dst, n, s);
+    if (t2 > tb) return 2;
+    cub::DeviceScan::ExclusiveSum(tmp, t2, src, dst, n, s);
+    return 0;
+  };
+  do {
+    p.tstart_host = new int64_t[nt + 1];
+    memcpy(p.tstart_host, starts, sizeof(int64_t) * (nt + 1));
+    P2_ALLOC(tmp, tb + 16, "scratch");
+    P2_ALLOC(tstart, sizeof(int64_t) * (nt + 1), "tile starts");
+    P2_ALLOC(tbase, sizeof(int64_t) * (nt + 1), "scratch");
+    P2_ALLOC(tptr, sizeof(int64_t) * (nt + 1), "scratch");
+    P2_ALLOC(iota, sizeof(int64_t) * (nt + 1), "scratch");
+    P2_ALLOC(btotal, sizeof(int64_t) * (nt + 1), "scratch");
+    P2_ALLOC(bnsl, sizeof(int64_t) * (nt + 1), "scratch");
+    P2_ALLOC(idx_off, sizeof(int64_t) * (nt + 1), "scratch");
+    P2_ALLOC(meta_off, sizeof(int64_t) * (nt + 1), "scratch");
+    P2_ALLOC(nsl_true, sizeof(int64_t) * (nt + 1), "scratch");
+    P2_ALLOC(u64tmp, sizeof(int64_t) * (nt + 1), "scratch");
+    P2_ALLOC(dmax, sizeof(int64_t) * 2, "scratch");
+    P2_ALLOC(imax, sizeof(int32_t) * 2, "scratch");
+    P2_ALLOC(derr, sizeof(int), "scratch");
+    P2_ALLOC(bcount, sizeof(int32_t) * nt, "scratch");
+    P2_ALLOC(vcount, sizeof(int32_t) * nt, "scratch");
+    P2_ALLOC(ucount, sizeof(int32_t) * nt, "scratch");
+    P2_ALLOC(bncls, sizeof(int32_t) * nt, "scratch");
+    cudaMemsetAsync(derr, 0, sizeof(int), s);
+    cudaMemcpyAsync(tstart, starts, sizeof(int64_t) * (nt + 1), cudaMemcpyHostToDevice, s);
+    iota64<<<GRID(nt + 1, 256), 256, 0, s>>>(iota, nt + 1);
+    // ---- cells and vertices of every tile
+    tile_cells<<<(unsigned)nt, 128, 0, s>>>(tstart, nt, 0, bcount, nullptr);
+    int32_t cmax = 0;
+    if ((rc = max_i32(bcount, nt, cmax))) break;
+    if ((int64_t)cmax * nd > RT_KEYS || cmax > 512 || cmax * p.ndp + 16 > 65535) {
+      fdts_set_error("residual tile plan: a cell tile is too large (cells x nodes per cell must not exceed 4096)");
+      rc = 4;
+      break;
+    }
+    p.cmax = cmax;
+    p.cmaxp = (cmax + 3) & ~3;
+    p.zaddr = (cmax * p.ndp + 15) & ~15;
+    P2_ALLOC(bcells, sizeof(int32_t) * (size_t)nt * cmax, "tile cell lists");
+    tile_cells<<<(unsigned)nt, 128, 0, s>>>(tstart, nt, cmax, bcount, bcells);
+    int kpv = PLAN_THREADS;
+    while (kpv < cmax * (dim + 1)) kpv <<= 1;
+    const size_t smv = sizeof(int32_t) * 2 * (size_t)kpv;
+    if (smv > 48 * 1024) {
+      cudaFuncSetAttribute(block_vertices<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smv);
+      cudaFuncSetAttribute(block_vertices<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smv);
+    }
+    block_vertices<false><<<(unsigned)nt, PLAN_THREADS, smv, s>>>(bcells, bcount, cmax, e->cell_coord, nc, dim, e->coords, kpv,
+                                                                0, vcount, nullptr, nullptr, derr);
+    int32_t vmax = 0;
+    if ((rc = max_i32(vcount, nt, vmax))) break;
+    vmax = (vmax + 1) & ~1;
+    p.vmax = vmax;
+    if (vmax > 254) {
+      fdts_set_error("residual tile plan: a cell tile touches more than 254 coordinate nodes (use smaller tiles)");
+      rc = 4;
+      break;
+    }
+    P2_ALLOC(p.bvcoords, sizeof(double) * (size_t)nt * vmax * dim + 64, "tile vertex tables");
+    P2_ALLOC(p.bcc, sizeof(uint32_t) * ((size_t)nt * p.cmaxp + 16), "tile cell vertices");
+    cudaMemsetAsync(p.bvcoords, 0, sizeof(double) * (size_t)nt * vmax * dim + 64, s);
+    cudaMemsetAsync(p.bcc, 0, sizeof(uint32_t) * ((size_t)nt * p.cmaxp + 16), s);
+    block_vertices<true><<<(unsigned)nt, PLAN_THREADS, smv, s>>>(bcells, bcount, cmax, e->cell_coord, nc, dim, e->coords, kpv,
+                                                               vmax, nullptr, p.bvcoords, p.bcc, derr);
+    // ---- unique nodes, local node ids
+    tile_nodes<false><<<(unsigned)nt, PLAN_THREADS, 0, s>>>(tstart, e->cell_node, nc, nd, nown, e->isbc, 0, p.cmaxp, ucount,
+                                                           nullptr, nullptr, nullptr, derr);
+    int32_t umax = 0;
+    if ((rc = max_i32(ucount, nt, umax))) break;
+    p.umaxp = (umax + 3) & ~3;
+    P2_ALLOC(p.tnode, sizeof(int32_t) * ((size_t)nt * p.umaxp + 16), "tile node lists");
+    P2_ALLOC(p.tlid, sizeof(uint16_t) * ((size_t)nt * p.cmaxp * nd + 16), "tile local node ids");
+    cudaMemsetAsync(p.tlid, 0, sizeof(uint16_t) * ((size_t)nt * p.cmaxp * nd + 16), s);
+    tile_nodes<true><<<(unsigned)nt, PLAN_THREADS, 0, s>>>(tstart, e->cell_node, nc, nd, nown, e->isbc, p.umaxp, p.cmaxp,
+                                                          ucount, tbase, p.tnode, p.tlid, derr);
+    // ---- per-node contribution counts, SELL layout (store groups of one node)
+    widen_i32<<<GRID(nt + 1, 256), 256, 0, s>>>(ucount, nt, u64tmp);
+    if ((rc = scan(u64tmp, tptr, nt + 1))) break;
+    int64_t total_u = 0;
+    cudaMemcpyAsync(&total_u, tptr + nt, sizeof(int64_t), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    P2_ALLOC(cnt8, (size_t)total_u + 1, "node counters");
+    P2_ALLOC(sellpos, sizeof(uint32_t) * (size_t)(total_u + 1), "node positions");
+    cudaMemsetAsync(cnt8, 0, (size_t)total_u + 1, s);
+    tile_contributions<0><<<(unsigned)nt, PLAN_THREADS, 0, s>>>(tstart, nd, p.ndp, p.cmaxp, p.tlid, tptr, cnt8, nullptr,
+                                                               nullptr, nullptr, derr);
+    cudaMemsetAsync(btotal, 0, sizeof(int64_t) * (nt + 1), s);
+    cudaMemsetAsync(bnsl, 0, sizeof(int64_t) * (nt + 1), s);
+    sell2_layout<false><<<(unsigned)nt, PLAN_THREADS, 0, s>>>(iota, tptr, cnt8, 1, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                            btotal, bnsl, derr);
+    if ((rc = scan(btotal, idx_off, nt + 1)) || (rc = scan(bnsl, meta_off, nt + 1))) break;
+    int64_t total = 0, total_sl = 0, max_idx = 0, max_sl = 0;
+    cudaMemcpyAsync(&total, idx_off + nt, sizeof(int64_t), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(&total_sl, meta_off + nt, sizeof(int64_t), cudaMemcpyDeviceToHost, s);
+    if ((rc = max_i64(btotal, nt, max_idx)) || (rc = max_i64(bnsl, nt, max_sl))) break;
+    int herr = 0;
+    cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    if (herr) {
+      fdts_set_error("residual tile plan: tile too large or internal inconsistency (code " + std::to_string(herr) + ")");
+      rc = 4;
+      break;
+    }
+    p.max_nidx = (int32_t)max_idx;
+    p.max_nsl = (int32_t)max_sl;
+    P2_ALLOC(p.cidx, sizeof(uint16_t) * (size_t)(total + 64), "contribution lists");
+    P2_ALLOC(p.cmeta, sizeof(uint2) * ((size_t)nt + 1) * PLAN2_MAX_CLASSES, "slice class table");
+    P2_ALLOC(p.gdst, sizeof(uint16_t) * (size_t)(total_sl + 16) * 32, "slice destinations");
+    P2_ALLOC(p.tdesc, sizeof(BlockDesc2) * (size_t)(nt + 4), "tile descriptors");
+    fill_padding<<<GRID(total + 64, 256), 256, 0, s>>>(p.cidx, total + 64, p.zaddr);
+    cudaMemsetAsync(p.cmeta, 0, sizeof(uint2) * ((size_t)nt + 1) * PLAN2_MAX_CLASSES, s);
+    cudaMemsetAsync(p.gdst, 0xff, sizeof(uint16_t) * (size_t)(total_sl + 16) * 32, s);
+    cudaMemsetAsync(p.tdesc, 0, sizeof(BlockDesc2) * (size_t)(nt + 4), s);
+    sell2_layout<true><<<(unsigned)nt, PLAN_THREADS, 0, s>>>(iota, tptr, cnt8, 1, meta_off, p.cmeta, bncls, p.gdst, sellpos,
+                                                           btotal, nsl_true, derr);
+    tile_contributions<1><<<(unsigned)nt, PLAN_THREADS, 0, s>>>(tstart, nd, p.ndp, p.cmaxp, p.tlid, tptr, cnt8, sellpos, idx_off,
+                                                               p.cidx, derr);
+    tile_descriptors<<<GRID(nt, 256), 256, 0, s>>>(nt, tbase, idx_off, meta_off, nsl_true, bncls, bcount, vcount, ucount,
+                                                  p.cmaxp, vmax, dim, p.tdesc);
+    cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, s);
+    cudaError_t ce = cudaStreamSynchronize(s);
+    if (ce != cudaSuccess || cudaGetLastError() != cudaSuccess || herr) {
+      fdts_set_error(std::string("residual tile plan kernels failed: ") + cudaGetErrorString(ce) + " code " + std::to_string(herr));
+      rc = 2;
+      break;
+    }
+    // ---- pattern dictionary + bank-conflict-aware ordering of the unique patterns
+    p.unique_patterns = nt;
+    if (e->opt_dedup) {
+      P2_ALLOC(hash_d, sizeof(uint64_t) * 2 * (size_t)nt, "pattern hashes");
+      P2_ALLOC(rep_d, sizeof(int64_t) * (size_t)nt, "pattern representatives");
+      tile_hash<<<(unsigned)nt, PLAN_THREADS, 0, s>>>(p.tdesc, p.cidx, p.cmeta, p.gdst, p.bcc, p.tnode, p.tlid, p.umaxp, p.cmaxp,
+                                                    nd, 63, hash_d);
+      std::vector<uint64_t> h(2 * (size_t)nt);
+      std::vector<BlockDesc2> hd((size_t)nt);
+      cudaMemcpyAsync(h.data(), hash_d, sizeof(uint64_t) * 2 * (size_t)nt, cudaMemcpyDeviceToHost, s);
+      cudaMemcpyAsync(hd.data(), p.tdesc, sizeof(BlockDesc2) * (size_t)nt, cudaMemcpyDeviceToHost, s);
+      if (cudaStreamSynchronize(s) != cudaSuccess) {
+        fdts_set_error("residual tile plan: hashing failed");
+        rc = 2;
+        break;
+      }
+      std::unordered_map<std::pair<uint64_t, uint64_t>, int64_t, PairHash> first;
+      first.reserve((size_t)nt);
+      std::vector<int64_t> rep((size_t)nt);
+      int64_t uniq = 0;
+      for (int64_t t = 0; t < nt; ++t) {
+        auto key = std::make_pair(h[2 * t], h[2 * t + 1]);
+        auto it = first.find(key);
+        if (it == first.end()) {
+          first.emplace(key, t);
+          rep[t] = t;
+          ++uniq;
+        } else {
+          rep[t] = it->second;
+        }
+      }
+      cudaMemcpyAsync(rep_d, rep.data(), sizeof(int64_t) * (size_t)nt, cudaMemcpyHostToDevice, s);
+      apply_representatives<<<GRID(nt, 256), 256, 0, s>>>(p.tdesc, rep_d, nt);
+      if (cudaStreamSynchronize(s) != cudaSuccess) {
+        fdts_set_error("residual tile plan: applying the pattern dictionary failed");
+        rc = 2;
+        break;
+      }
+      p.unique_patterns = uniq;
+      if (e->opt_optimize && uniq <= 4096) {
+        std::vector<uint2> hm;
+        std::vector<uint16_t> hi, hg;
+        bool ok = true;
+        for (int64_t t = 0; t < nt && ok; ++t) {
+          if (rep[t] != t || hd[t].nsl == 0 || hd[t].nidx == 0) continue;
+          hm.resize((size_t)hd[t].ncls);
+          hi.resize((size_t)hd[t].nidx);
+          hg.resize((size_t)hd[t].nsl * 32);
+          ok = cudaMemcpy(hm.data(), p.cmeta + hd[t].cls_off, sizeof(uint2) * hm.size(), cudaMemcpyDeviceToHost) == cudaSuccess &&
+               cudaMemcpy(hi.data(), p.cidx + hd[t].idx_off, sizeof(uint16_t) * hi.size(), cudaMemcpyDeviceToHost) == cudaSuccess &&
+               cudaMemcpy(hg.data(), p.gdst + hd[t].meta_off * 32, sizeof(uint16_t) * hg.size(), cudaMemcpyDeviceToHost) == cudaSuccess;
+          if (!ok) break;
+          optimize_pattern(hd[t], hm.data(), hi.data(), hg.data(), 1, p.zaddr);
+          ok = cudaMemcpy(p.cidx + hd[t].idx_off, hi.data(), sizeof(uint16_t) * hi.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+               cudaMemcpy(p.gdst + hd[t].meta_off * 32, hg.data(), sizeof(uint16_t) * hg.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+        }
+        if (!ok) {
+          fdts_set_error("residual tile plan: pattern optimisation failed");
+          rc = 2;
+          break;
+        }
+      }
+    }
+    p.ready = true;
+  } while (0);
+  void *scratch[] = {tmp, tstart, tbase, tptr, iota, btotal, bnsl, idx_off, meta_off, nsl_true, u64tmp, dmax, imax, derr, bcount,
+                     vcount, ucount, bncls, bcells, cnt8, sellpos, hash_d, rep_d};
+  for (void *q : scratch)
+    if (q) cudaFree(q);
+  if (rc) fdts_free_rplan(e);
+  return rc;
+}

@@ -9,6 +9,7 @@
 // zeros dropped.  Two scatter strategies share this element kernel:
 //   path 1  one thread per cell, `red.global.add.f64` into Vec / CSR (atomic)
 //   path 2  owner-computes gather (deterministic, write-once), see heat_gather.cuh
+#include <algorithm>
 #include <type_traits>
 #include <utility>
 
@@ -1068,6 +1069,165 @@ int launch_gather2(G2Args a, const GatherPlan2 &p, int threads, cudaStream_t s) 
   return launch_gather2_nt<DIM, DEG, VAR, 1024>(a, p, s);
 }
 
+// ------------------------------------------------------------------ residual, tile plan
+// One CTA per cell tile (gather_plan.cu: residual tile plan).  The tile's node values and vertex
+// coordinates come in with coalesced loads and live in shared memory, every thread computes the element
+// vector of one cell (closed form), the vectors are pre-reduced per unique node of the tile through
+// SELL lists (lane = node) and ONE `red.global.add.f64` per (tile, node) goes out -- 5x fewer atomics and
+// no scattered 8-byte gathers of u, udot and the coordinates (the per-cell atomic kernel is bound by
+// exactly those: 776 M L1 sector requests per call, ncu l1tex 69 % of peak).
+#ifndef RT_MINB
+#define RT_MINB 4
+#endif
+struct RTArgs {
+  const BlockDesc2 *tdesc;
+  const uint16_t *cidx, *gdst, *tlid;
+  const uint2 *cmeta;
+  const uint32_t *bcc;
+  const int32_t *tnode;
+  const double *bvcoords, *x, *xdot;
+  double *out;
+  int64_t t0;  // first tile of this launch
+  double p0;
+  int32_t cmaxp, umaxp, ndp, zaddr, off_su, off_sud, off_vtab;
+};
+
+template <int DIM, int DEG, int VAR, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) heat_residual_tiles(const RTArgs a) {
+  using T = RefT<DIM, DEG, VAR>;
+  constexpr int ND = T::ND, NP = T::NP, NDP = ND | 1, NWARPS = NT / 32;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double *stage = reinterpret_cast<double *>(smraw);
+  double *su = reinterpret_cast<double *>(smraw + a.off_su);
+  double *sud = reinterpret_cast<double *>(smraw + a.off_sud);
+  double *vtab = reinterpret_cast<double *>(smraw + a.off_vtab);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t t = a.t0 + blockIdx.x;
+  const BlockDesc2 d = a.tdesc[t];
+  const int64_t pat = d.pattern;
+  const int32_t *__restrict__ tn = a.tnode + pat * a.umaxp;
+  // ---- stage node values and vertex coordinates
+  for (int q = threadIdx.x; q < d.nslots; q += NT) {
+    const int64_t node = d.s0 + (tn[q] & 0x7fffffff);
+    su[q] = __ldg(a.x + node);
+    sud[q] = __ldg(a.xdot + node);
+  }
+  for (int q = threadIdx.x; q < d.nvert * DIM; q += NT) vtab[q] = __ldg(a.bvcoords + d.vc_off + q);
+  if (threadIdx.x < 16) stage[a.zaddr + threadIdx.x] = 0.0;
+  __syncthreads();
+  // ---- element vectors
+  for (int k = threadIdx.x; k < d.ncell; k += NT) {
+    const uint32_t packed = a.bcc[d.cc_off + k];
+    double X[DIM + 1][DIM];
+#pragma unroll
+    for (int v = 0; v <= DIM; ++v) {
+      const int lv = (packed >> (8 * v)) & 255;
+#pragma unroll
+      for (int q = 0; q < DIM; ++q) X[v][q] = vtab[lv * DIM + q];
+    }
+    Geom<DIM> g;
+    geometry_from_vertices<DIM>(X, g);
+    double gm[NP];
+    metric<DIM>(g, gm);
+    // two passes to keep the register footprint low (4 CTAs per SM): mass with udot, then stiffness with u
+    uint16_t lid[ND];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) lid[i] = a.tlid[(pat * ND + i) * a.cmaxp + k];
+    double *st = stage + k * NDP;
+    {
+      double ud[ND];
+#pragma unroll
+      for (int i = 0; i < ND; ++i) ud[i] = sud[lid[i]];
+      static_for<ND>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        double mass = -a.p0 * T::M0[i];
+        static_for<ND>([&](auto J) {
+          constexpr int j = decltype(J)::value;
+          constexpr double r = T::R00[i][j];
+          if constexpr (r != 0.0) mass = fma(r, ud[j], mass);
+        });
+        st[i] = mass * g.adet;
+      });
+    }
+    {
+      double u[ND];
+#pragma unroll
+      for (int i = 0; i < ND; ++i) u[i] = su[lid[i]];
+      static_for<ND>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        double f = st[i];
+        static_for<NP>([&](auto P) {
+          constexpr int p = decltype(P)::value;
+          double sacc = 0.0;
+          static_for<ND>([&](auto J) {
+            constexpr int j = decltype(J)::value;
+            constexpr double sv = T::S[p][i][j];
+            if constexpr (sv != 0.0) sacc = fma(sv, u[j], sacc);
+          });
+          f = fma(gm[p], sacc, f);
+        });
+        st[i] = f;
+      });
+    }
+  }
+  __syncthreads();
+  // ---- per-node sums (SELL sweep, lane = unique node of the tile), one atomic per node
+  const uint16_t *__restrict__ idx = a.cidx + d.idx_off;
+  const uint16_t *__restrict__ gd = a.gdst + d.meta_off * 32;
+  const uint2 *__restrict__ cls = a.cmeta + d.cls_off;
+  for (int c = 0; c < d.ncls; ++c) {
+    const uint2 ce = cls[c];
+    const int first = (int)(ce.x & 0xffffu), count = (int)(ce.x >> 16), w = (int)((ce.y >> 16) & 0xffu);
+    const bool split = (ce.y >> 24) != 0;
+    const uint32_t pairs = (uint32_t)((w + 1) >> 1);
+    for (int i = first_slice_of<NWARPS>(warp, (uint32_t)first); i < count; i += NWARPS) {
+      const uint32_t *ip = reinterpret_cast<const uint32_t *>(idx) + ((size_t)(ce.y & 0xffffu) + (size_t)i * pairs) * 32 + lane;
+      double a0 = 0.0, a1 = 0.0;
+      for (uint32_t q = 0; q < pairs; ++q) {
+        const uint32_t pr = __ldg(ip + q * 32);
+        a0 += stage[pr & 0xffffu];
+        if (2 * q + 1 < (uint32_t)w) a1 += stage[pr >> 16];
+      }
+      double acc = a0 + a1;
+      int gsel = lane;
+      bool wr = true;
+      if (split) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        gsel = lane >> 2;
+        wr = (lane & 3) == 0;
+      }
+      const uint32_t ln = gd[(size_t)(first + i) * 32 + gsel];
+      if (wr && ln != 0xffffu) {
+        const int32_t rel = tn[ln];
+        if (rel >= 0) red_add_f64(a.out + d.s0 + rel, acc);
+      }
+    }
+  }
+}
+
+template <int DIM, int DEG, int VAR>
+int launch_residual_tiles(RTArgs a, const ResidualPlan &p, int64_t t0, int64_t t1, cudaStream_t s) {
+  using T = RefT<DIM, DEG, VAR>;
+  constexpr int NT = 192;
+  if (p.ndp != (T::ND | 1)) return 3;
+  auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  size_t off = up16(sizeof(double) * ((size_t)p.zaddr + 16));
+  a.off_su = (int)off;
+  off += up16(8 * (size_t)p.umaxp);
+  a.off_sud = (int)off;
+  off += up16(8 * (size_t)p.umaxp);
+  a.off_vtab = (int)off;
+  off += up16(8 * (size_t)p.vmax * DIM + 16);
+  const size_t smem = off;
+  if (smem > 227 * 1024) return 4;
+  a.t0 = t0;
+  auto k = heat_residual_tiles<DIM, DEG, VAR, NT, RT_MINB>;
+  if (smem > 48 * 1024 && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
+  if (t1 > t0) k<<<(unsigned)(t1 - t0), NT, smem, s>>>(a);
+  return cudaGetLastError() == cudaSuccess ? 0 : 2;
+}
+
 __global__ void set_values_k(double *__restrict__ v, const int64_t *__restrict__ slots, int64_t n, double val) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n && slots[t] >= 0) v[slots[t]] = val;
@@ -1190,6 +1350,31 @@ int fdts_launch_heat(fdts_engine *e, int which, const double *x, const double *x
   if (var < 0) {
     fdts_set_error("closed-form heat path: run-time reference tensors do not match the compiled tables");
     return 3;
+  }
+  if (which == 0 && e->rplan.ready && e->opt_residual_tiles) {
+    // cell range -> tile range (only when both ends are tile boundaries; otherwise the per-cell kernel)
+    const ResidualPlan &p = e->rplan;
+    const int64_t *ts = p.tstart_host;
+    const int64_t *lo = std::lower_bound(ts, ts + p.ntiles + 1, c0), *hi = std::lower_bound(ts, ts + p.ntiles + 1, c1);
+    if (lo != ts + p.ntiles + 1 && hi != ts + p.ntiles + 1 && *lo == c0 && *hi == c1) {
+      if (flags & 1) FDTS_CHECK(cudaMemsetAsync(out, 0, sizeof(double) * e->cfg.num_owned_nodes, s));
+      RTArgs r;
+      r.tdesc = p.tdesc; r.cidx = p.cidx; r.gdst = p.gdst; r.tlid = p.tlid; r.cmeta = p.cmeta; r.bcc = p.bcc;
+      r.tnode = p.tnode; r.bvcoords = p.bvcoords; r.x = x; r.xdot = xdot; r.out = out; r.p0 = e->cfg.params[0];
+      r.cmaxp = p.cmaxp; r.umaxp = p.umaxp; r.ndp = p.ndp; r.zaddr = p.zaddr;
+      int rc = 3;
+#define RTCASE(D, K, V) \
+  if (dim == D && deg == K && (K < 3 || var == V)) rc = launch_residual_tiles<D, K, V>(r, p, lo - ts, hi - ts, s);
+      RTCASE(1, 1, 1) RTCASE(1, 2, 1) RTCASE(1, 3, 0) RTCASE(1, 3, 1)
+      RTCASE(2, 1, 1) RTCASE(2, 2, 1) RTCASE(2, 3, 0) RTCASE(2, 3, 1)
+      RTCASE(3, 1, 1) RTCASE(3, 2, 1) RTCASE(3, 3, 0) RTCASE(3, 3, 1)
+#undef RTCASE
+      if (rc == 2) fdts_set_error(std::string("residual tile kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+      if (rc == 3 || rc == 4) fdts_set_error("residual tile kernel: unsupported element or tile too large for shared memory");
+      if (rc) return rc;
+      e->launches++;
+      return 0;
+    }
   }
   if (flags & 1) {
     if (which == 0)

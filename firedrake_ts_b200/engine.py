@@ -25,6 +25,7 @@ SYMBOLS = [
     "fdts_get_node_csr", "fdts_set_param", "fdts_set_option", "fdts_get_option", "fdts_ifunction", "fdts_ijacobian",
     "fdts_ifunction_range", "fdts_ijacobian_range", "fdts_ifunction_host", "fdts_ijacobian_host", "fdts_halo_pack",
     "fdts_halo_unpack", "fdts_launch_count", "fdts_measure_fp64_peak", "fdts_csr_spmv", "fdts_csr_diagonal", "fdts_set_row_blocks",
+    "fdts_set_cell_tiles",
 ]
 
 
@@ -83,6 +84,7 @@ def load_library():
         lib.fdts_halo_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         lib.fdts_halo_unpack.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
         lib.fdts_set_row_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        lib.fdts_set_cell_tiles.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         lib.fdts_csr_spmv.argtypes = [C.c_int64] + [C.c_void_p] * 6
         lib.fdts_csr_diagonal.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                           C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
@@ -170,6 +172,8 @@ class Engine:
                     starts = torch.arange(0, V.num_owned_nodes + 128, 128).clamp(max=V.num_owned_nodes)
                     starts = torch.unique(starts)
                 self.set_row_blocks(starts)
+                if form.family == 0 and V.ncomp == 1 and (options or {}).get("residual_tiles", 0):
+                    self.set_cell_tiles(m.cell_tile_starts(max_pairs=4096 // V.nd))
             self.set_option("scatter", scatter)
 
     def __del__(self):
@@ -194,6 +198,12 @@ class Engine:
         st = torch.as_tensor(starts, dtype=torch.int64).cpu().contiguous()
         with torch.cuda.device(self.device):
             _check(self._lib.fdts_set_row_blocks(self._h, st.data_ptr(), st.numel() - 1), "fdts_set_row_blocks")
+
+    def set_cell_tiles(self, starts):
+        """cell tiles (cell offsets) of the residual tile kernel; builds the tile plan."""
+        st = torch.as_tensor(starts, dtype=torch.int64).cpu().contiguous()
+        with torch.cuda.device(self.device):
+            _check(self._lib.fdts_set_cell_tiles(self._h, st.data_ptr(), st.numel() - 1), "fdts_set_cell_tiles")
 
     def set_param(self, index, value):
         _check(self._lib.fdts_set_param(self._h, index, float(value)), "fdts_set_param")

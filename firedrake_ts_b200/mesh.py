@@ -235,6 +235,34 @@ class SimplexMesh:
         coords[flat] = self.cell_vlat.reshape(-1, dim).to(torch.float64) * h
         self.coords = coords
 
+    def cell_tile_starts(self, max_pairs=409):
+        """cell offsets of contiguous cell tiles for the residual tile kernel: the cubes of one numbering
+        tile (single rank, exact tile sizes) or uniform chunks (partitioned meshes / untiled numbering);
+        the interior/halo boundary is always a tile boundary; at most ``max_pairs`` cells per tile."""
+        cpc = self.cells_per_cube
+        dims = [self.box_hi[a] - self.box_lo[a] for a in range(self.dim)]
+        sizes = None
+        if self.partition.size == 1 and self.tile[0] > 0:
+            out = torch.ones(1, dtype=torch.int64)
+            for a in range(self.dim - 1, -1, -1):
+                out = (out[:, None] * torch.tensor(_tile_sizes(dims[a], self.tile[a], 0), dtype=torch.int64)[None, :]).reshape(-1)
+            sizes = out * cpc
+            if int(sizes.max()) > max_pairs:
+                sizes = None
+        if sizes is None:
+            chunk = max(cpc, (min(max_pairs, 27 * cpc) // cpc) * cpc)
+            parts = []
+            for lo, hi in ((0, self.num_interior_cells), (self.num_interior_cells, self.num_cells)):
+                n = hi - lo
+                if n > 0:
+                    full, rem = divmod(n, chunk)
+                    parts += [chunk] * full + ([rem] if rem else [])
+            sizes = torch.tensor(parts, dtype=torch.int64)
+        starts = torch.zeros(sizes.numel() + 1, dtype=torch.int64)
+        starts[1:] = torch.cumsum(sizes, 0)
+        assert int(starts[-1]) == self.num_cells
+        return starts
+
     # -- counts ------------------------------------------------------------
     @property
     def global_num_cells(self):

@@ -103,6 +103,11 @@ int fdts_set_param(fdts_handle h, int32_t index, double value);
  * offsets of contiguous blocks (one CTA each); builds the gather plan on the device.
  * Replaces nothing in the reference: it is the engine's own scatter schedule (K6). */
 int fdts_set_row_blocks(fdts_handle h, const int64_t *starts_host, int64_t nblocks);
+/* Cell tiles of the residual's tile kernel: starts_host[0..ntiles] are cell offsets of contiguous tiles
+ * (cells x nodes per cell <= 4096 per tile).  Builds the tile plan on the device: per tile the unique
+ * nodes, vertex table and per-node gather lists, so that the element vectors are pre-reduced in shared
+ * memory and one atomic per (tile, node) is issued.  The engine's own schedule (K1), replaces nothing. */
+int fdts_set_cell_tiles(fdts_handle h, const int64_t *starts_host, int64_t ntiles);
 /* options: "scatter" 0 = generic quadrature kernels + atomic scatter (REDG.ADD.F64),
  *                    1 = closed-form heat kernels + atomic scatter,
  *                    2 = closed-form heat kernels + owner-computes gather (deterministic, write-once);

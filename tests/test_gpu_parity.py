@@ -131,3 +131,33 @@ def test_overlapped_kernel_bitwise_equal(dim, degree, n, ftile):
     for _ in range(3):  # repeated launches: the hand-over barriers must not depend on timing
         assert torch.equal(e1.ijacobian(0.0, x, xd, 3.0), J0)
     assert rel_err(J0.cpu().numpy(), Oracle.from_form(form, bcs).ijacobian(0.0, u.data, udot.data, 3.0)) < TOL
+
+
+@pytest.mark.parametrize("dim,degree,n,tile", [(3, 2, 7, 3), (3, 2, 6, 0), (2, 2, 12, 4), (3, 1, 9, 3), (2, 3, 6, 2),
+                                               (1, 2, 30, 6), (3, 3, 3, 1)])
+def test_residual_tile_kernel(dim, degree, n, tile):
+    """residual tile kernel (coalesced staging of node values, per-tile pre-reduction, one atomic per
+    (tile, node)) against the oracle and against the per-cell kernel, incl. tile-aligned cell ranges."""
+    from firedrake_ts_b200.engine import Engine
+    from oracle import Oracle
+
+    form, bcs, u, udot = make_problem("heat", dim, degree, n, tile=tile, ftile=2 * tile if tile else None)
+    x, xd = u.data.cuda(), udot.data.cuda()
+    eng = Engine(form, bcs, device="cuda:0", scatter=1)
+    V = form.space
+    starts = V.mesh.cell_tile_starts(max_pairs=4096 // V.nd)
+    eng.set_cell_tiles(starts)
+    assert eng.get_option("residual_tiles") == starts.numel() - 1
+    Fo = Oracle.from_form(form, bcs).ifunction(0.0, u.data, udot.data)
+    F1 = eng.ifunction(0.0, x, xd)
+    assert rel_err(F1.cpu().numpy(), Fo) < TOL
+    eng.set_option("residual_tiles", 0)
+    F0 = eng.ifunction(0.0, x, xd)
+    eng.set_option("residual_tiles", 1)
+    assert rel_err(F1.cpu().numpy(), F0.cpu().numpy()) < TOL
+    # two tile-aligned ranges add up to the full residual
+    mid = int(starts[(starts.numel() - 1) // 2])
+    F2 = torch.empty_like(F1)
+    eng.ifunction_range(0.0, x, xd, F2, 0, mid, 1)
+    eng.ifunction_range(0.0, x, xd, F2, mid, eng.num_cells, 0)
+    assert rel_err(F2.cpu().numpy(), Fo) < TOL

@@ -26,6 +26,7 @@ ap.add_argument("--debug", type=int, default=0)
 ap.add_argument("--sector", type=int, default=4)
 ap.add_argument("--optimize", type=int, default=1)
 ap.add_argument("--threads", type=int, default=512)
+ap.add_argument("--rtiles", type=int, default=0)
 ap.add_argument("--dedup", type=int, default=1)
 ap.add_argument("--foffset", type=int, default=0)
 a = ap.parse_args()
@@ -46,14 +47,15 @@ torch.cuda.synchronize()
 print("mesh+space", time.time() - t0, "s; cells", form.space.mesh.num_cells, "dofs", form.space.num_dofs, flush=True)
 t0 = time.time()
 eng = Engine(form, bcs, scatter=a.scatter, plan_version=a.plan, dedup=a.dedup,
-             options={"sector": a.sector, "optimize": a.optimize, "threads": a.threads})
+             options={"sector": a.sector, "optimize": a.optimize, "threads": a.threads, "residual_tiles": a.rtiles})
 torch.cuda.synchronize()
 print("engine create", time.time() - t0, "s; nnz", eng.nnz, "maxrow", eng.max_row_nodes, "maxdeg", eng.max_degree, flush=True)
 if a.scatter == 2:
     print("plan: version", eng.get_option("plan_version"), "blocks", eng.get_option("plan_blocks"), "cells_max",
           eng.get_option("plan_cells_max"), "contrib", eng.get_option("plan_contributions"), "patterns",
           eng.get_option("plan_patterns"), "shared contrib", eng.get_option("plan_shared_contributions"),
-          "vmax", eng.get_option("plan_vertices_max"), flush=True)
+          "vmax", eng.get_option("plan_vertices_max"), "residual tiles", eng.get_option("residual_tiles"),
+          "patterns", eng.get_option("residual_patterns"), flush=True)
 x, xd = u.data, udot.data
 if a.debug:
     eng.set_option("debug", a.debug)
