@@ -158,7 +158,10 @@ int fdts_launch_jacobian(fdts_engine *e, const double *x, const double *xdot, do
   int rc = 3;
   switch (e->cfg.family) {
     case FDTS_HEAT: rc = fdts_generic_heat(true, e, a, s); break;
-    case FDTS_BBM: rc = fdts_generic_bbm(true, e, a, s); break;
+    case FDTS_BBM:
+      rc = fdts_bbm_jacobian_dmma(e, a, s);  // tensor-core contraction where it applies (P2/P3), else generic
+      if (rc == 3) rc = fdts_generic_bbm(true, e, a, s);
+      break;
     case FDTS_BURGERS: rc = fdts_generic_burgers(true, e, a, s); break;
     case FDTS_CAHN_HILLIARD: rc = fdts_generic_ch(true, e, a, s); break;
   }
@@ -252,7 +255,7 @@ extern "C" int fdts_destroy(fdts_handle e) {
   cudaSetDevice(e->device);
   void *ptrs[] = {e->coords, e->cell_coord, e->cell_node, e->B, e->w, e->R, e->M0, e->isbc, e->bc_nodes,
                   e->bc_diag_slot, e->nrowptr, e->ncolidx, e->pos8, e->adj_ptr, e->adj_cell, e->h2d_x, e->h2d_xdot,
-                  e->d_f, e->d_vals, e->cell_rowmask};
+                  e->d_f, e->d_vals, e->cell_rowmask, e->pos8_cm};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   fdts_free_plan(e);
@@ -350,6 +353,10 @@ extern "C" int fdts_set_option(fdts_handle e, const char *key, int64_t value) {
   }
   if (!strcmp(key, "residual_tiles")) {
     e->opt_residual_tiles = value ? 1 : 0;
+    return 0;
+  }
+  if (!strcmp(key, "dmma")) {
+    e->opt_dmma = value ? 1 : 0;
     return 0;
   }
   if (!strcmp(key, "overlap")) {

@@ -125,6 +125,7 @@ struct fdts_engine {
   int64_t node_nnz = 0;
   int32_t max_row_nodes = 0;
   uint8_t *pos8 = nullptr;       // num_cells x nd x nd : position of node j inside node row i
+  uint8_t *pos8_cm = nullptr;    // cell-major copy (DMMA kernel: one warp per cell), built on first use
   // row -> (cell, local index) adjacency, built for the pattern and reused by gather kernels
   int64_t *adj_ptr = nullptr;    // num_owned_nodes + 1
   int32_t *adj_cell = nullptr;   // cell * 32 + local index (nd <= 20 < 32)
@@ -141,6 +142,7 @@ struct fdts_engine {
   int64_t opt_sector = 4;        // plan 2: slots per store group (4 or 2)
   int64_t opt_optimize = 1;      // plan 2: bank-conflict-aware column order for the unique patterns
   int64_t opt_residual_tiles = 1; // residual: tile kernel (pre-reduced atomics) when a cell-tile plan exists (fdts_set_cell_tiles; the Python layer only builds one on request: the kernel is slower than the per-cell one today)
+  int64_t opt_dmma = 1;          // BBM P2/P3: fp64 tensor-core element-matrix contraction instead of the generic Jacobian kernel
   int64_t opt_overlap = 0;       // plan 2: warp-specialised kernel (element matrices of block b+1 overlap the gather of block b; needs two staging buffers in smem; slower than the two-phase kernel on every block shape measured so far)
   int64_t opt_threads = 512;     // plan 2: threads per persistent CTA (512: 128 registers per thread, or 1024)
   int64_t opt_debug = 0;         // development only (timing experiments with phases switched off)
@@ -170,6 +172,8 @@ int fdts_launch_jacobian(fdts_engine *e, const double *x, const double *xdot, do
 int fdts_launch_heat(fdts_engine *e, int which, const double *x, const double *xdot, double shift, double *out,
                      int64_t c0, int64_t c1, int flags, cudaStream_t s);
 int fdts_build_pattern(fdts_engine *e, cudaStream_t s);
+struct KArgs;
+int fdts_bbm_jacobian_dmma(fdts_engine *e, const KArgs &a, cudaStream_t s);
 int fdts_heat_match_tables(int dim, int deg, const double *R_host);
 int fdts_build_plan(fdts_engine *e, const int64_t *starts_host, int64_t nblocks);
 int fdts_build_plan2(fdts_engine *e, const int64_t *starts_host, int64_t nblocks);
