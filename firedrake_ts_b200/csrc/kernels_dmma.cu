@@ -25,7 +25,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) 
 }
 
 constexpr int DMMA_STRIDE = 28;  // doubles per quadrature row of a table (>= 24, = 12 mod 16: see header)
-constexpr int DMMA_WARPS = 8;
+constexpr int DMMA_WARPS = 16;
 
 __global__ void pos8_cell_major(const uint8_t *__restrict__ pos8_t, int64_t nc, int nd2, uint8_t *__restrict__ out) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
