@@ -352,7 +352,7 @@ extern "C" int fdts_set_option(fdts_handle e, const char *key, int64_t value) {
     return 0;
   }
   if (!strcmp(key, "residual_tiles")) {
-    e->opt_residual_tiles = value ? 1 : 0;
+    e->opt_residual_tiles = value < 0 ? 0 : (value > 2 ? 2 : value);  // 0 off, 1 staged inputs, 2 direct gathers
     return 0;
   }
   if (!strcmp(key, "dmma")) {

@@ -101,6 +101,7 @@ struct ResidualPlan {
   uint16_t *tlid = nullptr;     // per tile: [nd][cmaxp] tile-local node index of every cell
   BlockDesc2 *tdesc = nullptr;  // s0 = first node id of the tile, nslots = unique nodes
   int64_t *tstart_host = nullptr;  // ntiles+1 cell offsets (host copy, for cell-range calls)
+  int64_t *tstart_dev = nullptr;   // the same on the device
   int64_t unique_patterns = 0;
 };
 

@@ -1669,7 +1669,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) tile_hash(const BlockDesc2 *__re
 
 void fdts_free_rplan(fdts_engine *e) {
   ResidualPlan &p = e->rplan;
-  void *ptrs[] = {p.cidx, p.cmeta, p.gdst, p.bcc, p.bvcoords, p.tnode, p.tlid, p.tdesc};
+  void *ptrs[] = {p.cidx, p.cmeta, p.gdst, p.bcc, p.bvcoords, p.tnode, p.tlid, p.tdesc, p.tstart_dev};
   for (void *q : ptrs)
     if (q) cudaFree(q);
   delete[] p.tstart_host;
@@ -1912,6 +1912,8 @@ int fdts_build_rplan(fdts_engine *e, const int64_t *starts, int64_t nt) {
         }
       }
     }
+    p.tstart_dev = tstart;
+    tstart = nullptr;
     p.ready = true;
   } while (0);
   void *scratch[] = {tmp, tstart, tbase, tptr, iota, btotal, bnsl, idx_off, meta_off, nsl_true, u64tmp, dmax, imax, derr, bcount,

@@ -55,6 +55,115 @@ __device__ __forceinline__ double heat_entry(double m, const double (&gm)[NP]) {
   return v;
 }
 
+// Sum-factorised element residual of the heat form on a P2 tetrahedron (local node order of fem.py:
+// vertices 0-3, then edges (2,3) (1,3) (1,2) (0,3) (0,2) (0,1)).  Same result as the table form
+//   f_i = adet * sum_j R00_ij ud_j + sum_p gm_p sum_j S_pij u_j - p0 M0_i adet
+// in ~230 instead of ~460 fp64 operations and fewer live registers:
+//  * grad u is linear on the cell, so it is represented by its values at the 4 vertices
+//    (d_a^v = 3 u_a if a == v else 4 u_(a,v) - u_a in barycentric components), mapped through the metric
+//    (q = G grad u, 36 FMA) and tested with the (equally linear) basis gradients via the P1 mass matrix
+//    int lambda_v lambda_w = (1 + delta_vw) / 120;
+//  * the P2 mass matrix 1/2520 [6,1 | -4,-6 | 32,16,8] is applied through vertex / edge sums.
+__device__ __forceinline__ void p2tet_heat_residual(const double (&gm)[6], double adet, double p0, const double (&u)[10],
+                                                    const double (&ud)[10], double (&f)[10]) {
+  constexpr int E[4][4] = {{-1, 9, 8, 7}, {9, -1, 6, 5}, {8, 6, -1, 4}, {7, 5, 4, -1}};  // edge node of (a, b)
+  double d[4][4];  // d[a][v]: barycentric derivative a of u at vertex v
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) d[a][v] = a == v ? 3.0 * u[a] : fma(4.0, u[E[a][v]], -u[a]);
+  const double s120 = 1.0 / 120.0;
+  const double G[3][3] = {{gm[0] * s120, gm[1] * s120, gm[2] * s120},
+                          {gm[1] * s120, gm[3] * s120, gm[4] * s120},
+                          {gm[2] * s120, gm[4] * s120, gm[5] * s120}};
+  double Q[3][4], SQ[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double q[4], sq = 0.0;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      double t = 0.0;
+#pragma unroll
+      for (int e = 0; e < 3; ++e) t = fma(G[c][e], d[e + 1][v] - d[0][v], t);
+      q[v] = t;
+      sq += t;
+    }
+    SQ[c] = 0.0;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      Q[c][v] = q[v] + sq;
+      SQ[c] += Q[c][v];
+    }
+  }
+  f[0] = -(fma(4.0, Q[0][0], -SQ[0]) + fma(4.0, Q[1][0], -SQ[1]) + fma(4.0, Q[2][0], -SQ[2]));
+#pragma unroll
+  for (int a = 1; a < 4; ++a) f[a] = fma(4.0, Q[a - 1][a], -SQ[a - 1]);
+#pragma unroll
+  for (int a = 1; a < 4; ++a)
+#pragma unroll
+    for (int b = a + 1; b < 4; ++b) f[E[a][b]] = 4.0 * (Q[a - 1][b] + Q[b - 1][a]);
+#pragma unroll
+  for (int a = 1; a < 4; ++a) f[E[0][a]] = 4.0 * (Q[a - 1][0] - (Q[0][a] + Q[1][a] + Q[2][a]));
+  const double SV = (ud[0] + ud[1]) + (ud[2] + ud[3]);
+  const double SE = ((ud[4] + ud[5]) + (ud[6] + ud[7])) + (ud[8] + ud[9]);
+  const double ms = adet * (1.0 / 2520.0);
+  const double cv = fma(-6.0, SE, SV), ce = fma(16.0, SE, -6.0 * SV);
+  const double src_v = p0 * adet * (1.0 / 120.0), src_e = -p0 * adet * (1.0 / 30.0);  // -p0 * M0_i * adet
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    double adj = 0.0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if (b != a) adj += ud[E[a][b]];
+    f[a] += fma(fma(5.0, ud[a], fma(2.0, adj, cv)), ms, src_v);
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = a + 1; b < 4; ++b) {
+      int c = -1, dd = -1;  // opposite edge = the other two vertices
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        if (v != a && v != b) {
+          if (c < 0) c = v; else dd = v;
+        }
+      const int e = E[a][b];
+      f[e] += fma(fma(16.0, ud[e], fma(-8.0, ud[E[c][dd]], fma(2.0, ud[a] + ud[b], ce))), ms, src_e);
+    }
+}
+
+// element residual of one cell, table form or (P2 tetrahedra) sum-factorised
+template <int DIM, int DEG, int VAR, int ND, int NP>
+__device__ __forceinline__ void heat_element_residual(const double (&gm)[NP], double adet, double p0, const double (&u)[ND],
+                                                      const double (&ud)[ND], double (&f)[ND]) {
+  using T = RefT<DIM, DEG, VAR>;
+  if constexpr (DIM == 3 && DEG == 2) {
+    p2tet_heat_residual(gm, adet, p0, u, ud, f);
+  } else {
+    static_for<ND>([&](auto I) {
+      constexpr int i = decltype(I)::value;
+      double mass = -p0 * T::M0[i];
+      static_for<ND>([&](auto J) {
+        constexpr int j = decltype(J)::value;
+        constexpr double r = T::R00[i][j];
+        if constexpr (r != 0.0) mass = fma(r, ud[j], mass);
+      });
+      double fi = mass * adet;
+      static_for<NP>([&](auto P) {
+        constexpr int p = decltype(P)::value;
+        double sacc = 0.0;
+        static_for<ND>([&](auto J) {
+          constexpr int j = decltype(J)::value;
+          constexpr double sv = T::S[p][i][j];
+          if constexpr (sv != 0.0) sacc = fma(sv, u[j], sacc);
+        });
+        fi = fma(gm[p], sacc, fi);
+      });
+      f[i] = fi;
+    });
+  }
+}
+
 // ------------------------------------------------------------------ path 1: atomic
 template <int DIM, int DEG, int VAR>
 __global__ void __launch_bounds__(128) heat_jacobian_atomic(const KArgs a) {
@@ -1087,7 +1196,12 @@ struct RTArgs {
   const int32_t *tnode;
   const double *bvcoords, *x, *xdot;
   double *out;
+  const int64_t *tstart;        // direct variant: first cell of every tile, maps, coordinates
+  const int32_t *cell_node_t, *cell_coord_t;
+  const double *coords;
+  int64_t nc;
   int64_t t0;  // first tile of this launch
+  int32_t direct;
   double p0;
   int32_t cmaxp, umaxp, ndp, zaddr, off_su, off_sud, off_vtab;
 };
@@ -1206,6 +1320,78 @@ __global__ void __launch_bounds__(NT, MINB) heat_residual_tiles(const RTArgs a) 
   }
 }
 
+// variant: the cells gather their inputs directly (like the per-cell kernel: high memory-level
+// parallelism, no staging phase), only the element vectors are staged and pre-reduced per tile
+template <int DIM, int DEG, int VAR, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) heat_residual_tiles_direct(const RTArgs a) {
+  using T = RefT<DIM, DEG, VAR>;
+  constexpr int ND = T::ND, NP = T::NP, NDP = ND | 1, NWARPS = NT / 32;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double *stage = reinterpret_cast<double *>(smraw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t t = a.t0 + blockIdx.x;
+  const BlockDesc2 d = a.tdesc[t];
+  const int64_t c0 = a.tstart[t];
+  if (threadIdx.x < 16) stage[a.zaddr + threadIdx.x] = 0.0;
+  for (int k = threadIdx.x; k < d.ncell; k += NT) {
+    const int64_t c = c0 + k;
+    int32_t cc[DIM + 1], nodes[ND];
+#pragma unroll
+    for (int v = 0; v <= DIM; ++v) cc[v] = a.cell_coord_t[v * a.nc + c];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) nodes[i] = a.cell_node_t[i * a.nc + c];
+    Geom<DIM> g;
+    compute_geometry<DIM>(a.coords, cc, g);
+    double gm[NP];
+    metric<DIM>(g, gm);
+    double u[ND], ud[ND], f[ND];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) {
+      u[i] = __ldg(a.x + nodes[i]);
+      ud[i] = __ldg(a.xdot + nodes[i]);
+    }
+    heat_element_residual<DIM, DEG, VAR, ND, NP>(gm, g.adet, a.p0, u, ud, f);
+    double *st = stage + k * NDP;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) st[i] = f[i];
+  }
+  __syncthreads();
+  const int64_t pat = d.pattern;
+  const int32_t *__restrict__ tn = a.tnode + pat * a.umaxp;
+  const uint16_t *__restrict__ idx = a.cidx + d.idx_off;
+  const uint16_t *__restrict__ gd = a.gdst + d.meta_off * 32;
+  const uint2 *__restrict__ cls = a.cmeta + d.cls_off;
+  for (int c = 0; c < d.ncls; ++c) {
+    const uint2 ce = cls[c];
+    const int first = (int)(ce.x & 0xffffu), count = (int)(ce.x >> 16), w = (int)((ce.y >> 16) & 0xffu);
+    const bool split = (ce.y >> 24) != 0;
+    const uint32_t pairs = (uint32_t)((w + 1) >> 1);
+    for (int i = first_slice_of<NWARPS>(warp, (uint32_t)first); i < count; i += NWARPS) {
+      const uint32_t *ip = reinterpret_cast<const uint32_t *>(idx) + ((size_t)(ce.y & 0xffffu) + (size_t)i * pairs) * 32 + lane;
+      double a0 = 0.0, a1 = 0.0;
+      for (uint32_t q = 0; q < pairs; ++q) {
+        const uint32_t pr = __ldg(ip + q * 32);
+        a0 += stage[pr & 0xffffu];
+        if (2 * q + 1 < (uint32_t)w) a1 += stage[pr >> 16];
+      }
+      double acc = a0 + a1;
+      int gsel = lane;
+      bool wr = true;
+      if (split) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        gsel = lane >> 2;
+        wr = (lane & 3) == 0;
+      }
+      const uint32_t ln = gd[(size_t)(first + i) * 32 + gsel];
+      if (wr && ln != 0xffffu) {
+        const int32_t rel = tn[ln];
+        if (rel >= 0) red_add_f64(a.out + d.s0 + rel, acc);
+      }
+    }
+  }
+}
+
 template <int DIM, int DEG, int VAR>
 int launch_residual_tiles(RTArgs a, const ResidualPlan &p, int64_t t0, int64_t t1, cudaStream_t s) {
   using T = RefT<DIM, DEG, VAR>;
@@ -1222,6 +1408,13 @@ int launch_residual_tiles(RTArgs a, const ResidualPlan &p, int64_t t0, int64_t t
   const size_t smem = off;
   if (smem > 227 * 1024) return 4;
   a.t0 = t0;
+  if (a.direct) {
+    const size_t sm2 = up16(sizeof(double) * ((size_t)p.zaddr + 16));
+    auto k2 = heat_residual_tiles_direct<DIM, DEG, VAR, NT, RT_MINB>;
+    if (sm2 > 48 * 1024 && cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2) != cudaSuccess) return 2;
+    if (t1 > t0) k2<<<(unsigned)(t1 - t0), NT, sm2, s>>>(a);
+    return cudaGetLastError() == cudaSuccess ? 0 : 2;
+  }
   auto k = heat_residual_tiles<DIM, DEG, VAR, NT, RT_MINB>;
   if (smem > 48 * 1024 && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
   if (t1 > t0) k<<<(unsigned)(t1 - t0), NT, smem, s>>>(a);
@@ -1362,6 +1555,8 @@ int fdts_launch_heat(fdts_engine *e, int which, const double *x, const double *x
       r.tdesc = p.tdesc; r.cidx = p.cidx; r.gdst = p.gdst; r.tlid = p.tlid; r.cmeta = p.cmeta; r.bcc = p.bcc;
       r.tnode = p.tnode; r.bvcoords = p.bvcoords; r.x = x; r.xdot = xdot; r.out = out; r.p0 = e->cfg.params[0];
       r.cmaxp = p.cmaxp; r.umaxp = p.umaxp; r.ndp = p.ndp; r.zaddr = p.zaddr;
+      r.tstart = p.tstart_dev; r.cell_node_t = e->cell_node; r.cell_coord_t = e->cell_coord; r.coords = e->coords;
+      r.nc = e->cfg.num_cells; r.direct = e->opt_residual_tiles == 2 ? 1 : 0;
       int rc = 3;
 #define RTCASE(D, K, V) \
   if (dim == D && deg == K && (K < 3 || var == V)) rc = launch_residual_tiles<D, K, V>(r, p, lo - ts, hi - ts, s);

@@ -151,6 +151,8 @@ def test_residual_tile_kernel(dim, degree, n, tile):
     Fo = Oracle.from_form(form, bcs).ifunction(0.0, u.data, udot.data)
     F1 = eng.ifunction(0.0, x, xd)
     assert rel_err(F1.cpu().numpy(), Fo) < TOL
+    eng.set_option("residual_tiles", 2)  # variant: cells gather their inputs directly, tile pre-reduction only
+    assert rel_err(eng.ifunction(0.0, x, xd).cpu().numpy(), Fo) < TOL
     eng.set_option("residual_tiles", 0)
     F0 = eng.ifunction(0.0, x, xd)
     eng.set_option("residual_tiles", 1)

@@ -48,6 +48,8 @@ print("mesh+space", time.time() - t0, "s; cells", form.space.mesh.num_cells, "do
 t0 = time.time()
 eng = Engine(form, bcs, scatter=a.scatter, plan_version=a.plan, dedup=a.dedup,
              options={"sector": a.sector, "optimize": a.optimize, "threads": a.threads, "residual_tiles": a.rtiles})
+if a.rtiles:
+    eng.set_option("residual_tiles", a.rtiles)
 torch.cuda.synchronize()
 print("engine create", time.time() - t0, "s; nnz", eng.nnz, "maxrow", eng.max_row_nodes, "maxdeg", eng.max_degree, flush=True)
 if a.scatter == 2:
