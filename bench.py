@@ -164,8 +164,24 @@ class ClockSampler:
                 for nme, v in zip(names, f[2:6]):
                     if v.lower().startswith("active"):
                         reasons.add(nme)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        note = None
+        if not sm and self.samples:  # timed region shorter than the sampling period: use the nearest samples
+            near = sorted(self.samples, key=lambda s_: min(abs(s_[0] - t0), abs(s_[0] - t1)))[:3]
+            for ts, line in near:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[0]))
+                except (ValueError, IndexError):
+                    continue
+                for nme, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            note = "no sample fell inside the timed region; nearest samples used"
+        out = {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -228,13 +244,16 @@ def run_b200(a):
             eng.ifunction(0.0, x, xd, out=F)
         eng.ijacobian(0.0, x, xd, shift, out=J)
 
+    # clocks are sampled from before the warm-up on (nvidia-smi needs a few 100 ms to start streaming)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(a.warmup):
         step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    time.sleep(0.15)
+    t_wait = time.time()
+    while sampler is not None and not sampler.samples and time.time() - t_wait < 3.0:
+        time.sleep(0.05)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(a.steps)]
     l0 = eng.launch_count
     torch.cuda.synchronize()

@@ -364,8 +364,8 @@ extern "C" int fdts_set_option(fdts_handle e, const char *key, int64_t value) {
     return 0;
   }
   if (!strcmp(key, "threads")) {
-    if (value != 256 && value != 384 && value != 512 && value != 768 && value != 1024) {
-      fdts_set_error("threads must be 256, 384, 512, 768 or 1024");
+    if (value != 512 && value != 1024) {
+      fdts_set_error("threads must be 512 or 1024");
       return 1;
     }
     e->opt_threads = value;

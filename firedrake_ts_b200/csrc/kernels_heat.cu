@@ -1172,9 +1172,6 @@ int launch_gather2_nt(G2Args a, const GatherPlan2 &p, cudaStream_t s) {
 template <int DIM, int DEG, int VAR>
 int launch_gather2(G2Args a, const GatherPlan2 &p, int threads, cudaStream_t s) {
   if (threads == 512) return launch_gather2_nt<DIM, DEG, VAR, 512>(a, p, s);
-  if (threads == 768) return launch_gather2_nt<DIM, DEG, VAR, 768>(a, p, s);
-  if (threads == 384) return launch_gather2_nt<DIM, DEG, VAR, 384>(a, p, s);
-  if (threads == 256) return launch_gather2_nt<DIM, DEG, VAR, 256>(a, p, s);
   return launch_gather2_nt<DIM, DEG, VAR, 1024>(a, p, s);
 }
 

@@ -114,7 +114,7 @@ int fdts_set_cell_tiles(fdts_handle h, const int64_t *starts_host, int64_t ntile
  * schedule options (set before fdts_set_row_blocks; they never change a value beyond rounding):
  *   "plan_version" 2 (default: sector-grouped SELL + pattern dictionary) | 1 (windowed SELL, residual lists)
  *   "dedup" 1|0 share identical block tables; "optimize" 1|0 bank-conflict-aware ordering of the shared tables
- *   "sector" 4|2|1 CSR slots per store group; "threads" 256|384|512|768|1024 per persistent CTA
+ *   "sector" 4|2|1 CSR slots per store group; "threads" 512|1024 per persistent CTA
  *   "overlap" 0|1 warp-specialised Jacobian kernel; "residual_tiles" 1|0 use the tile plan when one exists
  *   "gather_residual" 0|1 (plan 1); "persist" 1|0 (plan 1)
  * read-only: "plan_cells_max", "plan_contributions", "plan_blocks", "plan_version", "plan_patterns",

@@ -108,7 +108,7 @@ def test_pattern_dictionary(n, ftile):
     # bank-conflict-aware column order, 16/8-byte store groups, CTA sizes and the warp-specialised
     # (overlapped) kernel only change the summation order / the schedule, never a value beyond rounding
     for opts in ({"optimize": 1}, {"optimize": 1, "sector": 2}, {"optimize": 0, "sector": 2}, {"sector": 1},
-                 {"threads": 1024}, {"threads": 256}, {"overlap": 1}, {"overlap": 1, "sector": 2}):
+                 {"threads": 1024}, {"overlap": 1}, {"overlap": 1, "sector": 2}):
         e2 = Engine(form, bcs, device="cuda:0", scatter=2, plan_version=2, dedup=1, options=opts)
         J2 = e2.ijacobian(0.0, x, xd, 10.0)
         assert rel_err(J2.cpu().numpy(), J0.cpu().numpy()) < TOL
