@@ -9,8 +9,9 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["fdts_api.cu", "pattern.cu", "inst_heat.cu", "inst_bbm.cu", "inst_burgers.cu", "inst_ch.cu",
-           "kernels_heat.cu", "microbench.cu", "linalg.cu", "gather_plan.cu", "kernels_dmma.cu"]
-HEADERS = ["fdts_common.cuh", "kernels_generic.cuh", "kargs.cuh", "ref_tables.cuh", "../../include/fdts.h"]
+           "kernels_heat.cu", "kernels_heat2.cu", "microbench.cu", "linalg.cu", "gather_plan.cu", "kernels_dmma.cu"]
+HEADERS = ["fdts_common.cuh", "kernels_generic.cuh", "kargs.cuh", "ref_tables.cuh", "heat_common.cuh",
+           "../../include/fdts.h"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -8,161 +8,13 @@
 // constants (ref_tables.cuh), fully unrolled into DFMA immediates with their
 // zeros dropped.  Two scatter strategies share this element kernel:
 //   path 1  one thread per cell, `red.global.add.f64` into Vec / CSR (atomic)
-//   path 2  owner-computes gather (deterministic, write-once), see heat_gather.cuh
-#include <algorithm>
-#include <type_traits>
-#include <utility>
+//   path 2  owner-computes gather (deterministic, write-once): plan 1 and the two-phase plan-2 kernel here,
+//           the warp-specialised variant and the residual tile kernels in kernels_heat2.cu
+#include <vector>
 
-#include "kargs.cuh"
-#include "ref_tables.cuh"
+#include "heat_common.cuh"
 
 namespace {
-
-template <class F, int... Is>
-__device__ __forceinline__ void static_for_impl(F &&f, std::integer_sequence<int, Is...>) {
-  (f(std::integral_constant<int, Is>{}), ...);
-}
-template <int N, class F>
-__device__ __forceinline__ void static_for(F &&f) {
-  static_for_impl(f, std::make_integer_sequence<int, N>{});
-}
-
-// g[p] = |detJ| * (Jinv Jinv^T)_{ab} for the pairs a<=b in the order of RefT::S
-template <int DIM>
-__device__ __forceinline__ void metric(const Geom<DIM> &g, double (&gm)[DIM * (DIM + 1) / 2]) {
-  int p = 0;
-#pragma unroll
-  for (int a = 0; a < DIM; ++a)
-#pragma unroll
-    for (int b = a; b < DIM; ++b) {
-      double t = 0.0;
-#pragma unroll
-      for (int k = 0; k < DIM; ++k) t += g.Jinv[a][k] * g.Jinv[b][k];
-      gm[p++] = t * g.adet;
-    }
-}
-
-template <class T, int I, int J, int NP>
-__device__ __forceinline__ double heat_entry(double m, const double (&gm)[NP]) {
-  double v = 0.0;
-  constexpr double r = T::R00[I][J];
-  if constexpr (r != 0.0) v = m * r;
-  static_for<NP>([&](auto P) {
-    constexpr int p = decltype(P)::value;
-    constexpr double s = T::S[p][I][J];
-    if constexpr (s != 0.0) v = fma(gm[p], s, v);
-  });
-  return v;
-}
-
-// Sum-factorised element residual of the heat form on a P2 tetrahedron (local node order of fem.py:
-// vertices 0-3, then edges (2,3) (1,3) (1,2) (0,3) (0,2) (0,1)).  Same result as the table form
-//   f_i = adet * sum_j R00_ij ud_j + sum_p gm_p sum_j S_pij u_j - p0 M0_i adet
-// in ~230 instead of ~460 fp64 operations and fewer live registers:
-//  * grad u is linear on the cell, so it is represented by its values at the 4 vertices
-//    (d_a^v = 3 u_a if a == v else 4 u_(a,v) - u_a in barycentric components), mapped through the metric
-//    (q = G grad u, 36 FMA) and tested with the (equally linear) basis gradients via the P1 mass matrix
-//    int lambda_v lambda_w = (1 + delta_vw) / 120;
-//  * the P2 mass matrix 1/2520 [6,1 | -4,-6 | 32,16,8] is applied through vertex / edge sums.
-__device__ __forceinline__ void p2tet_heat_residual(const double (&gm)[6], double adet, double p0, const double (&u)[10],
-                                                    const double (&ud)[10], double (&f)[10]) {
-  constexpr int E[4][4] = {{-1, 9, 8, 7}, {9, -1, 6, 5}, {8, 6, -1, 4}, {7, 5, 4, -1}};  // edge node of (a, b)
-  double d[4][4];  // d[a][v]: barycentric derivative a of u at vertex v
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int v = 0; v < 4; ++v) d[a][v] = a == v ? 3.0 * u[a] : fma(4.0, u[E[a][v]], -u[a]);
-  const double s120 = 1.0 / 120.0;
-  const double G[3][3] = {{gm[0] * s120, gm[1] * s120, gm[2] * s120},
-                          {gm[1] * s120, gm[3] * s120, gm[4] * s120},
-                          {gm[2] * s120, gm[4] * s120, gm[5] * s120}};
-  double Q[3][4], SQ[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    double q[4], sq = 0.0;
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      double t = 0.0;
-#pragma unroll
-      for (int e = 0; e < 3; ++e) t = fma(G[c][e], d[e + 1][v] - d[0][v], t);
-      q[v] = t;
-      sq += t;
-    }
-    SQ[c] = 0.0;
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      Q[c][v] = q[v] + sq;
-      SQ[c] += Q[c][v];
-    }
-  }
-  f[0] = -(fma(4.0, Q[0][0], -SQ[0]) + fma(4.0, Q[1][0], -SQ[1]) + fma(4.0, Q[2][0], -SQ[2]));
-#pragma unroll
-  for (int a = 1; a < 4; ++a) f[a] = fma(4.0, Q[a - 1][a], -SQ[a - 1]);
-#pragma unroll
-  for (int a = 1; a < 4; ++a)
-#pragma unroll
-    for (int b = a + 1; b < 4; ++b) f[E[a][b]] = 4.0 * (Q[a - 1][b] + Q[b - 1][a]);
-#pragma unroll
-  for (int a = 1; a < 4; ++a) f[E[0][a]] = 4.0 * (Q[a - 1][0] - (Q[0][a] + Q[1][a] + Q[2][a]));
-  const double SV = (ud[0] + ud[1]) + (ud[2] + ud[3]);
-  const double SE = ((ud[4] + ud[5]) + (ud[6] + ud[7])) + (ud[8] + ud[9]);
-  const double ms = adet * (1.0 / 2520.0);
-  const double cv = fma(-6.0, SE, SV), ce = fma(16.0, SE, -6.0 * SV);
-  const double src_v = p0 * adet * (1.0 / 120.0), src_e = -p0 * adet * (1.0 / 30.0);  // -p0 * M0_i * adet
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    double adj = 0.0;
-#pragma unroll
-    for (int b = 0; b < 4; ++b)
-      if (b != a) adj += ud[E[a][b]];
-    f[a] += fma(fma(5.0, ud[a], fma(2.0, adj, cv)), ms, src_v);
-  }
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = a + 1; b < 4; ++b) {
-      int c = -1, dd = -1;  // opposite edge = the other two vertices
-#pragma unroll
-      for (int v = 0; v < 4; ++v)
-        if (v != a && v != b) {
-          if (c < 0) c = v; else dd = v;
-        }
-      const int e = E[a][b];
-      f[e] += fma(fma(16.0, ud[e], fma(-8.0, ud[E[c][dd]], fma(2.0, ud[a] + ud[b], ce))), ms, src_e);
-    }
-}
-
-// element residual of one cell, table form or (P2 tetrahedra) sum-factorised
-template <int DIM, int DEG, int VAR, int ND, int NP>
-__device__ __forceinline__ void heat_element_residual(const double (&gm)[NP], double adet, double p0, const double (&u)[ND],
-                                                      const double (&ud)[ND], double (&f)[ND]) {
-  using T = RefT<DIM, DEG, VAR>;
-  if constexpr (DIM == 3 && DEG == 2) {
-    p2tet_heat_residual(gm, adet, p0, u, ud, f);
-  } else {
-    static_for<ND>([&](auto I) {
-      constexpr int i = decltype(I)::value;
-      double mass = -p0 * T::M0[i];
-      static_for<ND>([&](auto J) {
-        constexpr int j = decltype(J)::value;
-        constexpr double r = T::R00[i][j];
-        if constexpr (r != 0.0) mass = fma(r, ud[j], mass);
-      });
-      double fi = mass * adet;
-      static_for<NP>([&](auto P) {
-        constexpr int p = decltype(P)::value;
-        double sacc = 0.0;
-        static_for<ND>([&](auto J) {
-          constexpr int j = decltype(J)::value;
-          constexpr double sv = T::S[p][i][j];
-          if constexpr (sv != 0.0) sacc = fma(sv, u[j], sacc);
-        });
-        fi = fma(gm[p], sacc, fi);
-      });
-      f[i] = fi;
-    });
-  }
-}
 
 // ------------------------------------------------------------------ path 1: atomic
 template <int DIM, int DEG, int VAR>
@@ -557,146 +409,6 @@ int launch_gather(int which, GArgs a, const GatherPlan &p, cudaStream_t s) {
 // (addresses, slice table, sector ids) while phase A computes, phase-A tables (vertex coordinates,
 // per-cell local vertex ids) of the next block while phase B sweeps.  With the pattern dictionary the
 // index tables of a structured mesh are a few hundred KB in total and stay L2 resident.
-struct G2Args {
-  const BlockDesc2 *bdesc;
-  const uint16_t *cidx, *gdst;
-  const uint2 *cmeta;
-  const uint32_t *bcc;
-  const double *bvcoords;
-  double *out;
-  int64_t nblocks;
-  double shift;
-  int32_t off_idx, off_meta, off_gdst, off_vtab, off_lcc, off_bar, off_desc, zaddr, sector, inA_bytes, stage_bytes;
-  int32_t dbg;  // development only: bit0 skips phase A, bit1 skips phase B (timing experiments; results are wrong)
-};
-
-__device__ __forceinline__ double lds_f64(uint32_t addr) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
-  uint16_t v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
-  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
-}
-
-// loads the W 16-bit staging addresses of one slot (two per 32-bit word); ip = shared address of the
-// lane's first word
-template <int W>
-__device__ __forceinline__ void load_pairs(uint32_t ip, uint32_t (&pr)[(W + 1) / 2]) {
-#pragma unroll
-  for (int q = 0; q < (W + 1) / 2; ++q) pr[q] = lds_u32(ip + q * 128);
-}
-
-// sums the W staged contributions addressed by pr (units of 8 bytes from sbase)
-template <int W>
-__device__ __forceinline__ double sum_pairs(const uint32_t (&pr)[(W + 1) / 2], uint32_t sbase) {
-  double v[W];
-#pragma unroll
-  for (int k = 0; k < W; ++k)
-    v[k] = lds_f64(__byte_perm(pr[k >> 1], 0u, (k & 1) ? 0x4432u : 0x4410u) * 8u + sbase);
-  if constexpr (W == 1) return v[0];
-  double a0 = v[0], a1 = v[1];
-#pragma unroll
-  for (int k = 2; k < W; ++k) {
-    if (k & 1) a1 += v[k]; else a0 += v[k];
-  }
-  return a0 + a1;
-}
-
-// element-matrix entry from the integer form of the reference tensors (ref_tables.cuh):
-//   A_ij = ms * IR_ij + sum_p gs_p * IS_pij,   ms = shift |detJ| / RDEN,  gs_p = |detJ| G_p / SDEN.
-// The handful of distinct integer multipliers stay in uniform registers; the plain tables would cost one
-// 64-bit immediate (two UMOVs) per use.
-template <class T, int I, int J, int NP>
-__device__ __forceinline__ double heat_entry_i(double ms, const double (&gs)[NP]) {
-  double v = 0.0;
-  constexpr int r = T::IR[I][J];
-  if constexpr (r != 0) v = ms * (double)r;
-  static_for<NP>([&](auto P) {
-    constexpr int p = decltype(P)::value;
-    constexpr int c = T::IS[p][I][J];
-    if constexpr (c != 0) v = fma(gs[p], (double)c, v);
-  });
-  return v;
-}
-
-// slices are dealt round-robin over the whole block (slice s -> warp s mod NWARPS): index inside the
-// class of the first slice that belongs to `warp`
-template <int NWARPS>
-__device__ __forceinline__ uint32_t first_slice_of(int warp, uint32_t first) {
-  if constexpr ((NWARPS & (NWARPS - 1)) == 0) return (uint32_t)(warp - (int)first) & (NWARPS - 1);
-  const int r = (warp - (int)(first % NWARPS)) % NWARPS;
-  return (uint32_t)(r < 0 ? r + NWARPS : r);
-}
-
-// one class of slices (equal width W, equal split flag): warp `warp` takes the slices congruent to it
-template <int W, int G, int NWARPS, bool PIPE = true>
-__device__ __forceinline__ void sweep_class(uint32_t first, uint32_t count, uint32_t off64, bool split, int warp, int lane,
-                                            uint32_t idx0, uint32_t gd0, uint32_t sbase, double *__restrict__ out,
-                                            uint32_t lo, uint32_t span) {
-  constexpr int LG = G == 4 ? 2 : (G == 2 ? 1 : 0), PER_NORM = 32 / G, PAIRS = (W + 1) / 2;
-  uint32_t i = first_slice_of<NWARPS>(warp, first);
-  const uint32_t gsel = split ? (uint32_t)(lane >> (LG + 2)) : (uint32_t)(lane >> LG);
-  const uint32_t sub = split ? (uint32_t)((lane >> 2) & (G - 1)) : (uint32_t)(lane & (G - 1));
-  const bool wr = split ? (lane & 3) == 0 : true;
-  uint32_t ip = idx0 + (off64 + i * PAIRS) * 128u;
-  uint32_t gd = gd0 + ((first + i) * PER_NORM + gsel) * 2u;
-  if (i >= count) return;
-  if constexpr (!PIPE) {  // plain loop (fits 64 registers: used when the CTA runs 32 warps)
-    for (; i < count; i += NWARPS, ip += NWARPS * PAIRS * 128u, gd += NWARPS * PER_NORM * 2u) {
-      uint32_t pr[PAIRS];
-      load_pairs<W>(ip, pr);
-      const uint32_t gs = lds_u16(gd);
-      double acc = sum_pairs<W>(pr, sbase);
-      if (split) {
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      }
-      const uint32_t slot = gs * G + sub;
-      if (wr && slot - lo < span) out[slot] = acc;
-    }
-    return;
-  }
-  // software pipeline: the addresses and the sector id of the warp's next slice are fetched while the
-  // current slice is summed
-  uint32_t pr[PAIRS];
-  load_pairs<W>(ip, pr);
-  uint32_t gs = lds_u16(gd);
-  for (;;) {
-    const uint32_t in = i + NWARPS;
-    const bool has_next = in < count;
-    uint32_t prn[PAIRS], gsn = 0;
-    ip += NWARPS * PAIRS * 128u;
-    gd += NWARPS * PER_NORM * 2u;
-    if (has_next) {
-      load_pairs<W>(ip, prn);
-      gsn = lds_u16(gd);
-    }
-    double acc = sum_pairs<W>(pr, sbase);
-    if (split) {
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    }
-    const uint32_t slot = gs * G + sub;  // sector id 0xffff (none) lands far outside [lo, lo + span)
-    if (wr && slot - lo < span) out[slot] = acc;
-    if (!has_next) break;
-#pragma unroll
-    for (int q = 0; q < PAIRS; ++q) pr[q] = prn[q];
-    gs = gsn;
-    i = in;
-  }
-}
-
 template <int DIM, int DEG, int VAR, int NT, int G>
 __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) heat_jacobian_gather2(const G2Args a) {
   using T = RefT<DIM, DEG, VAR>;
@@ -868,264 +580,6 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) heat_jacobian_gather2(c
   }
 }
 
-// ------------------------------------------------------------------ path 2, plan 2, warp-specialised
-// Same plan, same arithmetic, same summation order as heat_jacobian_gather2, but the two phases run
-// concurrently on different warps of one persistent CTA with two staging buffers:
-//   NPW producer warps   element matrices of block b+1 -> stage[(b+1)&1]        (fp64 pipe)
-//   NCW consumer warps   gather/sum/store of block b from stage[b&1]            (shared-memory pipe)
-//   1 copy warp          lane 0 issues every TMA bulk copy and fetches the block descriptors
-// Hand-over through mbarriers: full[s] (producers -> consumers), empty[s] (consumers -> producers),
-// inA[s] (copy warp -> producers); no CTA-wide barrier after the prologue.  The index tables of the
-// resident pattern are only reloaded (by the consumers themselves) when the pattern changes.
-template <int DIM, int DEG, int VAR, int NPW, int NCW, int G>
-__global__ void __launch_bounds__((NPW + NCW + 1) * 32, 1) heat_jacobian_gather3(const G2Args a) {
-  using T = RefT<DIM, DEG, VAR>;
-  constexpr int ND = T::ND, NP = T::NP, NEP = (ND * (ND + 1) / 2) | 1;
-  constexpr int PER_NORM = 32 / G;
-  constexpr int NDESC = 8;
-  extern __shared__ __align__(16) unsigned char smraw[];
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smraw + a.off_bar);
-  constexpr int NA = 4;  // ring of phase-A input buffers: copies run three blocks ahead of the producers
-  uint64_t *inA = bars, *freeA = bars + NA, *full = bars + 2 * NA, *empty = bars + 2 * NA + 2, *barB = bars + 2 * NA + 4;
-  BlockDesc2 *sdesc = reinterpret_cast<BlockDesc2 *>(smraw + a.off_desc);  // ring of NDESC blocks
-  const uint32_t sbase = smem_u32(smraw);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t stride = gridDim.x;
-  const int64_t b0 = blockIdx.x;
-  if (b0 >= a.nblocks) return;
-  const int64_t nmine = (a.nblocks - b0 + stride - 1) / stride;  // blocks of this CTA
-
-  auto issue_A = [&](const BlockDesc2 &d, int buf) {
-    const uint32_t vb = (uint32_t)(((d.nvert * DIM + 1) & ~1) * 8);
-    const uint32_t cb = (uint32_t)(((d.ncell + 3) & ~3) * 4);
-    mbar_expect_tx(&inA[buf], vb + cb);
-    if (vb) bulk_g2s(smraw + a.off_vtab + buf * a.inA_bytes, a.bvcoords + d.vc_off, vb, &inA[buf]);
-    if (cb) bulk_g2s(smraw + a.off_lcc + buf * a.inA_bytes, a.bcc + d.cc_off, cb, &inA[buf]);
-  };
-
-  // ---- prologue (the only CTA-wide barrier)
-  if (threadIdx.x == 0) {
-    for (int q = 0; q < NA; ++q) {
-      mbar_init(&inA[q], 1);
-      mbar_init(&freeA[q], NPW);
-    }
-    mbar_init(&full[0], NPW);
-    mbar_init(&full[1], NPW);
-    mbar_init(&empty[0], NCW);
-    mbar_init(&empty[1], NCW);
-    mbar_init(barB, 1);
-    for (int q = 0; q < NA && q < nmine; ++q) {
-      sdesc[q] = a.bdesc[b0 + q * stride];
-      if (q < NA - 1) issue_A(sdesc[q], q);
-    }
-  }
-  if (threadIdx.x < 32) {  // one staged zero per 8-byte bank, in both staging buffers
-    const int q = threadIdx.x & 15, buf = threadIdx.x >> 4;
-    sts_f64(sbase + buf * a.stage_bytes + (a.zaddr + q) * 8, 0.0);
-  }
-  __syncthreads();
-
-  if (warp == NPW + NCW) {
-    // ================= copy warp
-    if (lane == 0) {
-      for (int64_t it = 0; it < nmine; ++it) {
-        // the phase-A inputs of block it+NA-1 reuse the buffer of block it-1: wait until the producers have
-        // released it (freeA cannot run ahead of this wait: its next phase needs the refill issued here);
-        // the copy is issued first, the (slow, dependent) descriptor fetch for block it+NA afterwards
-        if (it >= 1) mbar_wait(&freeA[(it - 1) % NA], (uint32_t)(((it - 1) / NA) & 1));
-        if (it + NA - 1 < nmine) issue_A(sdesc[(it + NA - 1) % NDESC], (int)((it + NA - 1) % NA));
-        if (it + NA < nmine) sdesc[(it + NA) % NDESC] = a.bdesc[b0 + (it + NA) * stride];
-      }
-    }
-  } else if (warp < NPW) {
-    // ================= producers: element matrices
-    const int tid = threadIdx.x;  // 0 .. NPW*32-1
-    for (int64_t it = 0; it < nmine; ++it) {
-      const int s = (int)(it & 1);
-      if (it >= 2) mbar_wait(&empty[s], (uint32_t)((((it >> 1) - 1)) & 1));
-      const int qa = (int)(it % NA);
-      mbar_wait(&inA[qa], (uint32_t)((it / NA) & 1));
-      const BlockDesc2 &d = sdesc[it % NDESC];
-      const int ncell = (a.dbg & 1) ? 0 : d.ncell;
-      const uint32_t lcc0 = sbase + a.off_lcc + qa * a.inA_bytes, vt0 = sbase + a.off_vtab + qa * a.inA_bytes;
-      const uint32_t stb = sbase + s * a.stage_bytes;
-      for (int k = tid; k < ncell; k += NPW * 32) {
-        const uint32_t packed = lds_u32(lcc0 + k * 4);
-        double X[DIM + 1][DIM];
-#pragma unroll
-        for (int v = 0; v <= DIM; ++v) {
-          const uint32_t va = vt0 + ((packed >> (8 * v)) & 255u) * (DIM * 8);
-#pragma unroll
-          for (int q = 0; q < DIM; ++q) X[v][q] = lds_f64(va + q * 8);
-        }
-        Geom<DIM> g;
-        geometry_from_vertices<DIM>(X, g);
-        double gm[NP];
-        metric<DIM>(g, gm);
-        const uint32_t st = stb + k * (NEP * 8);
-        if constexpr (T::INT) {
-          const double ms = a.shift * g.adet * (1.0 / T::RDEN);
-#pragma unroll
-          for (int p = 0; p < NP; ++p) gm[p] *= (1.0 / T::SDEN);
-          static_for<ND>([&](auto I) {
-            constexpr int i = decltype(I)::value;
-            static_for<ND - i>([&](auto JJ) {
-              constexpr int j = i + decltype(JJ)::value;
-              constexpr int e = i * ND - (i * (i - 1)) / 2 + (j - i);
-              sts_f64(st + e * 8, heat_entry_i<T, i, j, NP>(ms, gm));
-            });
-          });
-        } else {
-          const double m = a.shift * g.adet;
-          static_for<ND>([&](auto I) {
-            constexpr int i = decltype(I)::value;
-            static_for<ND - i>([&](auto JJ) {
-              constexpr int j = i + decltype(JJ)::value;
-              constexpr int e = i * ND - (i * (i - 1)) / 2 + (j - i);
-              sts_f64(st + e * 8, heat_entry<T, i, j, NP>(m, gm));
-            });
-          });
-        }
-      }
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&freeA[qa]);
-        mbar_arrive(&full[s]);
-      }
-    }
-  } else {
-    // ================= consumers: gather, sum, store
-    const int cw = warp - NPW;  // consumer warp id
-    const uint32_t idx0 = sbase + a.off_idx + lane * 4;
-    const uint32_t gd0 = sbase + a.off_gdst;
-    const uint32_t cls0 = sbase + a.off_meta;
-    int resident = -1;
-    uint32_t nloadB = 0;
-    for (int64_t it = 0; it < nmine; ++it) {
-      const int s = (int)(it & 1);
-      mbar_wait(&full[s], (uint32_t)((it >> 1) & 1));  // also orders the descriptor written by the copy warp
-      const BlockDesc2 &d = sdesc[it % NDESC];
-      const int pattern = d.pattern;
-      if (pattern != resident) {
-        // all consumers are done with the old tables (named barrier), then one of them reloads
-        asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");
-        if (cw == 0 && lane == 0) {
-          const uint32_t nslp = (uint32_t)((d.nsl + 3) & ~3);
-          const uint32_t ib = (uint32_t)d.nidx * 2u, mb = (uint32_t)((d.ncls + 1) & ~1) * 8u, gb = nslp * 2u * (uint32_t)PER_NORM;
-          mbar_expect_tx(barB, ib + mb + gb);
-          if (ib) bulk_g2s(smraw + a.off_idx, a.cidx + d.idx_off, ib, barB);
-          if (mb) bulk_g2s(smraw + a.off_meta, a.cmeta + d.cls_off, mb, barB);
-          if (gb) bulk_g2s(smraw + a.off_gdst, a.gdst + d.meta_off * PER_NORM, gb, barB);
-        }
-        mbar_wait(barB, nloadB & 1u);
-        ++nloadB;
-        resident = pattern;
-      }
-      const uint32_t lo = (uint32_t)(d.s0 & (G - 1)), span = (a.dbg & 8) ? 0u : (uint32_t)d.nslots;
-      double *__restrict__ out = a.out + (d.s0 - lo);
-      const uint32_t stb = sbase + s * a.stage_bytes;
-      const int ncls = (a.dbg & 2) ? 0 : d.ncls;
-      for (int c = 0; c < ncls; ++c) {
-        uint32_t c0, c1;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(c0), "=r"(c1) : "r"(cls0 + c * 8));
-        const uint32_t first = c0 & 0xffffu, count = c0 >> 16, off64 = c1 & 0xffffu, w = (c1 >> 16) & 0xffu;
-        const bool split = c1 >= 0x1000000u;
-#define SWEEP(W) sweep_class<W, G, NCW, (NCW <= 16)>(first, count, off64, split, cw, lane, idx0, gd0, stb, out, lo, span)
-        switch (w) {
-          case 0: {  // slots without contributions (Dirichlet rows/columns): write zeros
-            constexpr int LG = G == 4 ? 2 : (G == 2 ? 1 : 0);
-            for (uint32_t i = first_slice_of<NCW>(cw, first); i < count; i += NCW) {
-              const uint32_t gs = lds_u16(gd0 + ((first + i) * PER_NORM + (split ? (lane >> (LG + 2)) : (lane >> LG))) * 2u);
-              const uint32_t slot = gs * G + (split ? ((lane >> 2) & (G - 1)) : (lane & (G - 1)));
-              if ((!split || (lane & 3) == 0) && slot - lo < span) out[slot] = 0.0;
-            }
-            break;
-          }
-          case 1: SWEEP(1); break;
-          case 2: SWEEP(2); break;
-          case 3: SWEEP(3); break;
-          case 4: SWEEP(4); break;
-          case 5: SWEEP(5); break;
-          case 6: SWEEP(6); break;
-          case 7: SWEEP(7); break;
-          case 8: SWEEP(8); break;
-          default: {  // wider classes (high-valence vertices of unstructured meshes): generic loop
-            constexpr int LG = G == 4 ? 2 : (G == 2 ? 1 : 0);
-            const uint32_t pairs = (w + 1) >> 1;
-            for (uint32_t i = first_slice_of<NCW>(cw, first); i < count; i += NCW) {
-              const uint32_t ip = idx0 + (off64 + i * pairs) * 128u;
-              const uint32_t gs = lds_u16(gd0 + ((first + i) * PER_NORM + (split ? (lane >> (LG + 2)) : (lane >> LG))) * 2u);
-              double a0 = 0.0, a1 = 0.0;
-              for (uint32_t q = 0; q < pairs; ++q) {
-                const uint32_t pr = lds_u32(ip + q * 128);
-                a0 += lds_f64(stb + (pr & 0xffffu) * 8u);
-                if (2 * q + 1 < w) a1 += lds_f64(stb + (pr >> 16) * 8u);
-              }
-              double acc = a0 + a1;
-              if (split) {
-                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-              }
-              const uint32_t slot = gs * G + (split ? ((lane >> 2) & (G - 1)) : (lane & (G - 1)));
-              if ((!split || (lane & 3) == 0) && slot - lo < span) out[slot] = acc;
-            }
-          }
-        }
-#undef SWEEP
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
-    }
-  }
-}
-
-// shared-memory layout of the warp-specialised kernel; returns the total size (0: does not fit)
-template <int DIM>
-size_t layout_gather3(G2Args &a, const GatherPlan2 &p) {
-  auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
-  a.stage_bytes = (int)up16(sizeof(double) * ((size_t)p.zaddr + 16));
-  size_t off = 2 * (size_t)a.stage_bytes;
-  a.off_idx = (int)off;
-  off += up16(2 * (size_t)p.max_nidx + 64);
-  a.off_meta = (int)off;
-  off += up16(8 * (size_t)PLAN2_MAX_CLASSES + 16);
-  a.off_gdst = (int)off;
-  off += up16(2 * (size_t)(32 / p.sector) * (size_t)p.max_nsl + 16);
-  a.sector = p.sector;
-  a.inA_bytes = (int)(up16(8 * (size_t)p.vmax * DIM + 16) + up16(4 * (size_t)p.cmax + 16));
-  a.off_vtab = (int)off;
-  a.off_lcc = (int)(off + up16(8 * (size_t)p.vmax * DIM + 16));
-  off += 4 * (size_t)a.inA_bytes;
-  a.off_bar = (int)off;
-  off += 128;
-  a.off_desc = (int)off;
-  off += 8 * sizeof(BlockDesc2);
-  a.zaddr = p.zaddr;
-  return off <= 227 * 1024 ? off : 0;
-}
-
-template <int DIM, int DEG, int VAR>
-int launch_gather3(G2Args a, const GatherPlan2 &p, cudaStream_t s) {
-  using T = RefT<DIM, DEG, VAR>;
-  constexpr int ND = T::ND, NEP = (ND * (ND + 1) / 2) | 1;
-  constexpr int NPW = 6, NCW = 25;  // 192 cells per pass of the producers; 32 warps, 64 registers each
-  if (p.nep != NEP) return 3;
-  const size_t smem = layout_gather3<DIM>(a, p);
-  if (smem == 0) return 4;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t grid = p.nblocks < sms ? p.nblocks : sms;
-  auto launch = [&](auto kern) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
-    kern<<<(unsigned)grid, (NPW + NCW + 1) * 32, smem, s>>>(a);
-    return cudaGetLastError() == cudaSuccess ? 0 : 2;
-  };
-  if (p.sector == 4) return launch(heat_jacobian_gather3<DIM, DEG, VAR, NPW, NCW, 4>);
-  if (p.sector == 2) return launch(heat_jacobian_gather3<DIM, DEG, VAR, NPW, NCW, 2>);
-  return launch(heat_jacobian_gather3<DIM, DEG, VAR, NPW, NCW, 1>);
-}
-
 template <int DIM, int DEG, int VAR, int NT>
 int launch_gather2_nt(G2Args a, const GatherPlan2 &p, cudaStream_t s) {
   using T = RefT<DIM, DEG, VAR>;
@@ -1173,249 +627,6 @@ template <int DIM, int DEG, int VAR>
 int launch_gather2(G2Args a, const GatherPlan2 &p, int threads, cudaStream_t s) {
   if (threads == 512) return launch_gather2_nt<DIM, DEG, VAR, 512>(a, p, s);
   return launch_gather2_nt<DIM, DEG, VAR, 1024>(a, p, s);
-}
-
-// ------------------------------------------------------------------ residual, tile plan
-// One CTA per cell tile (gather_plan.cu: residual tile plan).  The tile's node values and vertex
-// coordinates come in with coalesced loads and live in shared memory, every thread computes the element
-// vector of one cell (closed form), the vectors are pre-reduced per unique node of the tile through
-// SELL lists (lane = node) and ONE `red.global.add.f64` per (tile, node) goes out -- 5x fewer atomics and
-// no scattered 8-byte gathers of u, udot and the coordinates (the per-cell atomic kernel is bound by
-// exactly those: 776 M L1 sector requests per call, ncu l1tex 69 % of peak).
-#ifndef RT_MINB
-#define RT_MINB 4
-#endif
-struct RTArgs {
-  const BlockDesc2 *tdesc;
-  const uint16_t *cidx, *gdst, *tlid;
-  const uint2 *cmeta;
-  const uint32_t *bcc;
-  const int32_t *tnode;
-  const double *bvcoords, *x, *xdot;
-  double *out;
-  const int64_t *tstart;        // direct variant: first cell of every tile, maps, coordinates
-  const int32_t *cell_node_t, *cell_coord_t;
-  const double *coords;
-  int64_t nc;
-  int64_t t0;  // first tile of this launch
-  int32_t direct;
-  double p0;
-  int32_t cmaxp, umaxp, ndp, zaddr, off_su, off_sud, off_vtab;
-};
-
-template <int DIM, int DEG, int VAR, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) heat_residual_tiles(const RTArgs a) {
-  using T = RefT<DIM, DEG, VAR>;
-  constexpr int ND = T::ND, NP = T::NP, NDP = ND | 1, NWARPS = NT / 32;
-  extern __shared__ __align__(16) unsigned char smraw[];
-  double *stage = reinterpret_cast<double *>(smraw);
-  double *su = reinterpret_cast<double *>(smraw + a.off_su);
-  double *sud = reinterpret_cast<double *>(smraw + a.off_sud);
-  double *vtab = reinterpret_cast<double *>(smraw + a.off_vtab);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t t = a.t0 + blockIdx.x;
-  const BlockDesc2 d = a.tdesc[t];
-  const int64_t pat = d.pattern;
-  const int32_t *__restrict__ tn = a.tnode + pat * a.umaxp;
-  // ---- stage node values and vertex coordinates
-  for (int q = threadIdx.x; q < d.nslots; q += NT) {
-    const int64_t node = d.s0 + (tn[q] & 0x7fffffff);
-    su[q] = __ldg(a.x + node);
-    sud[q] = __ldg(a.xdot + node);
-  }
-  for (int q = threadIdx.x; q < d.nvert * DIM; q += NT) vtab[q] = __ldg(a.bvcoords + d.vc_off + q);
-  if (threadIdx.x < 16) stage[a.zaddr + threadIdx.x] = 0.0;
-  __syncthreads();
-  // ---- element vectors
-  for (int k = threadIdx.x; k < d.ncell; k += NT) {
-    const uint32_t packed = a.bcc[d.cc_off + k];
-    double X[DIM + 1][DIM];
-#pragma unroll
-    for (int v = 0; v <= DIM; ++v) {
-      const int lv = (packed >> (8 * v)) & 255;
-#pragma unroll
-      for (int q = 0; q < DIM; ++q) X[v][q] = vtab[lv * DIM + q];
-    }
-    Geom<DIM> g;
-    geometry_from_vertices<DIM>(X, g);
-    double gm[NP];
-    metric<DIM>(g, gm);
-    // two passes to keep the register footprint low (4 CTAs per SM): mass with udot, then stiffness with u
-    uint16_t lid[ND];
-#pragma unroll
-    for (int i = 0; i < ND; ++i) lid[i] = a.tlid[(pat * ND + i) * a.cmaxp + k];
-    double *st = stage + k * NDP;
-    {
-      double ud[ND];
-#pragma unroll
-      for (int i = 0; i < ND; ++i) ud[i] = sud[lid[i]];
-      static_for<ND>([&](auto I) {
-        constexpr int i = decltype(I)::value;
-        double mass = -a.p0 * T::M0[i];
-        static_for<ND>([&](auto J) {
-          constexpr int j = decltype(J)::value;
-          constexpr double r = T::R00[i][j];
-          if constexpr (r != 0.0) mass = fma(r, ud[j], mass);
-        });
-        st[i] = mass * g.adet;
-      });
-    }
-    {
-      double u[ND];
-#pragma unroll
-      for (int i = 0; i < ND; ++i) u[i] = su[lid[i]];
-      static_for<ND>([&](auto I) {
-        constexpr int i = decltype(I)::value;
-        double f = st[i];
-        static_for<NP>([&](auto P) {
-          constexpr int p = decltype(P)::value;
-          double sacc = 0.0;
-          static_for<ND>([&](auto J) {
-            constexpr int j = decltype(J)::value;
-            constexpr double sv = T::S[p][i][j];
-            if constexpr (sv != 0.0) sacc = fma(sv, u[j], sacc);
-          });
-          f = fma(gm[p], sacc, f);
-        });
-        st[i] = f;
-      });
-    }
-  }
-  __syncthreads();
-  // ---- per-node sums (SELL sweep, lane = unique node of the tile), one atomic per node
-  const uint16_t *__restrict__ idx = a.cidx + d.idx_off;
-  const uint16_t *__restrict__ gd = a.gdst + d.meta_off * 32;
-  const uint2 *__restrict__ cls = a.cmeta + d.cls_off;
-  for (int c = 0; c < d.ncls; ++c) {
-    const uint2 ce = cls[c];
-    const int first = (int)(ce.x & 0xffffu), count = (int)(ce.x >> 16), w = (int)((ce.y >> 16) & 0xffu);
-    const bool split = (ce.y >> 24) != 0;
-    const uint32_t pairs = (uint32_t)((w + 1) >> 1);
-    for (int i = first_slice_of<NWARPS>(warp, (uint32_t)first); i < count; i += NWARPS) {
-      const uint32_t *ip = reinterpret_cast<const uint32_t *>(idx) + ((size_t)(ce.y & 0xffffu) + (size_t)i * pairs) * 32 + lane;
-      double a0 = 0.0, a1 = 0.0;
-      for (uint32_t q = 0; q < pairs; ++q) {
-        const uint32_t pr = __ldg(ip + q * 32);
-        a0 += stage[pr & 0xffffu];
-        if (2 * q + 1 < (uint32_t)w) a1 += stage[pr >> 16];
-      }
-      double acc = a0 + a1;
-      int gsel = lane;
-      bool wr = true;
-      if (split) {
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        gsel = lane >> 2;
-        wr = (lane & 3) == 0;
-      }
-      const uint32_t ln = gd[(size_t)(first + i) * 32 + gsel];
-      if (wr && ln != 0xffffu) {
-        const int32_t rel = tn[ln];
-        if (rel >= 0) red_add_f64(a.out + d.s0 + rel, acc);
-      }
-    }
-  }
-}
-
-// variant: the cells gather their inputs directly (like the per-cell kernel: high memory-level
-// parallelism, no staging phase), only the element vectors are staged and pre-reduced per tile
-template <int DIM, int DEG, int VAR, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) heat_residual_tiles_direct(const RTArgs a) {
-  using T = RefT<DIM, DEG, VAR>;
-  constexpr int ND = T::ND, NP = T::NP, NDP = ND | 1, NWARPS = NT / 32;
-  extern __shared__ __align__(16) unsigned char smraw[];
-  double *stage = reinterpret_cast<double *>(smraw);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t t = a.t0 + blockIdx.x;
-  const BlockDesc2 d = a.tdesc[t];
-  const int64_t c0 = a.tstart[t];
-  if (threadIdx.x < 16) stage[a.zaddr + threadIdx.x] = 0.0;
-  for (int k = threadIdx.x; k < d.ncell; k += NT) {
-    const int64_t c = c0 + k;
-    int32_t cc[DIM + 1], nodes[ND];
-#pragma unroll
-    for (int v = 0; v <= DIM; ++v) cc[v] = a.cell_coord_t[v * a.nc + c];
-#pragma unroll
-    for (int i = 0; i < ND; ++i) nodes[i] = a.cell_node_t[i * a.nc + c];
-    Geom<DIM> g;
-    compute_geometry<DIM>(a.coords, cc, g);
-    double gm[NP];
-    metric<DIM>(g, gm);
-    double u[ND], ud[ND], f[ND];
-#pragma unroll
-    for (int i = 0; i < ND; ++i) {
-      u[i] = __ldg(a.x + nodes[i]);
-      ud[i] = __ldg(a.xdot + nodes[i]);
-    }
-    heat_element_residual<DIM, DEG, VAR, ND, NP>(gm, g.adet, a.p0, u, ud, f);
-    double *st = stage + k * NDP;
-#pragma unroll
-    for (int i = 0; i < ND; ++i) st[i] = f[i];
-  }
-  __syncthreads();
-  const int64_t pat = d.pattern;
-  const int32_t *__restrict__ tn = a.tnode + pat * a.umaxp;
-  const uint16_t *__restrict__ idx = a.cidx + d.idx_off;
-  const uint16_t *__restrict__ gd = a.gdst + d.meta_off * 32;
-  const uint2 *__restrict__ cls = a.cmeta + d.cls_off;
-  for (int c = 0; c < d.ncls; ++c) {
-    const uint2 ce = cls[c];
-    const int first = (int)(ce.x & 0xffffu), count = (int)(ce.x >> 16), w = (int)((ce.y >> 16) & 0xffu);
-    const bool split = (ce.y >> 24) != 0;
-    const uint32_t pairs = (uint32_t)((w + 1) >> 1);
-    for (int i = first_slice_of<NWARPS>(warp, (uint32_t)first); i < count; i += NWARPS) {
-      const uint32_t *ip = reinterpret_cast<const uint32_t *>(idx) + ((size_t)(ce.y & 0xffffu) + (size_t)i * pairs) * 32 + lane;
-      double a0 = 0.0, a1 = 0.0;
-      for (uint32_t q = 0; q < pairs; ++q) {
-        const uint32_t pr = __ldg(ip + q * 32);
-        a0 += stage[pr & 0xffffu];
-        if (2 * q + 1 < (uint32_t)w) a1 += stage[pr >> 16];
-      }
-      double acc = a0 + a1;
-      int gsel = lane;
-      bool wr = true;
-      if (split) {
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        gsel = lane >> 2;
-        wr = (lane & 3) == 0;
-      }
-      const uint32_t ln = gd[(size_t)(first + i) * 32 + gsel];
-      if (wr && ln != 0xffffu) {
-        const int32_t rel = tn[ln];
-        if (rel >= 0) red_add_f64(a.out + d.s0 + rel, acc);
-      }
-    }
-  }
-}
-
-template <int DIM, int DEG, int VAR>
-int launch_residual_tiles(RTArgs a, const ResidualPlan &p, int64_t t0, int64_t t1, cudaStream_t s) {
-  using T = RefT<DIM, DEG, VAR>;
-  constexpr int NT = 192;
-  if (p.ndp != (T::ND | 1)) return 3;
-  auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
-  size_t off = up16(sizeof(double) * ((size_t)p.zaddr + 16));
-  a.off_su = (int)off;
-  off += up16(8 * (size_t)p.umaxp);
-  a.off_sud = (int)off;
-  off += up16(8 * (size_t)p.umaxp);
-  a.off_vtab = (int)off;
-  off += up16(8 * (size_t)p.vmax * DIM + 16);
-  const size_t smem = off;
-  if (smem > 227 * 1024) return 4;
-  a.t0 = t0;
-  if (a.direct) {
-    const size_t sm2 = up16(sizeof(double) * ((size_t)p.zaddr + 16));
-    auto k2 = heat_residual_tiles_direct<DIM, DEG, VAR, NT, RT_MINB>;
-    if (sm2 > 48 * 1024 && cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2) != cudaSuccess) return 2;
-    if (t1 > t0) k2<<<(unsigned)(t1 - t0), NT, sm2, s>>>(a);
-    return cudaGetLastError() == cudaSuccess ? 0 : 2;
-  }
-  auto k = heat_residual_tiles<DIM, DEG, VAR, NT, RT_MINB>;
-  if (smem > 48 * 1024 && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
-  if (t1 > t0) k<<<(unsigned)(t1 - t0), NT, smem, s>>>(a);
-  return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 
 __global__ void set_values_k(double *__restrict__ v, const int64_t *__restrict__ slots, int64_t n, double val) {
@@ -1483,7 +694,7 @@ int fdts_launch_heat(fdts_engine *e, int which, const double *x, const double *x
     int rc = 3;
 #define G2CASE(D, K, V)                                                      \
   if (dim == D && deg == K && (K < 3 || var == V)) {                         \
-    rc = e->opt_overlap ? launch_gather3<D, K, V>(g, p, s) : 4;              \
+    rc = e->opt_overlap ? fdts_heat_gather3(D, K, V, g, p, s) : 4;           \
     if (rc == 4) rc = launch_gather2<D, K, V>(g, p, (int)e->opt_threads, s); \
   }
     G2CASE(1, 1, 1) G2CASE(1, 2, 1) G2CASE(1, 3, 0) G2CASE(1, 3, 1)
@@ -1555,12 +766,7 @@ int fdts_launch_heat(fdts_engine *e, int which, const double *x, const double *x
       r.tstart = p.tstart_dev; r.cell_node_t = e->cell_node; r.cell_coord_t = e->cell_coord; r.coords = e->coords;
       r.nc = e->cfg.num_cells; r.direct = e->opt_residual_tiles == 2 ? 1 : 0;
       int rc = 3;
-#define RTCASE(D, K, V) \
-  if (dim == D && deg == K && (K < 3 || var == V)) rc = launch_residual_tiles<D, K, V>(r, p, lo - ts, hi - ts, s);
-      RTCASE(1, 1, 1) RTCASE(1, 2, 1) RTCASE(1, 3, 0) RTCASE(1, 3, 1)
-      RTCASE(2, 1, 1) RTCASE(2, 2, 1) RTCASE(2, 3, 0) RTCASE(2, 3, 1)
-      RTCASE(3, 1, 1) RTCASE(3, 2, 1) RTCASE(3, 3, 0) RTCASE(3, 3, 1)
-#undef RTCASE
+      rc = fdts_heat_residual_tiles(dim, deg, var, r, p, lo - ts, hi - ts, s);
       if (rc == 2) fdts_set_error(std::string("residual tile kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
       if (rc == 3 || rc == 4) fdts_set_error("residual tile kernel: unsupported element or tile too large for shared memory");
       if (rc) return rc;
