@@ -439,6 +439,10 @@ extern "C" int fdts_get_option(fdts_handle e, const char *key, int64_t *value) {
     *value = v2 ? e->plan2.shared_idx : e->plan.total_contrib;
     return 0;
   }
+  if (!strcmp(key, "plan_compacted")) {
+    *value = v2 ? e->plan2.compacted : 0;
+    return 0;
+  }
   if (!strcmp(key, "plan_vertices_max")) {
     *value = v2 ? e->plan2.vmax : e->plan.vmax;
     return 0;

@@ -80,6 +80,7 @@ struct GatherPlan2 {
   BlockDesc2 *bdesc = nullptr;
   int64_t total_idx = 0, unique_patterns = 0, shared_idx = 0;
   int32_t optimized = 0;        // unique patterns went through the bank-conflict-aware column ordering
+  int32_t compacted = 0;        // only the tables of the unique patterns are kept (the duplicates were freed)
 };
 
 // residual tile plan (gather_plan.cu: fdts_build_rplan): cells are cut into contiguous tiles; a CTA

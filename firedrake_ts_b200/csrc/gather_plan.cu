@@ -1399,6 +1399,59 @@ int fdts_build_plan2(fdts_engine *e, const int64_t *starts, int64_t nb) {
         }
         p.optimized = 1;
       }
+      // ---- compaction: keep only the tables of the unique patterns (C4: 12.2 GB built, 0.6 MB referenced)
+      if (uniq * 4 <= nb) {
+        int64_t n_idx = 0, n_sl = 0, n_cc = 0, k = 0;
+        std::vector<int64_t> nidx_of((size_t)nb, -1), nsl_of((size_t)nb, -1), ncc_of((size_t)nb, -1), ncls_of((size_t)nb, -1);
+        for (int64_t b = 0; b < nb; ++b) {
+          if (rep[b] != b) continue;
+          nidx_of[b] = n_idx;
+          nsl_of[b] = n_sl;
+          ncc_of[b] = n_cc;
+          ncls_of[b] = k * PLAN2_MAX_CLASSES;
+          n_idx += hd[b].nidx;
+          n_sl += (hd[b].nsl + 3) & ~3;
+          n_cc += (hd[b].ncell + 3) & ~3;
+          ++k;
+        }
+        uint16_t *cidx2 = nullptr, *gdst2 = nullptr;
+        uint2 *cmeta2 = nullptr;
+        uint32_t *bcc2 = nullptr;
+        bool ok = cudaMalloc(&cidx2, sizeof(uint16_t) * (size_t)(n_idx + 64)) == cudaSuccess &&
+                  cudaMalloc(&gdst2, sizeof(uint16_t) * (size_t)(n_sl + 16) * per_norm) == cudaSuccess &&
+                  cudaMalloc(&cmeta2, sizeof(uint2) * (size_t)(uniq + 1) * PLAN2_MAX_CLASSES) == cudaSuccess &&
+                  cudaMalloc(&bcc2, sizeof(uint32_t) * (size_t)(n_cc + 16)) == cudaSuccess;
+        for (int64_t b = 0; b < nb && ok; ++b) {
+          if (rep[b] != b) continue;
+          const BlockDesc2 &d0 = hd[b];
+          const size_t nslp = (size_t)((d0.nsl + 3) & ~3), nccp = (size_t)((d0.ncell + 3) & ~3);
+          ok = (d0.nidx == 0 || cudaMemcpyAsync(cidx2 + nidx_of[b], p.cidx + d0.idx_off, sizeof(uint16_t) * (size_t)d0.nidx, cudaMemcpyDeviceToDevice, s) == cudaSuccess) &&
+               (nslp == 0 || cudaMemcpyAsync(gdst2 + nsl_of[b] * per_norm, p.gdst + d0.meta_off * per_norm, sizeof(uint16_t) * nslp * per_norm, cudaMemcpyDeviceToDevice, s) == cudaSuccess) &&
+               cudaMemcpyAsync(cmeta2 + ncls_of[b], p.cmeta + d0.cls_off, sizeof(uint2) * PLAN2_MAX_CLASSES, cudaMemcpyDeviceToDevice, s) == cudaSuccess &&
+               (nccp == 0 || cudaMemcpyAsync(bcc2 + ncc_of[b], p.bcc + d0.cc_off, sizeof(uint32_t) * nccp, cudaMemcpyDeviceToDevice, s) == cudaSuccess);
+        }
+        if (ok) {
+          for (int64_t b = 0; b < nb; ++b) {  // final descriptors: own s0 / vertex table, tables of the representative
+            const int64_t r = rep[b];
+            hd[b].idx_off = nidx_of[r];
+            hd[b].meta_off = nsl_of[r];
+            hd[b].cc_off = ncc_of[r];
+            hd[b].cls_off = ncls_of[r];
+            hd[b].pattern = (int32_t)r;
+          }
+          ok = cudaMemcpyAsync(p.bdesc, hd.data(), sizeof(BlockDesc2) * (size_t)nb, cudaMemcpyHostToDevice, s) == cudaSuccess &&
+               cudaStreamSynchronize(s) == cudaSuccess;
+        }
+        if (!ok) {
+          cudaFree(cidx2); cudaFree(gdst2); cudaFree(cmeta2); cudaFree(bcc2);
+          fdts_set_error("gather plan 2: compacting the pattern dictionary failed");
+          rc = 2;
+          break;
+        }
+        cudaFree(p.cidx); cudaFree(p.gdst); cudaFree(p.cmeta); cudaFree(p.bcc);
+        p.cidx = cidx2; p.gdst = gdst2; p.cmeta = cmeta2; p.bcc = bcc2;
+        p.compacted = 1;
+      }
     }
     p.ready = true;
   } while (0);

@@ -181,3 +181,17 @@ def test_bbm_dmma_jacobian(dim, degree, n):
     eng.set_option("dmma", 0)
     J0 = eng.ijacobian(0.0, x, xd, 12.5)
     assert rel_err(J1.cpu().numpy(), J0.cpu().numpy()) < TOL
+
+
+def test_pattern_dictionary_compaction():
+    """with enough repeated blocks only the tables of the unique patterns are kept (the duplicates are
+    freed after hashing); values must not change."""
+    from firedrake_ts_b200.engine import Engine
+
+    form, bcs, u, udot = make_problem("heat", 3, 2, 24, tile=3, ftile=6, device="cuda:0")
+    x, xd = u.data, udot.data
+    e1 = Engine(form, bcs, device="cuda:0", scatter=2, plan_version=2, dedup=1, options={"optimize": 0})
+    e0 = Engine(form, bcs, device="cuda:0", scatter=2, plan_version=2, dedup=0)
+    assert e1.get_option("plan_compacted") == 1 and e0.get_option("plan_compacted") == 0
+    assert e1.get_option("plan_patterns") * 4 <= e1.get_option("plan_blocks")
+    assert torch.equal(e1.ijacobian(0.0, x, xd, 10.0), e0.ijacobian(0.0, x, xd, 10.0))
