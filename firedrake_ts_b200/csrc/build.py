@@ -8,7 +8,7 @@ import sys
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["fdts_api.cu", "pattern.cu", "inst_heat.cu", "inst_bbm.cu", "inst_burgers.cu", "inst_ch.cu",
+SOURCES = ["fdts_api.cu", "pattern.cu", "inst_heat.cu", "inst_bbm.cu", "inst_burgers.cu", "inst_ch.cu", "inst_diffusion.cu",
            "kernels_heat.cu", "kernels_heat2.cu", "microbench.cu", "linalg.cu", "gather_plan.cu", "kernels_dmma.cu"]
 HEADERS = ["fdts_common.cuh", "kernels_generic.cuh", "kargs.cuh", "ref_tables.cuh", "heat_common.cuh",
            "../../include/fdts.h"]

@@ -133,6 +133,7 @@ KArgs fdts_make_kargs(fdts_engine *e, const double *x, const double *xdot, doubl
   a.shift = shift;
   a.p0 = e->cfg.params[0];
   a.p1 = e->cfg.params[1];
+  a.p2 = e->cfg.params[2];
   return a;
 }
 
@@ -142,6 +143,7 @@ int fdts_launch_residual(fdts_engine *e, const double *x, const double *xdot, do
   int rc = 3;
   switch (e->cfg.family) {
     case FDTS_HEAT: rc = fdts_generic_heat(false, e, a, s); break;
+    case FDTS_DIFFUSION: rc = fdts_generic_diffusion(false, e, a, s); break;
     case FDTS_BBM: rc = fdts_generic_bbm(false, e, a, s); break;
     case FDTS_BURGERS: rc = fdts_generic_burgers(false, e, a, s); break;
     case FDTS_CAHN_HILLIARD: rc = fdts_generic_ch(false, e, a, s); break;
@@ -158,6 +160,7 @@ int fdts_launch_jacobian(fdts_engine *e, const double *x, const double *xdot, do
   int rc = 3;
   switch (e->cfg.family) {
     case FDTS_HEAT: rc = fdts_generic_heat(true, e, a, s); break;
+    case FDTS_DIFFUSION: rc = fdts_generic_diffusion(true, e, a, s); break;
     case FDTS_BBM:
       rc = fdts_bbm_jacobian_dmma(e, a, s);  // tensor-core contraction where it applies (P2/P3), else generic
       if (rc == 3) rc = fdts_generic_bbm(true, e, a, s);

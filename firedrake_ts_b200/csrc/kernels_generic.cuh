@@ -29,7 +29,7 @@ struct KArgs {
   int64_t ncells_total, c0, c1, nown, nnodes, node_nnz;
   int32_t nq;
   double shift;
-  double p0, p1;
+  double p0, p1, p2;
 };
 
 template <int DIM, int NC>
@@ -40,11 +40,16 @@ struct Point {
 
 // pointwise residual fluxes: F_{i,m} += wq * (f0[m] phi_i + sum_k f1[m][k] d_k phi_i)
 template <int FAM, int DIM, int NC>
-__device__ __forceinline__ void fluxes(const Point<DIM, NC> &s, double p0, double (&f0)[NC], double (&f1)[NC][DIM]) {
+__device__ __forceinline__ void fluxes(const Point<DIM, NC> &s, double p0, double p1, double p2, double (&f0)[NC],
+                                       double (&f1)[NC][DIM]) {
   if constexpr (FAM == FDTS_HEAT) {  // examples/heat.py:11
     f0[0] = s.ud[0] - p0;
 #pragma unroll
     for (int k = 0; k < DIM; ++k) f1[0][k] = s.gu[0][k];
+  } else if constexpr (FAM == FDTS_DIFFUSION) {  // examples/heat-explicit.py:13-14 (F and G are both of this shape)
+    f0[0] = p1 * s.ud[0] - p0;
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) f1[0][k] = p2 * s.gu[0][k];
   } else if constexpr (FAM == FDTS_BBM) {  // examples/bbm.py:35-40
     f0[0] = s.ud[0] + s.gu[0][0] + s.u[0] * s.gu[0][0];
 #pragma unroll
@@ -75,12 +80,15 @@ __device__ __forceinline__ void fluxes(const Point<DIM, NC> &s, double p0, doubl
 // pointwise Jacobian entry for test (i, m), trial (j, n):  shift*dF/dudot + dF/du
 template <int FAM, int DIM, int NC>
 __device__ __forceinline__ double jac_entry(int m, int n, double pj, const double *Gj, double pi, const double *Gi,
-                                            const Point<DIM, NC> &s, double shift, double p0) {
+                                            const Point<DIM, NC> &s, double shift, double p0, double p1,
+                                            double p2) {
   double gg = 0.0;
 #pragma unroll
   for (int k = 0; k < DIM; ++k) gg += Gj[k] * Gi[k];
   if constexpr (FAM == FDTS_HEAT) {
     return shift * pj * pi + gg;
+  } else if constexpr (FAM == FDTS_DIFFUSION) {
+    return shift * p1 * pj * pi + p2 * gg;
   } else if constexpr (FAM == FDTS_BBM) {
     return shift * (pj * pi + Gj[0] * Gi[0]) + Gj[0] * pi + (s.gu[0][0] * pj + s.u[0] * Gj[0]) * pi;
   } else if constexpr (FAM == FDTS_BURGERS) {
@@ -183,7 +191,7 @@ __global__ void __launch_bounds__(128) residual_kernel(const KArgs a) {
     Point<DIM, NC> s;
     eval_point<DIM, ND, NC>(Bq, g, ul, udl, s);
     double f0[NC], f1[NC][DIM];
-    fluxes<FAM, DIM, NC>(s, a.p0, f0, f1);
+    fluxes<FAM, DIM, NC>(s, a.p0, a.p1, a.p2, f0, f1);
     const double wq = sw[q] * g.adet;
     double r[NC][DIM];  // fluxes pulled back to reference derivatives
 #pragma unroll
@@ -289,7 +297,8 @@ __global__ void __launch_bounds__(128) jacobian_kernel(const KArgs a) {
             for (int j = 0; j < ND; ++j)
 #pragma unroll
               for (int n = 0; n < NC; ++n)
-                acc[r][m][j * NC + n] += jac_entry<FAM, DIM, NC>(m, n, Bq[j], G[j], pi, Gi, s, a.shift, a.p0);
+                acc[r][m][j * NC + n] += jac_entry<FAM, DIM, NC>(m, n, Bq[j], G[j], pi, Gi, s, a.shift, a.p0, a.p1,
+                                                              a.p2);
         }
       }
     }

@@ -12,6 +12,9 @@ that names the family, its constants, and the ``u`` / ``udot`` Functions:
   cahn_hilliard  examples/cahn-hilliard.py:26-38
                  F = (c_t, q) + (grad mu, grad q) + (mu, v) - (f'(c), v) - lambda (grad c, grad v)
                  f = 100 c^2 (1-c)^2
+  diffusion      examples/heat-explicit.py:13-14   a (u_t, v) + k (grad u, grad v) - s (1, v)
+                 the two sides of the IMEX split F(u_t, u, t) = G(u, t):
+                 F = (u_t, v) is (a, k, s) = (1, 0, 0);  G = -((grad u, grad v) - (1, v)) is (0, -1, -1)
 
 J is always ``shift * dF/dudot + dF/du`` (firedrake_ts/ts_solver.py:108); the
 derivative is taken by hand in the kernels (and in the oracle), ``shift`` stays
@@ -21,14 +24,15 @@ from __future__ import annotations
 
 from dataclasses import dataclass, field
 
-HEAT, BURGERS, BBM, CAHN_HILLIARD = 0, 1, 2, 3
-FAMILY_NAMES = {HEAT: "heat", BURGERS: "burgers", BBM: "bbm", CAHN_HILLIARD: "cahn_hilliard"}
+HEAT, BURGERS, BBM, CAHN_HILLIARD, DIFFUSION = 0, 1, 2, 3, 4
+FAMILY_NAMES = {HEAT: "heat", BURGERS: "burgers", BBM: "bbm", CAHN_HILLIARD: "cahn_hilliard",
+                DIFFUSION: "diffusion"}
 
 
 def quadrature_degree(family: int, degree: int) -> int:
     """UFL's estimated total polynomial degree for each family."""
     k = degree
-    if family == HEAT:
+    if family in (HEAT, DIFFUSION):
         return 2 * k
     if family in (BURGERS, BBM):
         return max(3 * k - 1, 2 * k)
@@ -67,6 +71,29 @@ class Form:
 def heat(u, udot, source: float = 1.0) -> Form:
     assert u.function_space().ncomp == 1
     return Form(HEAT, u, udot, (float(source), 0.0, 0.0, 0.0))
+
+
+def diffusion(u, udot, mass: float = 1.0, diffusivity: float = 1.0, source: float = 0.0) -> Form:
+    """a (u_t, v) + k (grad u, grad v) - s (1, v); params = (s, a, k)."""
+    assert u.function_space().ncomp == 1
+    return Form(DIFFUSION, u, udot, (float(source), float(mass), float(diffusivity), 0.0))
+
+
+def heat_explicit(u, udot, source: float = 1.0):
+    """The IMEX split of examples/heat-explicit.py:13-14: returns (F, G) with
+    F = (u_t, v) and G = -((grad u, grad v) - (source, v))."""
+    return (diffusion(u, udot, mass=1.0, diffusivity=0.0, source=0.0),
+            diffusion(u, udot, mass=0.0, diffusivity=-1.0, source=-float(source)))
+
+
+def mass_form(F: Form) -> Form:
+    """derivative(F, udot) as a form whose IJacobian at shift = 1 is the mass matrix (used by the
+    right-hand-side projection solver, reference solving_utils.py:429-445)."""
+    if F.family == HEAT:
+        return diffusion(F.u, F.udot, mass=1.0, diffusivity=0.0)
+    if F.family == DIFFUSION:
+        return diffusion(F.u, F.udot, mass=F.params[1], diffusivity=0.0)
+    raise NotImplementedError(f"mass matrix of the {F.name} family is not in the catalogue")
 
 
 def burgers(u, udot, nu: float = 1.0e-4) -> Form:

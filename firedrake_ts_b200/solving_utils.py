@@ -62,13 +62,12 @@ class _TSContext:
     def __init__(self, problem, mat_type=None, pmat_type=None, appctx=None,
                  pre_jacobian_callback=None, pre_function_callback=None,
                  post_jacobian_callback=None, post_function_callback=None,
-                 options_prefix=None, transfer_manager=None, assembler="b200", comm=None):
+                 options_prefix=None, transfer_manager=None, assembler="b200", comm=None,
+                 project_rhs=True, rhs_projection_parameters=None, rhs_assembler=None, mass_assembler=None):
         if mat_type not in (None, "aij", "aijcusparse"):
             raise ValueError(f"mat_type {mat_type!r}: the B200 engine assembles monolithic AIJ only")
         if problem.Jp is not None:
             raise NotImplementedError("a separate preconditioner form Jp is outside the engine's scope")
-        if problem.G is not None:
-            raise NotImplementedError("the IMEX G(t,u) branch is outside the engine's scope (SURVEY.md 2.1 row 2)")
         self._problem = problem
         self.mat_type, self.pmat_type = mat_type or "aij", pmat_type or "aij"
         self.appctx = appctx or {}
@@ -85,8 +84,9 @@ class _TSContext:
         self._shift = problem.shift
         self._time = problem.time
         self.F, self.J, self.Jp = problem.F, problem.J, problem.Jp
-        self.G, self.dGdu = None, None
+        self.G, self.dGdu = problem.G, problem.dGdu
         self.bcs_F = tuple(problem.dirichlet_bcs())
+        self.bcs_G = self.bcs_dGdu = self.bcs_F
         self.fcp = problem.form_compiler_parameters
         self._jacobian_assembled = False
         self._nullspace = self._nullspace_T = self._near_nullspace = None
@@ -125,6 +125,29 @@ class _TSContext:
         self._assemble_residual = self._b200_assemble_residual
         self._assemble_jac = self._b200_assemble_jac
 
+        # IMEX branch (reference :104-111): G is assembled by an engine of its own on the same
+        # space, so it shares the sparsity and the Dirichlet rows of F
+        if self.G is not None:
+            if assembler == "b200":
+                from .engine import Engine
+
+                self.rhs_engine = Engine(problem.G, self.bcs_G, device=self._device)
+            else:
+                if rhs_assembler is None:
+                    raise ValueError("a test assembler for F needs rhs_assembler= for G")
+                self.rhs_engine = rhs_assembler
+            self._mass_assembler = mass_assembler
+            self.rhs_projection_parameters = rhs_projection_parameters
+            self.project_rhs = project_rhs
+            self._G_vec = Vec(torch.zeros(V.num_owned_dofs, dtype=torch.float64, device=self._device), comm)
+            self._projected_G = Vec(torch.zeros_like(self._G_vec.array), comm)
+            self._G_or_projected_G = self._projected_G if self.project_rhs else self._G_vec
+            self._rhs_jac = _Assembled(Mat(rowptr, colidx, torch.zeros_like(values), V.num_dofs, halo=self._halo))
+            self._rhs_pjac = self._rhs_jac
+            self._dGdu = self._rhs_jac
+            self._rhs_jacobian_assembled = False
+            self._rhs_projection_solver_cache = None
+
     # -- the two assemblers that replace get_assembler(...).assemble ----------------
     def _b200_assemble_residual(self, tensor=None):
         tensor = tensor if tensor is not None else self._F
@@ -156,10 +179,84 @@ class _TSContext:
         ts.setIJacobian(self.form_jacobian, J=self._jac.petscmat, P=self._pjac.petscmat)
 
     def set_rhs_function(self, ts):
-        pass  # G is None on the engine path
+        r"""Set the function to compute G(t,u) where F() = G() is the equation to be solved
+        (reference :124-128)."""
+        if self.G is not None:
+            ts.setRHSFunction(self.form_rhs_function, self._G_or_projected_G)
 
     def set_rhs_jacobian(self, ts):
-        pass
+        r"""Set the function to compute the Jacobian of G (reference :130-133)."""
+        if self.G is not None:
+            ts.setRHSJacobian(self.form_rhs_jacobian, J=self._rhs_jac.petscmat, P=self._rhs_pjac.petscmat)
+
+    # -- IMEX assemblers (reference :429-458, :462-485) ---------------------------------------
+    def _assemble_rhs_residual(self, tensor):
+        out = self.rhs_engine.ifunction(float(self._time), self._x.data, self._xdot.data, out=tensor.array)
+        if out is not tensor.array:
+            tensor.array.copy_(torch.as_tensor(out))
+        return tensor
+
+    def _assemble_rhs_jac(self, jac):
+        mat = jac.petscmat
+        out = self.rhs_engine.ijacobian(float(self._time), self._x.data, self._xdot.data, 0.0, out=mat.values)
+        if out is not mat.values:
+            mat.values.copy_(torch.as_tensor(out))
+        return jac
+
+    @property
+    def _rhs_projection_solver(self):
+        r"""mass matrix = derivative(F, udot) assembled once with bcs_F, and the KSP that solves
+        with it (reference :429-445).  Default parameters: Jacobi-preconditioned CG to 1e-12 on
+        the device CSR (the reference's default is a direct solve; ``pc_type: lu`` gives that on
+        one rank)."""
+        if self.G is None:
+            return None
+        if self._rhs_projection_solver_cache is None:
+            from . import forms
+            from .ts import KSP, ksp_solve
+
+            F = self._problem.F
+            is_pure_mass = F.family == forms.DIFFUSION and F.params[2] == 0.0
+            if is_pure_mass:
+                eng = self.engine
+            elif self._mass_assembler is not None:
+                eng = self._mass_assembler
+            else:
+                from .engine import Engine
+
+                eng = Engine(forms.mass_form(F), self.bcs_F, device=self._device)
+            base = self._jac.petscmat
+            vals = torch.zeros_like(base.values)
+            out = eng.ijacobian(0.0, self._x.data, self._xdot.data, 1.0, out=vals)
+            if out is not vals:
+                vals.copy_(torch.as_tensor(out))
+            M = Mat(base.rowptr, base.colidx, vals, base.ncols, halo=self._halo)
+            k = KSP()
+            k.type, k.pc_type, k.rtol, k.atol = "cg", "jacobi", 1e-12, 1e-50
+            o = dict(self.rhs_projection_parameters or {})
+            k.type = o.get("ksp_type", k.type)
+            k.pc_type = o.get("pc_type", k.pc_type)
+            k.rtol = float(o.get("ksp_rtol", k.rtol))
+            k.atol = float(o.get("ksp_atol", k.atol))
+            k.max_it = int(o.get("ksp_max_it", k.max_it))
+            comm = self.comm
+
+            class _Solver:
+                mass_matrix, ksp = M, k
+
+                @staticmethod
+                def solve(x, bvec):
+                    x.array.copy_(ksp_solve(M, bvec.array, k, comm))
+
+            self._rhs_projection_solver_cache = _Solver
+        return self._rhs_projection_solver_cache
+
+    def _assemble_projected_rhs_residual(self):
+        """solve(mass_matrix_form == self.G, self._projected_G, self.bcs_G)  (reference :447-458)"""
+        if self.G is not None:
+            self._assemble_rhs_residual(self._G_vec)
+            if self.project_rhs:
+                self._rhs_projection_solver.solve(self._projected_G, self._G_vec)
 
     def set_nullspace(self, nullspace, ises=None, transpose=False, near=False):
         if nullspace is None:
@@ -195,6 +292,59 @@ class _TSContext:
 
         # F may not be the same vector as self._F, so copy residual out to F.
         ctx._F.copy(F)
+
+    @staticmethod
+    def form_rhs_function(ts, t, X, G):
+        r"""Form the right-hand side G(t, u) for this problem (reference :320-347)
+
+        :arg ts: a TS object
+        :arg t: the time at step/stage being solved
+        :arg X: state vector
+        :arg G: function vector
+        """
+        dm = ts.getDM()
+        ctx = dmhooks.get_appctx(dm)
+        # X may not be the same vector as the vec behind self._x, so copy guess in from X.
+        ctx._x.set_owned(X.array)
+        if ctx._halo is not None:
+            ctx._halo.forward(ctx._x.data)
+        ctx._time.assign(t)
+
+        ctx._assemble_projected_rhs_residual()
+
+        # G may not be the same vector as self._projected_G, so copy residual out to G.
+        ctx._G_or_projected_G.copy(G)
+
+    @staticmethod
+    def form_rhs_jacobian(ts, t, X, J, P):
+        r"""Form the Jacobian dG/du for this problem (reference :349-384)
+
+        :arg ts: a TS object
+        :arg t: the time at step/stage being solved
+        :arg X: state vector
+        :arg J: the Jacobian (a Mat)
+        :arg P: the preconditioner matrix (a Mat)
+        """
+        dm = ts.getDM()
+        ctx = dmhooks.get_appctx(dm)
+        problem = ctx._problem
+
+        assert J.handle == ctx._rhs_jac.petscmat.handle
+        if problem._constant_rhs_jacobian and ctx._rhs_jacobian_assembled:
+            # Don't need to do any work with a constant jacobian that's already assembled
+            return
+        ctx._rhs_jacobian_assembled = True
+
+        ctx._x.set_owned(X.array)
+        if ctx._halo is not None:
+            ctx._halo.forward(ctx._x.data)
+        ctx._time.assign(t)
+
+        ctx._assemble_rhs_jac(ctx._dGdu)
+
+        ctx.set_nullspace(ctx._nullspace, None, transpose=False, near=False)
+        ctx.set_nullspace(ctx._nullspace_T, None, transpose=True, near=False)
+        ctx.set_nullspace(ctx._near_nullspace, None, transpose=False, near=True)
 
     @staticmethod
     def form_jacobian(ts, t, X, Xdot, shift, J, P):

@@ -139,6 +139,53 @@ class ConvergedReason:
     DIVERGED_STEP_REJECTED = -2
 
 
+def ksp_solve(A, rhs: torch.Tensor, k, comm=None) -> torch.Tensor:
+    """Solve A x = rhs with the Krylov method / preconditioner named by the KSP ``k``
+    (cg | gmres, jacobi | none | lu).  Shared by the Newton step and by the right-hand-side
+    projection solver (reference solving_utils.py:429-458)."""
+    from . import linalg
+
+    def to_local(v):
+        return v if A.halo is None else A.halo.owned_to_local(v)
+
+    def matvec(v):
+        return A.mult(to_local(v))
+
+    def dot(a, b):
+        return float(_allreduce_sum(torch.dot(a, b), comm))
+
+    if k.pc_type == "lu":
+        assert comm is None, "pc_type lu is a single-rank test facility"
+        import numpy as np
+        import scipy.sparse.linalg as spla
+
+        lu = spla.splu(A.to_scipy().tocsc())
+        sol = lu.solve(rhs.cpu().numpy())
+        k.its = 1
+        return torch.from_numpy(np.ascontiguousarray(sol)).to(rhs.device)
+    if k.pc_type == "jacobi":
+        dinv = 1.0 / A.diagonal()
+        prec = lambda r: r * dinv  # noqa: E731
+    else:
+        prec = lambda r: r  # noqa: E731
+    if k.type == "cg":
+        x, k.its = linalg.pcg(matvec, rhs, prec, dot, k.rtol, k.atol, k.max_it)
+    else:
+        x, k.its = linalg.gmres(matvec, rhs, prec, dot, k.rtol, k.atol, k.max_it, k.restart)
+    return x
+
+
+# IMEX Runge-Kutta tableaus (At: implicit part, A: explicit part) in PETSc's TSARKIMEX naming.
+# Only schemes whose first stage is explicit and carries no implicit weight are listed, so the
+# implicit slope of the first stage is never needed.
+ARKIMEX_TABLEAUS = {
+    # first-order IMEX Euler (forward Euler on G, backward Euler on F)
+    "1": dict(At=[[0.0, 0.0], [0.0, 1.0]], A=[[0.0, 0.0], [1.0, 0.0]], bt=[0.0, 1.0], b=[1.0, 0.0]),
+    # Ascher-Ruuth-Spiteri (1,2,2): implicit-explicit midpoint, second order
+    "ars122": dict(At=[[0.0, 0.0], [0.0, 0.5]], A=[[0.0, 0.0], [0.5, 0.0]], bt=[0.0, 1.0], b=[0.0, 1.0]),
+}
+
+
 class TS:
     """BEULER / THETA time stepper with Newton + Krylov, PETSc callback protocol."""
 
@@ -146,6 +193,8 @@ class TS:
 
     class EquationType:
         IMPLICIT = 1
+
+    TYPES = ("beuler", "theta", "arkimex")
 
     def __init__(self, comm=None):
         self.comm = comm
@@ -159,6 +208,10 @@ class TS:
         self.reason = 0
         self._ifunction = self._ijacobian = None
         self._F = self._J = self._P = None
+        self._rhsfunction = self._rhsjacobian = None
+        self._G = self._Jrhs = self._Prhs = None
+        self.arkimex_type = "ars122"
+        self.rhs_evals = 0
         self._monitor = None
         self.equation_type = None
         self.newton_its = 0
@@ -206,7 +259,7 @@ class TS:
         self.equation_type = et
 
     def setType(self, name):
-        assert name in ("beuler", "theta"), f"TS type {name!r} is not provided by the stand-in"
+        assert name in self.TYPES, f"TS type {name!r} is not provided by the stand-in"
         self.type = name
         if name == "beuler":
             self.theta = 1.0
@@ -220,6 +273,16 @@ class TS:
     def setIJacobian(self, f, J=None, P=None):
         self._ijacobian, self._J, self._P = f, J, P
 
+    def setRHSFunction(self, f, vec=None):
+        self._rhsfunction, self._G = f, vec
+
+    def setRHSJacobian(self, f, J=None, P=None):
+        self._rhsjacobian, self._Jrhs, self._Prhs = f, J, P
+
+    def setARKIMEXType(self, name):
+        assert name in ARKIMEX_TABLEAUS, f"ARKIMEX type {name!r}: the stand-in provides {sorted(ARKIMEX_TABLEAUS)}"
+        self.arkimex_type = name
+
     def getConvergedReason(self):
         return self.reason
 
@@ -227,6 +290,8 @@ class TS:
         o = dict(opts or {})
         if "ts_type" in o:
             self.setType(o["ts_type"])
+        if "ts_arkimex_type" in o:
+            self.setARKIMEXType(o["ts_arkimex_type"])
         if "ts_theta_theta" in o:
             self.setTheta(o["ts_theta_theta"])
         if "ts_dt" in o:
@@ -248,44 +313,8 @@ class TS:
         k.restart = int(o.get("ksp_gmres_restart", k.restart))
 
     # -- linear solve ---------------------------------------------------------------
-    def _to_local(self, x_owned):
-        """owned vector -> local (owned + ghost) vector for the mat-vec."""
-        halo = self._J.halo
-        if halo is None:
-            return x_owned
-        return halo.owned_to_local(x_owned)
-
     def _linear_solve(self, rhs: torch.Tensor) -> torch.Tensor:
-        from . import linalg
-
-        k, A = self.snes.ksp, self._J
-        comm = self.comm
-
-        def matvec(v):
-            return A.mult(self._to_local(v))
-
-        def dot(a, b):
-            return float(_allreduce_sum(torch.dot(a, b), comm))
-
-        if k.pc_type == "lu":
-            assert comm is None, "pc_type lu is a single-rank test facility"
-            import numpy as np
-            import scipy.sparse.linalg as spla
-
-            lu = spla.splu(A.to_scipy().tocsc())
-            sol = lu.solve(rhs.cpu().numpy())
-            k.its = 1
-            return torch.from_numpy(np.ascontiguousarray(sol)).to(rhs.device)
-        if k.pc_type == "jacobi":
-            dinv = 1.0 / A.diagonal()
-            prec = lambda r: r * dinv  # noqa: E731
-        else:
-            prec = lambda r: r  # noqa: E731
-        if k.type == "cg":
-            x, k.its = linalg.pcg(matvec, rhs, prec, dot, k.rtol, k.atol, k.max_it)
-        else:
-            x, k.its = linalg.gmres(matvec, rhs, prec, dot, k.rtol, k.atol, k.max_it, k.restart)
-        return x
+        return ksp_solve(self._J, rhs, self.snes.ksp, self.comm)
 
     # -- the integrator ---------------------------------------------------------------
     def _stage_solve(self, X: Vec, X0: torch.Tensor, ts_time: float, shift: float):
@@ -320,9 +349,72 @@ class TS:
         s.reason = -1
         return None
 
+    def _solve_arkimex(self, u: Vec):
+        """Fixed-step additive Runge-Kutta IMEX integrator for F(t, u, udot) = G(t, u) in PETSc's
+        formulation (TSARKIMEX): every implicit stage solves F(t, Y, shift (Y - Z)) = 0 with the
+        IFunction / IJacobian callbacks only, Z carrying the earlier implicit slopes and the
+        explicit slopes YdotRHS_j = RHSFunction(t_j, Y_j).  As in PETSc, the RHSFunction value is
+        used as a slope, which is why the reference projects G with the mass matrix first
+        (solving_utils.py:447-458)."""
+        tab = ARKIMEX_TABLEAUS[self.arkimex_type]
+        At, A, bt, b = tab["At"], tab["A"], tab["bt"], tab["b"]
+        ns = len(b)
+        c = [sum(row) for row in A]
+        ct = [sum(row) for row in At]
+        Y = Vec(u.array.clone(), self.comm)
+        G = self._G if self._G is not None else Y.duplicate()
+        while self.time < self.max_time * (1 - 1e-14) and self.steps < self.max_steps:
+            h = self.dt
+            if self.exact_final_time == "matchstep" and self.time + h > self.max_time:
+                h = self.max_time - self.time
+            YdotI = [None] * ns
+            YdotRHS = [None] * ns
+            for i in range(ns):
+                Z = u.array.clone()
+                for j in range(i):
+                    if At[i][j] != 0.0:
+                        Z.add_(YdotI[j], alpha=h * At[i][j])
+                    if A[i][j] != 0.0:
+                        Z.add_(YdotRHS[j], alpha=h * A[i][j])
+                if At[i][i] == 0.0:
+                    Y.array.copy_(Z)  # explicit stage
+                    YdotI[i] = None
+                else:
+                    Y.array.copy_(Z)
+                    shift = 1.0 / (h * At[i][i])
+                    Ydot = self._stage_solve(Y, Z, self.time + ct[i] * h, shift)
+                    if Ydot is None:
+                        self.reason = ConvergedReason.DIVERGED_NONLINEAR_SOLVE
+                        return
+                    YdotI[i] = Ydot.array.clone()
+                if any(A[k][i] != 0.0 for k in range(i + 1, ns)) or b[i] != 0.0:
+                    self._rhsfunction(self, self.time + c[i] * h, Y, G)
+                    self.rhs_evals += 1
+                    YdotRHS[i] = G.array.clone()
+            for i in range(ns):
+                if bt[i] != 0.0:
+                    u.array.add_(YdotI[i], alpha=h * bt[i])
+                if b[i] != 0.0:
+                    u.array.add_(YdotRHS[i], alpha=h * b[i])
+            self.time += h
+            self.steps += 1
+            if self._monitor:
+                self._monitor(self, self.steps, self.time, u)
+
     def solve(self, u: Vec):
         assert self._ifunction is not None and self._ijacobian is not None
         self.steps, self.reason = 0, 0
+        if self._rhsfunction is not None and self.type != "arkimex":
+            raise NotImplementedError(f"TS type {self.type!r} with a right-hand-side function G: use ts_type arkimex")
+        if self.type == "arkimex":
+            assert self._rhsfunction is not None, "ts_type arkimex needs G (setRHSFunction)"
+            if self._monitor:
+                self._monitor(self, self.steps, self.time, u)
+            self._solve_arkimex(u)
+            if self.reason == 0:
+                self.reason = (ConvergedReason.CONVERGED_TIME if self.time >= self.max_time * (1 - 1e-14)
+                               else ConvergedReason.CONVERGED_ITS)
+            return
         theta = self.theta
         if self._monitor:
             self._monitor(self, self.steps, self.time, u)

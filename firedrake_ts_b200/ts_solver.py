@@ -64,8 +64,8 @@ class DAEProblem(object):
         :param Jp: a form used for preconditioning the linear system (optional)
         :param dict form_compiler_parameters: accepted and stored (no form compiler here)
         :is_linear: internally used to check form style consistency
-        :param G: G(t, u) term treated explicitly by IMEX methods (not assembled by
-            the B200 engine)
+        :param G: G(t, u) term treated explicitly by IMEX methods: F(u̇, u, t) = G(u, t)
+            (reference ts_solver.py:111; examples/heat-explicit.py)
         """
         self.bcs = _extract_bcs(bcs)
         self.is_linear = is_linear
@@ -91,7 +91,8 @@ class DAEProblem(object):
         # Use the user-provided Jacobian. If none is provided, derive the Jacobian from the residual
         # (reference ts_solver.py:108: J = shift*derivative(F, udot) + derivative(F, u)).
         self.J = J or (forms.derivative(F, self.shift) if isinstance(F, forms.Form) else None)
-        self.dGdu = None
+        # reference ts_solver.py:111: dGdu = derivative(G, u)  (no udot term: shift 0)
+        self.dGdu = forms.derivative(G, Constant(0.0)) if isinstance(G, forms.Form) else None
 
         check_pde_args(self.F, self.G, self.J, self.Jp)
 
@@ -181,7 +182,10 @@ class DAESolver(OptionsManager):
         ctx = _TSContext(problem, mat_type=mat_type, pmat_type=pmat_type, appctx=appctx,
                          pre_jacobian_callback=pre_j_callback, pre_function_callback=pre_f_callback,
                          post_jacobian_callback=post_j_callback, post_function_callback=post_f_callback,
-                         options_prefix=self.options_prefix, assembler=kwargs.get("assembler", "b200"), comm=comm)
+                         options_prefix=self.options_prefix, assembler=kwargs.get("assembler", "b200"), comm=comm,
+                         project_rhs=kwargs.get("project_rhs", True),
+                         rhs_projection_parameters=kwargs.get("rhs_projection_parameters"),
+                         rhs_assembler=kwargs.get("rhs_assembler"), mass_assembler=kwargs.get("mass_assembler"))
 
         if ctx.is_mixed:
             # Mixed problem, use jacobi pc if user has not supplied one.
@@ -202,6 +206,9 @@ class DAESolver(OptionsManager):
         self.ts.setMaxTime(problem.tspan[1])
         if problem.G is None:
             self.ts.setEquationType(TS.EquationType.IMPLICIT)
+        else:
+            # If G is provided use the arkimex solver (reference ts_solver.py:252-253)
+            self.set_default_parameter("ts_type", "arkimex")
         self.set_default_parameter("ts_exact_final_time", "stepover")
 
         self._set_problem_eval_funcs(ctx, problem, nullspace, nullspace_T, near_nullspace)

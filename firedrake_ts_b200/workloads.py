@@ -23,7 +23,7 @@ def make_problem(family, dim, degree, n, *, tile=0, partition=None, device="cpu"
     """returns (form, bcs, u, udot) with the seeded states of SURVEY.md 8(d)."""
     shape = (n,) * dim
     msh = M.SimplexMesh(shape, partition=partition, tile=tile, device=device)
-    if family in ("heat", "bbm"):
+    if family in ("heat", "bbm", "diffusion"):
         V = M.FunctionSpace(msh, degree, variant=variant, tile=ftile, tile_offset=foffset)
     elif family == "burgers":
         V = M.FunctionSpace(msh, degree, ncomp=dim, layout="interleaved", variant=variant)
@@ -46,11 +46,14 @@ def make_problem(family, dim, degree, n, *, tile=0, partition=None, device="cpu"
         return loc.t().reshape(-1)
 
     x = V.node_coords.cpu()
-    if family in ("heat", "bbm"):
+    if family in ("heat", "bbm", "diffusion"):
         u.data.copy_(torch.prod(torch.sin(math.pi * x), dim=1))
         udot.data.copy_(rnd(1))
-        form = forms.heat(u, udot) if family == "heat" else forms.bbm(u, udot)
-        bcs = [DirichletBC(V, 0.0, "on_boundary")] if family == "heat" else []
+        if family == "diffusion":  # generic coefficients; the IMEX split uses (1, 0, 0) and (0, -1, -1)
+            form = forms.diffusion(u, udot, mass=0.75, diffusivity=-1.5, source=0.3)
+        else:
+            form = forms.heat(u, udot) if family == "heat" else forms.bbm(u, udot)
+        bcs = [DirichletBC(V, 0.0, "on_boundary")] if family != "bbm" else []
     elif family == "burgers":
         v = torch.zeros((V.num_nodes, dim), dtype=torch.float64)
         v[:, 0] = torch.sin(math.pi * x[:, 0])

@@ -44,7 +44,11 @@ extern "C" {
 
 typedef struct fdts_engine *fdts_handle;
 
-enum { FDTS_HEAT = 0, FDTS_BURGERS = 1, FDTS_BBM = 2, FDTS_CAHN_HILLIARD = 3 };
+/* FDTS_DIFFUSION is the two-sided form of the IMEX branch (reference examples/heat-explicit.py:13-14, assembled by
+ * _TSContext.form_rhs_function / form_rhs_jacobian, firedrake_ts/solving_utils.py:320-384):
+ *   params[1] (u_t, v) + params[2] (grad u, grad v) - params[0] (1, v)
+ * F = (u_t, v) is params (0, 1, 0); G = -((grad u, grad v) - (1, v)) is params (-1, 0, -1). */
+enum { FDTS_HEAT = 0, FDTS_BURGERS = 1, FDTS_BBM = 2, FDTS_CAHN_HILLIARD = 3, FDTS_DIFFUSION = 4 };
 enum { FDTS_INTERLEAVED = 0, FDTS_BLOCKED = 1 };
 enum { FDTS_MEM_HOST = 0, FDTS_MEM_DEVICE = 1 };
 

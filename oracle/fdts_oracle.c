@@ -37,7 +37,7 @@
 #define MAXND 20
 #define MAXC 3
 
-enum { FAM_HEAT = 0, FAM_BURGERS = 1, FAM_BBM = 2, FAM_CH = 3 };
+enum { FAM_HEAT = 0, FAM_BURGERS = 1, FAM_BBM = 2, FAM_CH = 3, FAM_DIFFUSION = 4 };
 enum { LAYOUT_INTERLEAVED = 0, LAYOUT_BLOCKED = 1 };
 
 typedef struct {
@@ -154,6 +154,9 @@ static void element_residual(const oracle_problem *p, int64_t c, const double *u
         case FAM_HEAT: /* examples/heat.py:11 */
           Fe[i] += s.wq * (s.ud[0] * ph + dotd(s.gu[0], Gi, d) - p->params[0] * ph);
           break;
+        case FAM_DIFFUSION: /* examples/heat-explicit.py:13-14: a (u_t, v) + k (grad u, grad v) - s (1, v) */
+          Fe[i] += s.wq * (p->params[1] * s.ud[0] * ph + p->params[2] * dotd(s.gu[0], Gi, d) - p->params[0] * ph);
+          break;
         case FAM_BBM: /* examples/bbm.py:35-40 */
           Fe[i] += s.wq * (s.ud[0] * ph + s.gu[0][0] * ph + s.u[0] * s.gu[0][0] * ph + s.gud[0][0] * Gi[0]);
           break;
@@ -193,6 +196,9 @@ static void element_jacobian(const oracle_problem *p, int64_t c, const double *u
         switch (p->family) {
           case FAM_HEAT:
             Ae[i * ne + j] += s.wq * (shift * pj * pi + gg);
+            break;
+          case FAM_DIFFUSION:
+            Ae[i * ne + j] += s.wq * (shift * p->params[1] * pj * pi + p->params[2] * gg);
             break;
           case FAM_BBM:
             Ae[i * ne + j] += s.wq * (shift * (pj * pi + Gj[0] * Gi[0]) + Gj[0] * pi +

@@ -174,3 +174,42 @@ def test_headline_size_properties(n, degree):
     assert float(J[isb[ci.long()] & ~sel].abs().max()) == 0.0  # Dirichlet columns dropped
     F = eng.ifunction(0.0, u.data, udot.data)
     assert float(F[b].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("arktype,dim,n", [("ars122", 1, 10), ("1", 2, 6)])
+def test_heat_explicit_imex_trajectory(arktype, dim, n):
+    """examples/heat-explicit.py (F = (u_t, v), G = -((grad u, grad v) - (1, v)), ts_type arkimex by
+    default) on the B200 engine vs the same stepper driven by the oracle: form_rhs_function with the
+    mass-matrix projection (CG + Jacobi on the device CSR vs LU on the CPU), reference
+    solving_utils.py:320-347, 429-458."""
+    dt, nsteps = (5.0e-4, 20) if dim == 1 else (2.0e-4, 10)
+    finals = []
+    for which in ("oracle", "b200"):
+        if dim == 1:
+            mesh = fts.UnitIntervalMesh(n)
+        else:
+            mesh = fts.UnitSquareMesh(n, n)
+        V = fts.FunctionSpace(mesh, 1 if dim == 1 else 2)
+        u, u_t = fts.Function(V), fts.Function(V)
+        F, G = forms.heat_explicit(u, u_t)
+        bcs = [fts.DirichletBC(V, 0.0, "on_boundary")]
+        u.interpolate(lambda x: torch.prod(torch.sin(math.pi * x), dim=1) + (x[:, 0] < 0.5).double())
+        problem = fts.DAEProblem(F, u, u_t, (0.0, dt * nsteps), bcs=bcs, G=G)
+        kw = dict(solver_parameters={"pc_type": "lu", "ts_arkimex_type": arktype})
+        if which == "oracle":
+            kw.update(assembler=OracleAssembler(F, bcs), rhs_assembler=OracleAssembler(G, bcs),
+                      rhs_projection_parameters={"pc_type": "lu"})
+        else:
+            kw.update(rhs_projection_parameters={"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-14})
+        solver = fts.DAESolver(problem, **kw)
+        assert solver.ts.type == "arkimex"
+        solver.ts.setTimeStep(dt)
+        solver.solve()
+        assert solver.ts.getStepNumber() == nsteps
+        finals.append((u.data.detach().cpu().clone(), solver))
+    (uo, _), (ug, s) = finals
+    assert (uo - ug).abs().max() < TRAJ_TOL
+    assert s._ctx.rhs_engine.launch_count > 0 and s._ctx._projected_G.array.is_cuda
+    # G is not the residual of a steady problem: the state really moved
+    assert (ug - s._problem.u_restrict.function_space().interpolate(
+        lambda x: torch.prod(torch.sin(math.pi * x), dim=1) + (x[:, 0] < 0.5).double())).abs().max() > 1e-3

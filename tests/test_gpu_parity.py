@@ -18,6 +18,8 @@ CASES = [
     ("heat", 3, 1, 5), ("heat", 3, 2, 4), ("heat", 3, 3, 3),
     ("bbm", 1, 1, 12), ("bbm", 2, 2, 5), ("bbm", 2, 3, 4), ("bbm", 3, 1, 4), ("bbm", 3, 2, 3), ("bbm", 3, 3, 2),
     ("burgers", 2, 1, 6), ("burgers", 2, 2, 6), ("burgers", 2, 3, 3), ("burgers", 3, 1, 3), ("burgers", 3, 2, 2),
+    ("diffusion", 1, 1, 10), ("diffusion", 1, 3, 5), ("diffusion", 2, 2, 7), ("diffusion", 3, 1, 5),
+    ("diffusion", 3, 2, 4), ("diffusion", 3, 3, 3),
     ("cahn_hilliard", 2, 1, 8), ("cahn_hilliard", 2, 2, 4), ("cahn_hilliard", 3, 1, 3), ("cahn_hilliard", 3, 2, 2),
 ]
 
@@ -195,3 +197,30 @@ def test_pattern_dictionary_compaction():
     assert e1.get_option("plan_compacted") == 1 and e0.get_option("plan_compacted") == 0
     assert e1.get_option("plan_patterns") * 4 <= e1.get_option("plan_blocks")
     assert torch.equal(e1.ijacobian(0.0, x, xd, 10.0), e0.ijacobian(0.0, x, xd, 10.0))
+
+
+@pytest.mark.parametrize("dim,degree,n", [(1, 1, 10), (2, 2, 6), (3, 2, 4)])
+def test_imex_split_forms(dim, degree, n):
+    """the two sides of examples/heat-explicit.py:13-14 on the engine: F = (u_t, v) and
+    G = -((grad u, grad v) - (1, v)) against the oracle, and F - G against the closed-form heat
+    kernels (a different kernel family, so this is not a tautology)."""
+    from firedrake_ts_b200 import forms
+    from firedrake_ts_b200.engine import Engine
+    from oracle import Oracle
+
+    heat, bcs, u, udot = make_problem("heat", dim, degree, n, tile=2)
+    F, G = forms.heat_explicit(u, udot)
+    x, xd = u.data.cuda(), udot.data.cuda()
+    out = {}
+    for name, form in (("F", F), ("G", G), ("heat", heat)):
+        orc, eng = Oracle.from_form(form, bcs), Engine(form, bcs, device="cuda:0")
+        shift = 0.0 if name == "G" else 4.0
+        r = eng.ifunction(0.0, x, xd).cpu().numpy()
+        Jv = eng.ijacobian(0.0, x, xd, shift).cpu().numpy()
+        assert rel_err(r, orc.ifunction(0.0, u.data, udot.data)) < TOL
+        assert rel_err(Jv, orc.ijacobian(0.0, u.data, udot.data, shift)) < TOL
+        out[name] = (r, Jv)
+    assert rel_err(out["F"][0] - out["G"][0], out["heat"][0]) < 1e-11
+    isbc_diag = np.abs(out["F"][1] - out["G"][1] - out["heat"][1])  # Dirichlet rows: 1 - 1 vs 1
+    assert np.sort(isbc_diag)[-1] <= 1.0 + 1e-12 and np.count_nonzero(isbc_diag > 1e-10) == sum(
+        int(b.nodes.numel()) for b in bcs)
