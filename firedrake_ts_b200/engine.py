@@ -24,7 +24,7 @@ SYMBOLS = [
     "fdts_last_error", "fdts_version", "fdts_create", "fdts_destroy", "fdts_sizes", "fdts_get_csr",
     "fdts_get_node_csr", "fdts_set_param", "fdts_set_option", "fdts_get_option", "fdts_ifunction", "fdts_ijacobian",
     "fdts_ifunction_range", "fdts_ijacobian_range", "fdts_ifunction_host", "fdts_ijacobian_host", "fdts_halo_pack",
-    "fdts_halo_unpack", "fdts_launch_count", "fdts_measure_fp64_peak", "fdts_csr_spmv", "fdts_csr_diagonal", "fdts_set_row_blocks",
+    "fdts_halo_unpack", "fdts_launch_count", "fdts_measure_fp64_peak", "fdts_csr_spmv", "fdts_csr_spmv_warp", "fdts_csr_diagonal", "fdts_set_row_blocks",
     "fdts_set_cell_tiles",
 ]
 
@@ -86,6 +86,7 @@ def load_library():
         lib.fdts_set_row_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         lib.fdts_set_cell_tiles.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         lib.fdts_csr_spmv.argtypes = [C.c_int64] + [C.c_void_p] * 6
+        lib.fdts_csr_spmv_warp.argtypes = [C.c_int64] + [C.c_void_p] * 6
         lib.fdts_csr_diagonal.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                           C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         lib.fdts_measure_fp64_peak.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_double)]

@@ -14,15 +14,17 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def csr_spmv(rowptr, colidx, values, x):
+def csr_spmv(rowptr, colidx, values, x, kernel="stream"):
     n = rowptr.numel() - 1
     if values.is_cuda:
         from .engine import _check, load_library
 
         y = torch.empty(n, dtype=torch.float64, device=values.device)
+        lib = load_library()
+        fn = lib.fdts_csr_spmv if kernel == "stream" else lib.fdts_csr_spmv_warp
         with torch.cuda.device(values.device):
-            _check(load_library().fdts_csr_spmv(n, rowptr.data_ptr(), colidx.data_ptr(), values.data_ptr(),
-                                                x.data_ptr(), y.data_ptr(), _stream()), "fdts_csr_spmv")
+            _check(fn(n, rowptr.data_ptr(), colidx.data_ptr(), values.data_ptr(), x.data_ptr(), y.data_ptr(),
+                      _stream()), "fdts_csr_spmv")
         return y
     import scipy.sparse as sp
 
@@ -71,6 +73,34 @@ def pcg(matvec, b, prec, dot, rtol, atol, max_it):
         z = prec(r)
         rz_new = dot(r, z)
         p = z + (rz_new / rz) * p
+        rz = rz_new
+        it += 1
+    return x, it
+
+
+def pcg_device(matvec, b, prec, rtol, atol, max_it, check_every=4, allreduce=None):
+    """PCG with every scalar kept on the device (0-d tensors): no host synchronisation per
+    iteration; the norm is read back every ``check_every`` iterations only.  ``allreduce`` sums a
+    0-d tensor over the ranks (None on one rank).  Same recurrence as :func:`pcg`."""
+    red = allreduce or (lambda t: t)
+    dot = lambda a, c: red(torch.dot(a, c))  # noqa: E731
+    x = torch.zeros_like(b)
+    r = b.clone()
+    z = prec(r)
+    p = z.clone()
+    rz = dot(r, z)
+    tol = max(rtol * float(dot(b, b)) ** 0.5, atol)
+    it = 0
+    while it < max_it:
+        if it % check_every == 0 and float(dot(r, r)) ** 0.5 <= tol:
+            break
+        Ap = matvec(p)
+        alpha = rz / dot(p, Ap)
+        x.addcmul_(p, alpha)
+        r.addcmul_(Ap, -alpha)
+        z = prec(r)
+        rz_new = dot(r, z)
+        p = torch.addcmul(z, p, rz_new / rz)
         rz = rz_new
         it += 1
     return x, it

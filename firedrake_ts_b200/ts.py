@@ -168,7 +168,10 @@ def ksp_solve(A, rhs: torch.Tensor, k, comm=None) -> torch.Tensor:
         prec = lambda r: r * dinv  # noqa: E731
     else:
         prec = lambda r: r  # noqa: E731
-    if k.type == "cg":
+    if k.type == "cg" and rhs.is_cuda:
+        red = None if comm is None else (lambda t: _allreduce_sum(t, comm))
+        x, k.its = linalg.pcg_device(matvec, rhs, prec, k.rtol, k.atol, k.max_it, allreduce=red)
+    elif k.type == "cg":
         x, k.its = linalg.pcg(matvec, rhs, prec, dot, k.rtol, k.atol, k.max_it)
     else:
         x, k.its = linalg.gmres(matvec, rhs, prec, dot, k.rtol, k.atol, k.max_it, k.restart)

@@ -155,6 +155,9 @@ int64_t fdts_launch_count(fdts_handle h);
  * PETSc's MatMult / MatGetDiagonal on the MATAIJCUSPARSE Mat the reference's KSP would hold) */
 int fdts_csr_spmv(int64_t nrows, const int64_t *rowptr, const int32_t *colidx, const double *vals, const double *x,
                   double *y, void *stream);
+/* the same product with one warp per row (kept as the comparison kernel for fdts_csr_spmv's CSR-stream scheme) */
+int fdts_csr_spmv_warp(int64_t nrows, const int64_t *rowptr, const int32_t *colidx, const double *vals,
+                       const double *x, double *y, void *stream);
 int fdts_csr_diagonal(int64_t nrows, const int64_t *rowptr, const int32_t *colidx, const double *vals,
                       int64_t nown_nodes, int64_t nnodes, int32_t ncomp, int32_t layout, double *d, void *stream);
 

@@ -225,3 +225,22 @@ def test_implicit_ts_type_with_G_is_rejected():
                       solver_parameters={"ts_type": "beuler", "pc_type": "lu"})
     with pytest.raises(NotImplementedError):
         s.solve()
+
+
+def test_pcg_device_matches_pcg():
+    """the synchronisation-free PCG (device scalars, periodic convergence check) follows the same
+    recurrence as the reference PCG."""
+    from firedrake_ts_b200 import linalg
+
+    rng = np.random.default_rng(2)
+    n = 60
+    Q = rng.standard_normal((n, n))
+    A = torch.from_numpy(Q @ Q.T + n * np.eye(n))
+    b = torch.from_numpy(rng.standard_normal(n))
+    dinv = 1.0 / torch.diagonal(A)
+    mv, pc = (lambda v: A @ v), (lambda r: r * dinv)
+    x1, it1 = linalg.pcg(mv, b, pc, lambda a, c: float(torch.dot(a, c)), 1e-12, 1e-50, 500)
+    x2, it2 = linalg.pcg_device(mv, b, pc, 1e-12, 1e-50, 500, check_every=4)
+    assert it1 <= it2 < it1 + 4
+    assert (A @ x2 - b).norm() <= 1e-12 * b.norm()
+    assert (x1 - x2).abs().max() < 1e-12
