@@ -237,7 +237,7 @@ extern "C" int fdts_create(const fdts_config *cfg, fdts_handle *out) {
       }
       e->variant = fdts_heat_match_tables(d, cfg->degree, Rh.data());
       // default path: closed form + atomics for the heat family when the tables match
-      e->opt_scatter = (cfg->family == FDTS_HEAT && cfg->ncomp == 1 && e->variant >= 0) ? 1 : 0;
+      e->opt_scatter = ((cfg->family == FDTS_HEAT || cfg->family == FDTS_DIFFUSION) && cfg->ncomp == 1 && e->variant >= 0) ? 1 : 0;
     }
   } while (0);
   cudaFree(tmp_cc);
@@ -258,7 +258,7 @@ extern "C" int fdts_destroy(fdts_handle e) {
   cudaSetDevice(e->device);
   void *ptrs[] = {e->coords, e->cell_coord, e->cell_node, e->B, e->w, e->R, e->M0, e->isbc, e->bc_nodes,
                   e->bc_diag_slot, e->nrowptr, e->ncolidx, e->pos8, e->adj_ptr, e->adj_cell, e->h2d_x, e->h2d_xdot,
-                  e->d_f, e->d_vals, e->cell_rowmask, e->pos8_cm};
+                  e->d_f, e->d_vals, e->cell_rowmask, e->pos8_cm, e->scr_x, e->scr_xdot};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   fdts_free_plan(e);
@@ -454,8 +454,16 @@ extern "C" int fdts_get_option(fdts_handle e, const char *key, int64_t *value) {
   return 1;
 }
 
-static bool use_fast_heat(fdts_engine *e) {
-  return e->opt_scatter >= 1 && e->cfg.family == FDTS_HEAT && e->cfg.ncomp == 1 && e->variant >= 0;
+// closed-form kernels: the heat family, and the diffusion family a (u_t,v) + k (grad u,grad v) - s (1,v) by
+// linearity (fdts_launch_heat).  The diffusion Jacobian with k = 0 (a pure mass matrix) and partial cell
+// ranges of a k != 1 Jacobian stay on the quadrature kernels.
+static bool use_fast_heat(fdts_engine *e, int which = 0, bool full_range = true) {
+  if (!(e->opt_scatter >= 1 && e->cfg.ncomp == 1 && e->variant >= 0)) return false;
+  if (e->cfg.family == FDTS_HEAT) return true;
+  if (e->cfg.family != FDTS_DIFFUSION) return false;
+  if (which == 0) return true;
+  const double k = e->cfg.params[2];
+  return k == 1.0 || (k != 0.0 && full_range);
 }
 
 extern "C" int fdts_ifunction_range(fdts_handle e, double t, const double *x, const double *xdot, double *f,
@@ -502,7 +510,7 @@ extern "C" int fdts_ifunction(fdts_handle e, double t, const double *x, const do
 extern "C" int fdts_ijacobian(fdts_handle e, double t, const double *x, const double *xdot, double shift, double *vals,
                               void *stream) {
   if (!e) return 1;
-  if (use_fast_heat(e)) return fdts_launch_heat(e, 1, x, xdot, shift, vals, 0, e->cfg.num_cells, 3, (cudaStream_t)stream);
+  if (use_fast_heat(e, 1)) return fdts_launch_heat(e, 1, x, xdot, shift, vals, 0, e->cfg.num_cells, 3, (cudaStream_t)stream);
   return fdts_ijacobian_range(e, t, x, xdot, shift, vals, 0, e->cfg.num_cells, 3, stream);
 }
 

@@ -151,6 +151,7 @@ struct fdts_engine {
   int variant = -1;              // which baked RefT table matches cfg.R (-1: none, closed-form path off)
   // scratch
   double *h2d_x = nullptr, *h2d_xdot = nullptr, *d_f = nullptr, *d_vals = nullptr;  // host-variant staging
+  double *scr_x = nullptr, *scr_xdot = nullptr;  // coefficient-scaled states of the diffusion family
   int64_t launches = 0;
   cudaStream_t own_stream = nullptr;
 };

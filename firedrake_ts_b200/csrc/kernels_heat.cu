@@ -670,12 +670,8 @@ int fdts_heat_match_tables(int dim, int deg, const double *R) {
 
 // which: 0 residual, 1 Jacobian.  Full call: zero, assemble, boundary fix-up.
 // flags: bit0 zero the output first (atomic paths), bit1 apply the Dirichlet diagonal afterwards (Jacobian)
-int fdts_launch_heat(fdts_engine *e, int which, const double *x, const double *xdot, double shift, double *out,
-                     int64_t c0, int64_t c1, int flags, cudaStream_t s) {
-  if (e->cfg.family != FDTS_HEAT || e->cfg.ncomp != 1) {
-    fdts_set_error("closed-form path: heat family only");
-    return 3;
-  }
+static int launch_heat_impl(fdts_engine *e, int which, const double *x, const double *xdot, double shift, double *out,
+                            int64_t c0, int64_t c1, int flags, cudaStream_t s) {
   KArgs a = fdts_make_kargs(e, x, xdot, shift, out, c0, c1);
   const int dim = e->cfg.dim, deg = e->cfg.degree, var = e->variant;
   if (e->opt_scatter == 2 && var < 0) {
@@ -792,6 +788,70 @@ int fdts_launch_heat(fdts_engine *e, int which, const double *x, const double *x
   if (rc) return rc;
   e->launches++;
   if (which == 1 && (flags & 2) && e->cfg.num_bc_nodes > 0) {
+    const int64_t n = e->cfg.num_bc_nodes;
+    set_values_k<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, e->bc_diag_slot, n, 1.0);
+    e->launches++;
+  }
+  FDTS_CHECK(cudaGetLastError());
+  return 0;
+}
+
+namespace {
+__global__ void scale_copy_k(const double *__restrict__ in, double *__restrict__ out, int64_t n, double c) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = c * in[i];
+}
+__global__ void scale_inplace_k(double *__restrict__ v, int64_t n, double c) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] *= c;
+}
+}  // namespace
+
+// Heat family: straight through.  Diffusion family  a (u_t, v) + k (grad u, grad v) - s (1, v)
+// (params = (s, a, k); the two sides of the reference's IMEX split, examples/heat-explicit.py:13-14) on the
+// same closed-form kernels by linearity:
+//   residual:  F(u, udot) = F_heat(k u, a udot; source s)        (two scaled copies of the state)
+//   Jacobian:  shift a M + k K = k (shift a / k  M + K)          (k = 1: nothing extra; else one scaling pass
+//                                                                 over the values, Dirichlet diagonal re-set)
+// Both are exact for the coefficients 0 and +-1 of the split.
+int fdts_launch_heat(fdts_engine *e, int which, const double *x, const double *xdot, double shift, double *out,
+                     int64_t c0, int64_t c1, int flags, cudaStream_t s) {
+  if (e->cfg.ncomp != 1 || (e->cfg.family != FDTS_HEAT && e->cfg.family != FDTS_DIFFUSION)) {
+    fdts_set_error("closed-form path: heat / diffusion families only");
+    return 3;
+  }
+  if (e->cfg.family == FDTS_HEAT) return launch_heat_impl(e, which, x, xdot, shift, out, c0, c1, flags, s);
+  const double a = e->cfg.params[1], k = e->cfg.params[2];
+  const int64_t nloc = e->cfg.num_nodes;
+  if (which == 0) {
+    if (a != 1.0 || k != 1.0) {
+      if (!e->scr_x) {
+        FDTS_CHECK(cudaMalloc(&e->scr_x, sizeof(double) * (nloc + 1)));
+        FDTS_CHECK(cudaMalloc(&e->scr_xdot, sizeof(double) * (nloc + 1)));
+      }
+      const unsigned grid = (unsigned)((nloc + 255) / 256);
+      if (k != 1.0) {
+        scale_copy_k<<<grid, 256, 0, s>>>(x, e->scr_x, nloc, k);
+        x = e->scr_x;
+        e->launches++;
+      }
+      if (a != 1.0) {
+        scale_copy_k<<<grid, 256, 0, s>>>(xdot, e->scr_xdot, nloc, a);
+        xdot = e->scr_xdot;
+        e->launches++;
+      }
+    }
+    return launch_heat_impl(e, 0, x, xdot, 0.0, out, c0, c1, flags, s);
+  }
+  if (k == 0.0 || (k != 1.0 && !(c0 == 0 && c1 == e->cfg.num_cells && (flags & 1)))) {
+    fdts_set_error("closed-form diffusion Jacobian: k = 0 or a partial range with k != 1 belongs to the quadrature kernels");
+    return 3;
+  }
+  int rc = launch_heat_impl(e, 1, x, xdot, shift * a / k, out, c0, c1, flags, s);
+  if (rc || k == 1.0) return rc;
+  scale_inplace_k<<<(unsigned)((e->node_nnz + 255) / 256), 256, 0, s>>>(out, e->node_nnz, k);
+  e->launches++;
+  if (e->cfg.num_bc_nodes > 0 && ((flags & 2) || e->opt_scatter == 2)) {
     const int64_t n = e->cfg.num_bc_nodes;
     set_values_k<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, e->bc_diag_slot, n, 1.0);
     e->launches++;

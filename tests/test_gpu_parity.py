@@ -33,7 +33,7 @@ def test_engine_matches_oracle(family, dim, degree, n, tile):
     form, bcs, u, udot = make_problem(family, dim, degree, n, tile=tile)
     orc = Oracle.from_form(form, bcs)
     eng = Engine(form, bcs, device="cuda:0")
-    paths = [0, 1, 2] if family == "heat" else [0]
+    paths = [0, 1, 2] if family in ("heat", "diffusion") else [0]
     # sparsity: bit exact
     rp, ci = orc.pattern()
     grp, gci = eng.csr()

@@ -83,7 +83,7 @@ ms_step = e0.elapsed_time(e1) / max(1, ts.getStepNumber())
 nnz = int(M.values.numel())
 print(json.dumps({
     "workload": f"heat-explicit IMEX split, 3-D P{a.degree} tets UnitCube n={a.n}", "dofs": int(V.num_dofs), "nnz": nnz,
-    "ms_G_assembly_generic_kernel": ms_G, "ms_form_rhs_function": ms_rhs, "projection_cg_iterations": int(its),
+    "ms_G_assembly": ms_G, "ms_form_rhs_function": ms_rhs, "projection_cg_iterations": int(its),
     "projection_rtol": a.rtol, "projection_residual": res, "ms_form_rhs_jacobian": ms_jac,
     "ms_mass_spmv": ms_spmv, "ms_mass_spmv_warp_per_row": ms_spmv_warp, "spmv_GBps": (12.0 * nnz + 16.0 * V.num_dofs) / ms_spmv * 1e-6,
     "ms_arkimex_ars122_step": ms_step, "steps": int(ts.getStepNumber()),
