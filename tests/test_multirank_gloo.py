@@ -57,6 +57,7 @@ def global_matrix(res, nglob):
 
 @pytest.mark.parametrize("family,dim,degree,n,grid,solve", [
     ("heat", 2, 2, 6, (2, 1), True),
+    ("heat", 2, 2, 6, (2, 1), "imex"),
     ("heat", 3, 2, 4, (2, 2, 1), False),
     ("burgers", 2, 2, 4, (2, 1), False),
     ("cahn_hilliard", 2, 1, 6, (1, 2), False),
@@ -108,8 +109,22 @@ def test_partitioned_equals_single_rank(family, dim, degree, n, grid, solve):
     assert Jp.nnz == J1.nnz  # same sparsity pattern, every row assembled by exactly one owner
     if solve:
         import firedrake_ts_b200 as fts
-        problem = fts.DAEProblem(form, u, udot, (0.0, 0.2), bcs=bcs or None)
-        fts.DAESolver(problem, assembler=asm, solver_parameters={"pc_type": "lu", "snes_rtol": 1e-12}).solve()
+        if solve == "imex":
+            from firedrake_ts_b200 import forms
+            from mr_worker import IMEX_DT
+
+            F, G = forms.heat_explicit(u, udot)
+            problem = fts.DAEProblem(F, u, udot, (0.0, 4 * IMEX_DT), bcs=bcs, G=G)
+            s1 = fts.DAESolver(problem, assembler=OracleAssembler(F, bcs), rhs_assembler=OracleAssembler(G, bcs),
+                               solver_parameters={"pc_type": "lu"}, rhs_projection_parameters={"pc_type": "lu"})
+            s1.ts.setTimeStep(IMEX_DT)
+            u0 = u.data.clone()
+            s1.solve()
+            assert s1.ts.getStepNumber() == 4 and all(o["steps"] == 4 for o in res)
+            assert (u.data - u0).abs().max() > 1e-3
+        else:
+            problem = fts.DAEProblem(form, u, udot, (0.0, 0.2), bcs=bcs or None)
+            fts.DAESolver(problem, assembler=asm, solver_parameters={"pc_type": "lu", "snes_rtol": 1e-12}).solve()
         ug = np.zeros(V.num_dofs)
         for r, o in enumerate(res):
             gid = o["gid"].numpy()[:o["nown"]]
