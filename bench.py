@@ -411,6 +411,12 @@ def run_b200(a):
 
 def main():
     a = parse()
+    # stdout carries exactly one JSON line: native libraries that print to file descriptor 1 (NCCL's
+    # version banner under torchrun) are sent to stderr, Python's stdout keeps the original descriptor
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
     if a.impl == "reference":
         return run_reference(a)
     return run_b200(a)
