@@ -131,7 +131,8 @@ class _TSContext:
             if assembler == "b200":
                 from .engine import Engine
 
-                self.rhs_engine = Engine(problem.G, self.bcs_G, device=self._device)
+                self.rhs_engine = Engine(problem.G, self.bcs_G, device=self._device,
+                                         scatter=self.appctx.get("scatter"))
             else:
                 if rhs_assembler is None:
                     raise ValueError("a test assembler for F needs rhs_assembler= for G")

@@ -176,8 +176,8 @@ def test_headline_size_properties(n, degree):
     assert float(F[b].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("arktype,dim,n", [("ars122", 1, 10), ("1", 2, 6)])
-def test_heat_explicit_imex_trajectory(arktype, dim, n):
+@pytest.mark.parametrize("arktype,dim,n,scatter", [("ars122", 1, 10, None), ("1", 2, 6, None), ("ars122", 2, 6, 2)])
+def test_heat_explicit_imex_trajectory(arktype, dim, n, scatter):
     """examples/heat-explicit.py (F = (u_t, v), G = -((grad u, grad v) - (1, v)), ts_type arkimex by
     default) on the B200 engine vs the same stepper driven by the oracle: form_rhs_function with the
     mass-matrix projection (CG + Jacobi on the device CSR vs LU on the CPU), reference
@@ -201,7 +201,21 @@ def test_heat_explicit_imex_trajectory(arktype, dim, n):
                       rhs_projection_parameters={"pc_type": "lu"})
         else:
             kw.update(rhs_projection_parameters={"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-14})
+            if scatter is not None:  # owner-computes gather for F and for G (dG/du through the scaling wrapper)
+                kw["appctx"] = {"scatter": scatter}
         solver = fts.DAESolver(problem, **kw)
+        if which == "b200" and scatter is not None:
+            ctx = solver._ctx
+            assert ctx.rhs_engine.get_option("scatter") == scatter and ctx.rhs_engine.get_option("plan_blocks") > 0
+            from firedrake_ts_b200 import dmhooks
+            from firedrake_ts_b200.ts import Vec
+
+            with dmhooks.add_hooks(solver.ts.getDM(), solver, appctx=ctx):
+                ctx.form_rhs_jacobian(solver.ts, 0.0, Vec(u.owned().clone().to(ctx._device)), ctx._rhs_jac.petscmat,
+                                      ctx._rhs_pjac.petscmat)
+            Jg = ctx._rhs_jac.petscmat.values.cpu().numpy()
+            Jo = OracleAssembler(G, bcs).ijacobian(0.0, u.data.cpu(), u_t.data.cpu(), 0.0).numpy()
+            assert np.abs(Jg - Jo).max() < 1e-12 * np.abs(Jo).max()
         assert solver.ts.type == "arkimex"
         solver.ts.setTimeStep(dt)
         solver.solve()

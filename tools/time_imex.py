@@ -19,6 +19,7 @@ ap.add_argument("-n", type=int, default=96)
 ap.add_argument("--degree", type=int, default=2)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--rtol", type=float, default=1e-10)
+ap.add_argument("--scatter", type=int, default=None)
 a = ap.parse_args()
 
 mesh = fts.UnitCubeMesh(a.n, tile=3, device="cuda")
@@ -29,7 +30,8 @@ bc = fts.DirichletBC(V, 0.0, "on_boundary")
 u.interpolate(lambda x: torch.prod(torch.sin(3.141592653589793 * x), dim=1))
 problem = fts.DAEProblem(F, u, u_t, (0.0, 1.0), bcs=bc, G=G)
 solver = fts.DAESolver(problem, solver_parameters={"ksp_type": "cg", "pc_type": "jacobi"},
-                       rhs_projection_parameters={"ksp_rtol": a.rtol})
+                       rhs_projection_parameters={"ksp_rtol": a.rtol},
+                       appctx={"scatter": a.scatter} if a.scatter is not None else None)
 ctx, ts = solver._ctx, solver.ts
 X = Vec(u.owned().clone().to(ctx._device))
 Gv = Vec(torch.zeros_like(X.array))
@@ -82,7 +84,7 @@ torch.cuda.synchronize()
 ms_step = e0.elapsed_time(e1) / max(1, ts.getStepNumber())
 nnz = int(M.values.numel())
 print(json.dumps({
-    "workload": f"heat-explicit IMEX split, 3-D P{a.degree} tets UnitCube n={a.n}", "dofs": int(V.num_dofs), "nnz": nnz,
+    "scatter": a.scatter, "workload": f"heat-explicit IMEX split, 3-D P{a.degree} tets UnitCube n={a.n}", "dofs": int(V.num_dofs), "nnz": nnz,
     "ms_G_assembly": ms_G, "ms_form_rhs_function": ms_rhs, "projection_cg_iterations": int(its),
     "projection_rtol": a.rtol, "projection_residual": res, "ms_form_rhs_jacobian": ms_jac,
     "ms_mass_spmv": ms_spmv, "ms_mass_spmv_warp_per_row": ms_spmv_warp, "spmv_GBps": (12.0 * nnz + 16.0 * V.num_dofs) / ms_spmv * 1e-6,
