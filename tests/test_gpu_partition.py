@@ -1,0 +1,259 @@
+"""GPU parity of the paths the scaling bench times: the engine on one
+rank's part of a box partition (owned rows x owned+ghost columns, interior / halo cell ranges), the halo
+pack / unpack kernels, the host-buffer entry points, and row blocks of the full-size headline problem
+against the oracle run on the covering cells.
+
+Every partition rank is built on cuda:0 in turn (the profiling recipe forbids ranks that wait for each
+other on one GPU); ghosts are filled from the global state, which is what the exchange delivers.
+Reference: PyOP2's halo exchange triggered at firedrake_ts/solving_utils.py:249-252 and the owner-only
+row assembly behind :258 and :305."""
+import numpy as np
+import pytest
+import torch
+
+from firedrake_ts_b200 import mesh as M
+from firedrake_ts_b200.workloads import make_problem, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _dof_keys(V, nodes_key, n_nodes, glob_nodes):
+    """rank-independent key of every local dof (lexicographic lattice index of the node, component)"""
+    nc = V.ncomp
+    k = nodes_key[:n_nodes]
+    if V.layout == "interleaved":
+        return (k[:, None] * nc + np.arange(nc)[None, :]).reshape(-1)
+    return (np.arange(nc)[:, None] * glob_nodes + k[None, :]).reshape(-1)
+
+
+def _single_rank_reference(family, dim, degree, n, shift):
+    import scipy.sparse as sp
+    from oracle import Oracle
+
+    form, bcs, u, udot = make_problem(family, dim, degree, n, tile=2)
+    V = form.space
+    orc = Oracle.from_form(form, bcs)
+    key = V._lex_key(V.node_lattice).numpy()
+    dk = _dof_keys(V, key, V.num_nodes, V.global_num_nodes)
+    F = orc.ifunction(0.0, u.data, udot.data)
+    rp, ci = orc.pattern()
+    Jv = orc.ijacobian(0.0, u.data, udot.data, shift)
+    ng = V.global_num_nodes * V.ncomp
+    rows = np.repeat(np.arange(len(rp) - 1), np.diff(rp))
+    Jg = sp.csr_matrix((Jv, (dk[rows], dk[ci])), shape=(ng, ng))
+    # keep explicit zeros out of the comparison of values but remember the pattern
+    Pg = sp.csr_matrix((np.ones_like(Jv), (dk[rows], dk[ci])), shape=(ng, ng))
+    Fg = np.zeros(ng)
+    Fg[dk] = F
+    return Fg, Jg, Pg
+
+
+PART_CASES = [
+    ("heat", 3, 2, 6, (2, 2, 2), 6), ("heat", 3, 2, 5, (2, 1, 1), None), ("heat", 2, 2, 8, (2, 1), 6),
+    ("heat", 2, 1, 9, (1, 2), None), ("burgers", 2, 2, 4, (2, 1), None), ("cahn_hilliard", 2, 1, 6, (1, 2), None),
+    ("bbm", 3, 3, 3, (2, 1, 1), None), ("cahn_hilliard", 3, 1, 4, (2, 2, 1), None),
+]
+
+
+@pytest.mark.parametrize("family,dim,degree,n,grid,ftile", PART_CASES)
+def test_partitioned_engine_matches_single_rank_oracle(family, dim, degree, n, grid, ftile):
+    """for every rank of the partition: sparsity of the local CSR bit-exact against the oracle on the
+    same local maps, F and J against the local oracle AND against the single-rank oracle (owned rows,
+    matched through rank-independent node keys), interior + halo cell ranges equal the full call."""
+    import scipy.sparse as sp
+    from firedrake_ts_b200.engine import Engine
+    from oracle import Oracle
+
+    shift = 4.0
+    Fg, Jg, Pg = _single_rank_reference(family, dim, degree, n, shift)
+    world = int(np.prod(grid))
+    seen_rows = np.zeros(Fg.size, dtype=np.int64)
+    for r in range(world):
+        part = M.Partition(tuple(grid), r)
+        form, bcs, u, udot = make_problem(family, dim, degree, n, partition=part, tile=2, ftile=ftile)
+        V = form.space
+        assert V.num_ghost_nodes > 0
+        orc = Oracle.from_form(form, bcs)
+        paths = [0, 1, 2] if family == "heat" else [0]
+        eng = Engine(form, bcs, device="cuda:0", scatter=2 if family == "heat" else None)
+        rp, ci = orc.pattern()
+        grp, gci = eng.csr()
+        assert np.array_equal(grp.cpu().numpy(), rp) and np.array_equal(gci.cpu().numpy(), ci)
+        assert eng.num_rows == V.num_owned_dofs and eng.num_cols == V.num_dofs
+        x, xd = u.data.cuda(), udot.data.cuda()
+        Fo = orc.ifunction(0.0, u.data, udot.data)
+        Jo = orc.ijacobian(0.0, u.data, udot.data, shift)
+        key = V._lex_key(V.node_lattice).numpy()
+        dk_cols = _dof_keys(V, key, V.num_nodes, V.global_num_nodes)
+        dk_rows = _dof_keys(V, key, V.num_owned_nodes, V.global_num_nodes)
+        rows = np.repeat(np.arange(len(rp) - 1), np.diff(rp))
+        for path in paths:
+            eng.set_option("scatter", path)
+            F = eng.ifunction(0.0, x, xd).cpu().numpy()
+            Jv = eng.ijacobian(0.0, x, xd, shift).cpu().numpy()
+            assert rel_err(F, Fo) < TOL and rel_err(Jv, Jo) < TOL, (r, path)
+            assert rel_err(F, Fg[dk_rows]) < TOL, (r, path)
+            Jl = sp.csr_matrix((Jv, (dk_rows[rows], dk_cols[ci])), shape=Jg.shape)
+            sel = np.zeros(Jg.shape[0], dtype=bool)
+            sel[dk_rows] = True
+            D = sp.diags(sel.astype(np.float64))
+            assert abs(Jl - D @ Jg).max() < TOL * abs(Jg).max(), (r, path)
+            # interior cells, then the cells that touch ghosts: the split ifunction_overlapped uses
+            ni, ncell = eng.num_interior_cells, eng.num_cells
+            assert 0 < ni < ncell
+            F2 = torch.empty(eng.num_rows, dtype=torch.float64, device="cuda")
+            eng.ifunction_range(0.0, x, xd, F2, 0, ni, 1)
+            eng.ifunction_range(0.0, x, xd, F2, ni, ncell, 0)
+            assert rel_err(F2.cpu().numpy(), Fo) < TOL, (r, path)
+        # pattern of the owned rows equals the single-rank pattern of the same rows
+        Pl = sp.csr_matrix((np.ones(len(ci)), (dk_rows[rows], dk_cols[ci])), shape=Pg.shape)
+        assert (Pl != D @ Pg).nnz == 0
+        seen_rows[dk_rows] += 1
+        # the interior cells touch no ghost node (that is what makes the overlap legal)
+        cn = V.cell_node_map[: V.mesh.num_interior_cells]
+        assert int(cn.max()) < V.num_owned_nodes
+    assert np.all(seen_rows == 1)  # every global row assembled by exactly one owner
+
+
+@pytest.mark.parametrize("family,dim,degree,n,grid", [("heat", 3, 2, 5, (2, 2, 2)), ("heat", 2, 2, 7, (2, 1)),
+                                                       ("burgers", 2, 2, 5, (2, 2)), ("cahn_hilliard", 2, 1, 7, (2, 2)),
+                                                       ("burgers", 3, 1, 4, (1, 2, 1))])
+def test_halo_pack_unpack_kernels(family, dim, degree, n, grid):
+    """fdts_halo_pack / fdts_halo_unpack against torch indexing (ncomp 1, 2, 3; interleaved and blocked
+    layouts), then a full emulated exchange: what rank s packs for rank r, unpacked into r's ghost tail,
+    restores r's scrambled ghosts bit for bit."""
+    from firedrake_ts_b200.engine import Engine
+
+    world = int(np.prod(grid))
+    spaces, engines, states = [], [], []
+    for r in range(world):
+        form, bcs, u, udot = make_problem(family, dim, degree, n, partition=M.Partition(tuple(grid), r), tile=2)
+        spaces.append(form.space)
+        engines.append(Engine(form, bcs, device="cuda:0"))
+        states.append(u.data.cuda())
+    for r in range(world):
+        V, eng, x = spaces[r], engines[r], states[r]
+        nc = V.ncomp
+        ref = x.clone()
+        for s, idx in V.send_lists.items():  # pack: buffer layout [component][node]
+            idx = idx.cuda()
+            buf = torch.full((idx.numel() * nc,), -1.0, dtype=torch.float64, device="cuda")
+            eng.halo_pack(x, idx, buf)
+            li = idx.long()
+            want = x.view(-1, nc)[li].t() if V.layout == "interleaved" else x.view(nc, -1)[:, li]
+            assert torch.equal(buf.view(nc, -1), want.contiguous())
+        for s, (first, count) in V.recv_slices.items():
+            # the owner packs in the receiver's ghost order
+            Vs, es, xs = spaces[s], engines[s], states[s]
+            idx = Vs.send_lists[r].cuda()
+            assert idx.numel() == count
+            buf = torch.empty(count * nc, dtype=torch.float64, device="cuda")
+            es.halo_pack(xs, idx, buf)
+            for m in range(nc):  # scramble the slice
+                x[V.dof_index(torch.arange(first, first + count), m).cuda()] = -777.0
+            eng.halo_unpack(x, first, count, buf)
+        assert torch.equal(x, ref)
+
+
+@pytest.mark.parametrize("family,dim,degree,n,ftile", [("heat", 3, 2, 6, 6), ("heat", 2, 1, 12, 4), ("bbm", 2, 2, 5, None),
+                                                        ("cahn_hilliard", 2, 1, 8, None)])
+def test_host_entry_points_equal_device_entry_points(family, dim, degree, n, ftile):
+    """fdts_ifunction_host / fdts_ijacobian_host (the e2e path of bench.py: host Vec / Mat storage,
+    copies inside the call) against the device entry points and the oracle."""
+    from firedrake_ts_b200.engine import Engine
+    from oracle import Oracle
+
+    form, bcs, u, udot = make_problem(family, dim, degree, n, tile=2, ftile=ftile)
+    gather = family == "heat"
+    eng = Engine(form, bcs, device="cuda:0", scatter=2 if gather else None)
+    orc = Oracle.from_form(form, bcs)
+    x, xd = u.data.cuda(), udot.data.cuda()
+    Fd = eng.ifunction(0.0, x, xd)
+    Jd = eng.ijacobian(0.0, x, xd, 2.5)
+    for pinned in (True, False):
+        xh, xdh = u.data.clone(), udot.data.clone()
+        Fh = torch.full((eng.num_rows,), 7.0, dtype=torch.float64)
+        Jh = torch.full((eng.nnz,), 7.0, dtype=torch.float64)
+        if pinned:
+            xh, xdh, Fh, Jh = xh.pin_memory(), xdh.pin_memory(), Fh.pin_memory(), Jh.pin_memory()
+        eng.ifunction_host(0.0, xh, xdh, Fh)
+        eng.ijacobian_host(0.0, xh, xdh, 2.5, Jh)
+        if gather:  # write-once gather: bitwise; the atomic residual differs by the order of the adds
+            assert torch.equal(Jh, Jd.cpu())
+        assert rel_err(Jh.numpy(), Jd.cpu().numpy()) < 1e-14
+        assert rel_err(Fh.numpy(), Fd.cpu().numpy()) < 1e-14
+        assert rel_err(Fh.numpy(), orc.ifunction(0.0, u.data, udot.data)) < TOL
+        assert rel_err(Jh.numpy(), orc.ijacobian(0.0, u.data, udot.data, 2.5)) < TOL
+
+
+def covering_subproblem(V, mesh, rows):
+    """cells touching the given node rows, renumbered: the rows first (owned), every other node of
+    those cells after them (ghost columns).  Returns the Oracle keyword arrays and the local->global map."""
+    cn = V.cell_node_map
+    mark = torch.zeros(V.num_nodes, dtype=torch.bool, device=cn.device)
+    mark[rows] = True
+    cells = torch.nonzero(mark[cn.long()].any(dim=1)).reshape(-1)
+    sub = cn[cells].long()
+    nodes = torch.unique(sub)
+    others = nodes[~mark[nodes]]
+    l2g = torch.cat([rows, others])
+    g2l = torch.full((V.num_nodes,), -1, dtype=torch.int64, device=cn.device)
+    g2l[l2g] = torch.arange(l2g.numel(), device=cn.device)
+    cc = mesh.cell_coord_map[cells].long()
+    cnodes = torch.unique(cc)
+    c2l = torch.full((mesh.num_coord_nodes,), -1, dtype=torch.int64, device=cn.device)
+    c2l[cnodes] = torch.arange(cnodes.numel(), device=cn.device)
+    return dict(coords=mesh.coords[cnodes].cpu(), cell_coord=c2l[cc].to(torch.int32).cpu(),
+                cell_node=g2l[sub].to(torch.int32).cpu(), num_nodes=int(l2g.numel()),
+                num_owned_nodes=int(rows.numel())), l2g.cpu()
+
+
+@pytest.mark.parametrize("n,degree", [(184, 2)])
+def test_headline_row_blocks_match_oracle(n, degree):
+    """C4 at full size: rows of F and J of five row blocks (domain corner, face, edge, interior, last
+    block) against the oracle assembled on the cells covering each block; columns matched by global id;
+    sparsity of those rows bit-exact."""
+    from firedrake_ts_b200 import fem
+    from firedrake_ts_b200.engine import Engine
+    from oracle import Oracle
+
+    form, bcs, u, udot = make_problem("heat", 3, degree, n, tile=3, ftile=6, device="cuda:0")
+    V, msh = form.space, form.space.mesh
+    eng = Engine(form, bcs, device="cuda:0", scatter=2)
+    shift = 10.0
+    F = eng.ifunction(0.0, u.data, udot.data)
+    J = eng.ijacobian(0.0, u.data, udot.data, shift)
+    rp, ci = eng.csr()
+    starts = V.row_block_starts()
+    nb = starts.numel() - 1
+    per = int(round(nb ** (1 / 3)))
+    # blocks are numbered with the slowest dimension outermost: pick blocks by their lattice position
+    picks = {"corner": 0, "edge": per // 2, "face": (per // 2) * per + per // 2,
+             "interior": ((per // 2) * per + per // 2) * per + per // 2, "last": nb - 1}
+    et = fem.element_tables(3, degree, form.qdegree, V.variant)
+    isbc = torch.zeros(V.num_nodes, dtype=torch.bool, device="cuda")
+    isbc[bcs[0].nodes.long().cuda()] = True
+    for name, b in picks.items():
+        r0, r1 = int(starts[b]), int(starts[b + 1])
+        rows = torch.arange(r0, r1, device="cuda")
+        kw, l2g = covering_subproblem(V, msh, rows)
+        bc_local = torch.nonzero(isbc[l2g.cuda()]).reshape(-1).to(torch.int32).cpu()
+        orc = Oracle(dim=3, nd=V.nd, ncomp=1, layout="interleaved", family=form.family, params=form.params, B=et.B,
+                     w=et.w, bc_nodes=bc_local, **kw)
+        ul, udl = u.data[l2g.cuda()].cpu(), udot.data[l2g.cuda()].cpu()
+        Fo = orc.ifunction(0.0, ul, udl)
+        assert rel_err(F[r0:r1].cpu().numpy(), Fo) < TOL, name
+        orp, oci = orc.pattern()
+        Jo = orc.ijacobian(0.0, ul, udl, shift)
+        s0, s1 = int(rp[r0]), int(rp[r1])
+        assert np.array_equal((rp[r0:r1 + 1] - s0).cpu().numpy(), orp), name
+        gcols = l2g.numpy()[oci]  # oracle columns in global numbering (sorted by local id inside a row)
+        ecols = ci[s0:s1].cpu().numpy()
+        evals = J[s0:s1].cpu().numpy()
+        rows_l = np.repeat(np.arange(r1 - r0), np.diff(orp))
+        # same column set per row; compare values after sorting both by (row, global column)
+        oo = np.lexsort((gcols, rows_l))
+        assert np.array_equal(gcols[oo], ecols), name
+        assert rel_err(evals, Jo[oo]) < TOL, name
+        assert np.abs(evals).max() > 0
