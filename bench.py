@@ -42,7 +42,10 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("-n", type=int, default=184, help="cubes per edge of the unit cube (184 = headline C4)")
     ap.add_argument("--degree", type=int, default=2)
-    ap.add_argument("--cpu-n", type=int, default=40, help="mesh size of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-n", type=int, default=None,
+                    help="mesh size of the CPU runs (default: --impl reference runs the full configuration -n; "
+                         "the cpu_baseline sample inside the B200 arm uses n=96)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1/C2/C3/C5 record (N=1 only)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-nodict", action="store_true")
@@ -100,9 +103,11 @@ def run_reference(a):
 
     build_oracle()
     cores = os.cpu_count() or 1
-    n = a.cpu_n
-    # bounded sample: at most ~4 timed pairs so that the whole run stays within a few minutes
-    steps, warmup = max(1, min(a.steps, 4)), min(a.warmup, 1)
+    # the SAME configuration as the B200 arm (-n, default 184 = C4); bounded by the number of timed pairs:
+    # one pair of the oracle port takes ~50 s at C4 on 16 cores, so 2 timed pairs + 1 warm-up + set-up
+    # stay within a few minutes
+    n = a.cpu_n or a.n
+    steps, warmup = max(1, min(a.steps, 2 if n > 100 else 4)), (0 if n > 100 else min(a.warmup, 1))
     t, cores = cpu_pair_seconds(n, a.degree, steps, warmup, cores)
     dofs = (a.degree * n + 1) ** 3
     value = dofs * steps / t
@@ -112,7 +117,7 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": 1e3 * t / steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a.n, a.degree), "sample": f"n={n}",
+        "config": {"workload": workload_name(n, a.degree), "sample": f"n={n}, {steps} timed pairs",
                    "note": "restated CPU baseline (not Firedrake: the reference's Firedrake/PETSc stack is not "
                            "installable in this image)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -195,6 +200,70 @@ def algorithmic_bytes(nc, nd, dim, nv, ndofs, nnz, linear=True):
     return ifun, ijac
 
 
+C5_FLOP_PER_CELL = (11040, 110400)  # dense-quadrature convention nq = 46, nd = 20
+
+
+def time_other_configs(dev, hbm_peak, reps=5):
+    """C1, C2, C3, C5 of SURVEY.md section 8(d) on one GPU (the headline line stays C4): ms per call, DOF/s and
+    the roofline fraction of each (HBM bytes for C1-C3, the 8(d) flop convention against the fp64 peak measured
+    on this box for C5)."""
+    import torch
+
+    from firedrake_ts_b200.engine import Engine, measure_fp64_peak
+    from firedrake_ts_b200.workloads import CONFIGS, make_problem
+
+    peak_dfma = measure_fp64_peak(dev.index or 0, False) / 1e3
+    peak_dmma = measure_fp64_peak(dev.index or 0, True) / 1e3
+    out = {"fp64_peak": {"dfma_tflops": peak_dfma, "dmma_tflops": peak_dmma, "how": "fdts_measure_fp64_peak: "
+                         "dependent-free FMA / mma.sync.m8n8k4.f64 chains, all SMs, CUDA events"}}
+    for name in ("C1", "C2", "C3", "C5"):
+        family, dim, degree, n, ftile, foffset, mtile = CONFIGS[name]
+        form, bcs, u, udot = make_problem(family, dim, degree, n, tile=mtile, device=dev, ftile=ftile or None,
+                                          foffset=foffset)
+        V = form.space
+        eng = Engine(form, bcs, device=dev, scatter=2 if (family == "heat" and ftile) else None)
+        x, xd = u.data, udot.data
+        F = torch.empty(eng.num_rows, dtype=torch.float64, device=dev)
+        J = eng.new_values()
+        for _ in range(2):
+            eng.ifunction(0.0, x, xd, out=F)
+            eng.ijacobian(0.0, x, xd, 10.0, out=J)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        for _ in range(reps):
+            eng.ifunction(0.0, x, xd, out=F)
+        ev[1].record()
+        for _ in range(reps):
+            eng.ijacobian(0.0, x, xd, 10.0, out=J)
+        ev[2].record()
+        torch.cuda.synchronize()
+        t_if, t_ij = ev[0].elapsed_time(ev[1]) / reps, ev[1].elapsed_time(ev[2]) / reps
+        nc, nv = V.mesh.num_cells, V.mesh.num_coord_nodes
+        maps = 4 * nc * V.nd + 4 * nc * (dim + 1) + 8 * dim * nv
+        b_if = maps + 3 * 8 * V.num_dofs
+        b_ij = maps + (0 if family == "heat" else 8 * V.num_dofs) + 8 * eng.nnz
+        rec = {"workload": f"{family} P{degree} dim {dim} n={n}: {nc} cells, {V.num_dofs} DOFs, {eng.nnz} non-zeros",
+               "ms_ifunction": t_if, "ms_ijacobian": t_ij, "value": V.num_dofs / ((t_if + t_ij) * 1e-3), "unit": UNIT,
+               "algorithmic_bytes": {"ifunction": b_if, "ijacobian": b_ij}}
+        if name == "C5":
+            fl = [c * nc for c in C5_FLOP_PER_CELL]
+            ach = sum(fl) / ((t_if + t_ij) * 1e-3) / 1e12
+            rec["roofline"] = {"bound": "fp64", "achieved": ach, "peak": max(peak_dfma, peak_dmma), "unit": "TFLOP/s",
+                               "frac": ach / max(peak_dfma, peak_dmma), "algorithmic_flop": {"ifunction": fl[0], "ijacobian": fl[1]},
+                               "ifunction_frac": fl[0] / (t_if * 1e-3) / 1e12 / max(peak_dfma, peak_dmma),
+                               "ijacobian_frac": fl[1] / (t_ij * 1e-3) / 1e12 / max(peak_dfma, peak_dmma)}
+        else:
+            ach = (b_if + b_ij) / ((t_if + t_ij) * 1e-3) / 1e9
+            rec["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                               "ifunction_frac": b_if / (t_if * 1e-3) / 1e9 / hbm_peak,
+                               "ijacobian_frac": b_ij / (t_ij * 1e-3) / 1e9 / hbm_peak}
+        rec["checksum"] = {"sum_F": float(F.sum()), "sum_J": float(J.sum())}
+        out[name] = rec
+        del eng, F, J, form, bcs, u, udot, x, xd, V
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(a):
     import torch
     import torch.distributed as dist
@@ -214,11 +283,13 @@ def run_b200(a):
     cpu_base = None
     if rank == 0 and world == 1 and not a.no_cpu:
         # timed before CUDA work starts (spawned workers; GPU idle)
-        t, cores = cpu_pair_seconds(a.cpu_n, a.degree, 2, 1, os.cpu_count() or 1)
-        d = (a.degree * a.cpu_n + 1) ** 3
+        cn = a.cpu_n or min(a.n, 96)
+        t, cores = cpu_pair_seconds(cn, a.degree, 2, 1, os.cpu_count() or 1)
+        d = (a.degree * cn + 1) ** 3
         cpu_base = {"value": d * 2 / t, "unit": UNIT, "cores": cores, "kind": "port",
                     "sample": f"oracle port (gcc -O3), {cores} processes x 1 thread, slab partition, same form on "
-                              f"UnitCube n={a.cpu_n} ({6 * a.cpu_n ** 3} cells, {d} DOFs), 2 timed pairs, slowest worker"}
+                              f"UnitCube n={cn} ({6 * cn ** 3} cells, {d} DOFs), 2 timed pairs, slowest worker; "
+                              f"the full configuration is timed by --impl reference"}
 
     from firedrake_ts_b200 import mesh as M
     from firedrake_ts_b200.engine import Engine
@@ -388,6 +459,13 @@ def run_b200(a):
     elif world > 1:
         e2e = None
 
+    plan_info = (eng.get_option("plan_blocks"), eng.get_option("plan_patterns")) if ftile else (0, 0)
+    configs = None
+    if world == 1 and not a.no_configs and a.n == 184 and a.degree == 2:
+        del eng, F, x, xd, u, udot, form, bcs, V
+        torch.cuda.empty_cache()
+        configs = time_other_configs(dev, peak)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -396,12 +474,11 @@ def run_b200(a):
             "config": {"workload": workload_name(a.n, a.degree), "partition": "x".join(map(str, M.default_grid(world, 3))),
                        "l2": "inputs >> L2 (126 MB), no flush", "scatter": "closed-form residual + atomics, "
                        "owner-computes gather Jacobian (plan 2: sector SELL + pattern dictionary)", "shift": shift,
-                       "row_blocks": eng.get_option("plan_blocks") if ftile else 0,
-                       "index_patterns": eng.get_option("plan_patterns") if ftile else 0},
+                       "row_blocks": plan_info[0], "index_patterns": plan_info[1]},
             "ms_ifunction": t_if, "ms_ijacobian": t_ij,
             "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": int(launches),
             "checksum": {"sum_F": chk[0], "sum_absF": chk[1], "sum_J": chk[2], "sum_absJ": chk[3]},
-            "clocks": clocks,
+            "clocks": clocks, "configs": configs,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

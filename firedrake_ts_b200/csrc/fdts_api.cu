@@ -374,10 +374,12 @@ extern "C" int fdts_set_option(fdts_handle e, const char *key, int64_t value) {
     e->opt_threads = value;
     return 0;
   }
+#ifdef FDTS_DEV_SWITCHES
   if (!strcmp(key, "debug")) {
     e->opt_debug = value;
     return 0;
   }
+#endif
   if (!strcmp(key, "dedup")) {
     e->opt_dedup = value ? 1 : 0;
     return 0;

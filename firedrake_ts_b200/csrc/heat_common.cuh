@@ -18,9 +18,18 @@ struct G2Args {
   int64_t nblocks;
   double shift;
   int32_t off_idx, off_meta, off_gdst, off_vtab, off_lcc, off_bar, off_desc, zaddr, sector, inA_bytes, stage_bytes;
-  int32_t dbg;  // development only: bit0 skips phase A, bit1 skips phase B (timing experiments; results are wrong)
+#ifdef FDTS_DEV_SWITCHES  // timing experiments only (phases switched off, results wrong); never compiled into the shipped library
+  int32_t dbg;
+#endif
 };
 
+
+// FDTS_DEV(a, bit): development switch `bit` of the launch arguments; constant false in the shipped build
+#ifdef FDTS_DEV_SWITCHES
+#define FDTS_DEV(a, bit) (((a).dbg & (bit)) != 0)
+#else
+#define FDTS_DEV(a, bit) false
+#endif
 
 #ifndef RT_MINB
 #define RT_MINB 4

@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) heat_jacobian_gather2(c
     }
     // ---- phase A
     mbar_wait(&bars[2 + (it & 1)], (uint32_t)((it >> 1) & 1));
-    const int ncell = (a.dbg & 1) ? 0 : d.ncell;
+    const int ncell = FDTS_DEV(a, 1) ? 0 : d.ncell;
     const uint32_t lcc0 = sbase + a.off_lcc + (it & 1) * a.inA_bytes, vt0 = sbase + a.off_vtab + (it & 1) * a.inA_bytes;
     for (int k = threadIdx.x; k < ncell; k += NT) {
       const uint32_t packed = lds_u32(lcc0 + k * 4);
@@ -525,9 +525,9 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) heat_jacobian_gather2(c
     __syncthreads();
     // ---- phase B: class by class, no barrier in between
     if (loadB) mbar_wait(&bars[1], (nloadB - 1u) & 1u);
-    const uint32_t lo = (uint32_t)(d.s0 & (G - 1)), span = (a.dbg & 8) ? 0u : (uint32_t)d.nslots;
+    const uint32_t lo = (uint32_t)(d.s0 & (G - 1)), span = FDTS_DEV(a, 8) ? 0u : (uint32_t)d.nslots;
     double *__restrict__ out = a.out + (d.s0 - lo);
-    const int ncls = (a.dbg & 2) ? 0 : d.ncls;
+    const int ncls = FDTS_DEV(a, 2) ? 0 : d.ncls;
     for (int c = 0; c < ncls; ++c) {
       uint32_t c0, c1;
       asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(c0), "=r"(c1) : "r"(cls0 + c * 8));
@@ -686,7 +686,10 @@ static int launch_heat_impl(fdts_engine *e, int which, const double *x, const do
     const GatherPlan2 &p = e->plan2;
     G2Args g;
     g.bdesc = p.bdesc; g.cidx = p.cidx; g.gdst = p.gdst; g.cmeta = p.cmeta; g.bcc = p.bcc; g.bvcoords = p.bvcoords;
-    g.out = out; g.nblocks = p.nblocks; g.shift = shift; g.dbg = (int32_t)e->opt_debug;
+    g.out = out; g.nblocks = p.nblocks; g.shift = shift;
+#ifdef FDTS_DEV_SWITCHES
+    g.dbg = (int32_t)e->opt_debug;
+#endif
     int rc = 3;
 #define G2CASE(D, K, V)                                                      \
   if (dim == D && deg == K && (K < 3 || var == V)) {                         \

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__((NPW + NCW + 1) * 32, 1) heat_jacobian_gather3
       const int qa = (int)(it % NA);
       mbar_wait(&inA[qa], (uint32_t)((it / NA) & 1));
       const BlockDesc2 &d = sdesc[it % NDESC];
-      const int ncell = (a.dbg & 1) ? 0 : d.ncell;
+      const int ncell = FDTS_DEV(a, 1) ? 0 : d.ncell;
       const uint32_t lcc0 = sbase + a.off_lcc + qa * a.inA_bytes, vt0 = sbase + a.off_vtab + qa * a.inA_bytes;
       const uint32_t stb = sbase + s * a.stage_bytes;
       for (int k = tid; k < ncell; k += NPW * 32) {
@@ -157,10 +157,10 @@ __global__ void __launch_bounds__((NPW + NCW + 1) * 32, 1) heat_jacobian_gather3
         ++nloadB;
         resident = pattern;
       }
-      const uint32_t lo = (uint32_t)(d.s0 & (G - 1)), span = (a.dbg & 8) ? 0u : (uint32_t)d.nslots;
+      const uint32_t lo = (uint32_t)(d.s0 & (G - 1)), span = FDTS_DEV(a, 8) ? 0u : (uint32_t)d.nslots;
       double *__restrict__ out = a.out + (d.s0 - lo);
       const uint32_t stb = sbase + s * a.stage_bytes;
-      const int ncls = (a.dbg & 2) ? 0 : d.ncls;
+      const int ncls = FDTS_DEV(a, 2) ? 0 : d.ncls;
       for (int c = 0; c < ncls; ++c) {
         uint32_t c0, c1;
         asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(c0), "=r"(c1) : "r"(cls0 + c * 8));

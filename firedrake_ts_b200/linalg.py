@@ -95,12 +95,14 @@ def pcg_device(matvec, b, prec, rtol, atol, max_it, check_every=4, allreduce=Non
         if it % check_every == 0 and float(dot(r, r)) ** 0.5 <= tol:
             break
         Ap = matvec(p)
-        alpha = rz / dot(p, Ap)
+        pAp = dot(p, Ap)
+        # an exactly converged iterate between two checks (r = 0, p = 0) must not produce 0/0
+        alpha = torch.where(pAp != 0, rz / pAp, torch.zeros_like(rz))
         x.addcmul_(p, alpha)
         r.addcmul_(Ap, -alpha)
         z = prec(r)
         rz_new = dot(r, z)
-        p = torch.addcmul(z, p, rz_new / rz)
+        p = torch.addcmul(z, p, torch.where(rz != 0, rz_new / rz, torch.zeros_like(rz)))
         rz = rz_new
         it += 1
     return x, it

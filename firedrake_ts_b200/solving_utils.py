@@ -63,11 +63,10 @@ class _TSContext:
                  pre_jacobian_callback=None, pre_function_callback=None,
                  post_jacobian_callback=None, post_function_callback=None,
                  options_prefix=None, transfer_manager=None, assembler="b200", comm=None,
-                 project_rhs=True, rhs_projection_parameters=None, rhs_assembler=None, mass_assembler=None):
+                 project_rhs=True, rhs_projection_parameters=None, rhs_assembler=None, mass_assembler=None,
+                 jac_du_assembler=None, pjac_assembler=None):
         if mat_type not in (None, "aij", "aijcusparse"):
             raise ValueError(f"mat_type {mat_type!r}: the B200 engine assembles monolithic AIJ only")
-        if problem.Jp is not None:
-            raise NotImplementedError("a separate preconditioner form Jp is outside the engine's scope")
         self._problem = problem
         self.mat_type, self.pmat_type = mat_type or "aij", pmat_type or "aij"
         self.appctx = appctx or {}
@@ -92,6 +91,7 @@ class _TSContext:
         self._nullspace = self._nullspace_T = self._near_nullspace = None
         self._splits = {}
         V = self._x.function_space()
+        F_ = problem.F
         self.is_mixed = V.layout == "blocked" and V.ncomp > 1
         dev = self._x.data.device
 
@@ -120,10 +120,38 @@ class _TSContext:
                                       device=self._device)
         # residual Cofunction and Jacobian Matrix stand-ins (base class: _F, _jac, _pjac)
         self._F = Vec(torch.zeros(V.num_owned_dofs, dtype=torch.float64, device=self._device), comm)
-        self._jac = _Assembled(Mat(rowptr, colidx, values, V.num_dofs, halo=self._halo))
+        self._jac = _Assembled(Mat(rowptr, colidx, values, V.num_dofs, halo=self._halo, space=V))
         self._pjac = self._jac
         self._assemble_residual = self._b200_assemble_residual
         self._assemble_jac = self._b200_assemble_jac
+
+        def side_engine(form, test_assembler, what):
+            """an engine of its own for a form that is not F (user J, Jp): same space, same sparsity,
+            same Dirichlet rows"""
+            if form.space is not V:
+                raise ValueError(f"{what} must live on the function space of F")
+            if assembler == "b200":
+                from .engine import Engine
+
+                return Engine(forms.Form(form.family, self._x, self._xdot, form.params), self.bcs_F,
+                              device=self._device, scatter=self.appctx.get("scatter"))
+            if test_assembler is None:
+                raise ValueError(f"a test assembler for F needs an assembler for {what} as well")
+            return test_assembler
+
+        # user-provided J: J = shift * dF/dudot + J_du  (reference ts_solver.py:108)
+        self._jac_du_engine = self._mass_engine = None
+        Ju = getattr(problem, "J_du", None)
+        if Ju is not None and not (Ju.family == F_.family and tuple(Ju.params) == tuple(F_.params)):
+            self._jac_du_engine = side_engine(Ju, jac_du_assembler, "J")
+            self._mass_engine = side_engine(forms.mass_form(F_), mass_assembler, "derivative(F, udot)")
+            self._jac_scratch = torch.zeros_like(values)
+            self._bc_diag_slots = self._find_bc_diagonal_slots(rowptr, colidx, V)
+        # preconditioning form Jp: a Mat of its own, assembled after J (reference :310-312)
+        self._pjac_engine = None
+        if self.Jp is not None:
+            self._pjac_engine = side_engine(self.Jp, pjac_assembler, "Jp")
+            self._pjac = _Assembled(Mat(rowptr, colidx, torch.zeros_like(values), V.num_dofs, halo=self._halo, space=V))
 
         # IMEX branch (reference :104-111): G is assembled by an engine of its own on the same
         # space, so it shares the sparsity and the Dirichlet rows of F
@@ -143,7 +171,7 @@ class _TSContext:
             self._G_vec = Vec(torch.zeros(V.num_owned_dofs, dtype=torch.float64, device=self._device), comm)
             self._projected_G = Vec(torch.zeros_like(self._G_vec.array), comm)
             self._G_or_projected_G = self._projected_G if self.project_rhs else self._G_vec
-            self._rhs_jac = _Assembled(Mat(rowptr, colidx, torch.zeros_like(values), V.num_dofs, halo=self._halo))
+            self._rhs_jac = _Assembled(Mat(rowptr, colidx, torch.zeros_like(values), V.num_dofs, halo=self._halo, space=V))
             self._rhs_pjac = self._rhs_jac
             self._dGdu = self._rhs_jac
             self._rhs_jacobian_assembled = False
@@ -159,11 +187,52 @@ class _TSContext:
 
     def _b200_assemble_jac(self, jac):
         mat = jac.petscmat
+        if self._jac_du_engine is not None:
+            # shift * derivative(F, udot) + J_du: mass matrix of F at the current shift plus the user's
+            # bilinear form (its own udot term switched off); both assemblies put 1 on the Dirichlet diagonal
+            t, x, xd = float(self._time), self._x.data, self._xdot.data
+            self._fill(self._mass_engine.ijacobian(t, x, xd, float(self._shift), out=mat.values), mat.values)
+            self._fill(self._jac_du_engine.ijacobian(t, x, xd, 0.0, out=self._jac_scratch), self._jac_scratch)
+            mat.values.add_(self._jac_scratch)
+            if self._bc_diag_slots.numel():
+                mat.values[self._bc_diag_slots] = 1.0
+            return jac
         out = self.engine.ijacobian(float(self._time), self._x.data, self._xdot.data, float(self._shift),
                                     out=mat.values)
         if out is not mat.values:
             mat.values.copy_(torch.as_tensor(out))
         return jac
+
+    @staticmethod
+    def _fill(out, target):
+        if out is not target:
+            target.copy_(torch.as_tensor(out))
+
+    def _assemble_pjac(self, pjac):
+        """assemble(problem.Jp) into the preconditioning matrix (reference :310-312): the form is taken
+        verbatim, its own shift constant (problem.shift when the user built it from that) applies"""
+        mat = pjac.petscmat
+        sh = self.Jp.shift if self.Jp.shift is not None else self._shift
+        self._fill(self._pjac_engine.ijacobian(float(self._time), self._x.data, self._xdot.data, float(sh),
+                                               out=mat.values), mat.values)
+        return pjac
+
+    def _find_bc_diagonal_slots(self, rowptr, colidx, V):
+        """CSR slots of the diagonal entries of the Dirichlet rows (owned dofs)"""
+        nodes = [bc.nodes.to(torch.int64) for bc in self.bcs_F]
+        if not nodes:
+            return torch.zeros(0, dtype=torch.int64, device=rowptr.device)
+        nodes = torch.unique(torch.cat(nodes))
+        nodes = nodes[nodes < V.num_owned_nodes].to(rowptr.device)
+        slots = []
+        for m in range(V.ncomp):
+            rows = V.dof_index(nodes, m, V.num_owned_nodes)
+            cols = V.dof_index(nodes, m)
+            for r, c in zip(rows.tolist(), cols.tolist()):
+                seg = colidx[int(rowptr[r]):int(rowptr[r + 1])]
+                k = int(torch.nonzero(seg == c)[0])
+                slots.append(int(rowptr[r]) + k)
+        return torch.tensor(slots, dtype=torch.int64, device=rowptr.device)
 
     def _refresh_halo(self):
         if self._halo is not None:
@@ -231,7 +300,7 @@ class _TSContext:
             out = eng.ijacobian(0.0, self._x.data, self._xdot.data, 1.0, out=vals)
             if out is not vals:
                 vals.copy_(torch.as_tensor(out))
-            M = Mat(base.rowptr, base.colidx, vals, base.ncols, halo=self._halo)
+            M = Mat(base.rowptr, base.colidx, vals, base.ncols, halo=self._halo, space=self._x.function_space())
             k = KSP()
             k.type, k.pc_type, k.rtol, k.atol = "cg", "jacobi", 1e-12, 1e-50
             o = dict(self.rhs_projection_parameters or {})
@@ -260,9 +329,13 @@ class _TSContext:
                 self._rhs_projection_solver.solve(self._projected_G, self._G_vec)
 
     def set_nullspace(self, nullspace, ises=None, transpose=False, near=False):
+        # three separate attachments, as MatSetNullSpace / MatSetTransposeNullSpace / MatSetNearNullSpace
+        # keep them (reference solving_utils.py:314-317 re-attaches all three after every assembly)
         if nullspace is None:
             return
-        self._jac.petscmat._nullspace = nullspace
+        attr = "_near_nullspace" if near else ("_transpose_nullspace" if transpose else "_nullspace")
+        for mat in {id(self._jac.petscmat): self._jac.petscmat, id(self._pjac.petscmat): self._pjac.petscmat}.values():
+            setattr(mat, attr, nullspace)
 
     # -- callbacks (reference :236-317) ------------------------------------------------------
     @staticmethod
@@ -381,6 +454,10 @@ class _TSContext:
 
         if ctx._post_jacobian_callback is not None:
             ctx._post_jacobian_callback(X, Xdot, J)
+
+        if ctx.Jp is not None:
+            assert P.handle == ctx._pjac.petscmat.handle
+            ctx._assemble_pjac(ctx._pjac)
 
         ctx.set_nullspace(ctx._nullspace, None, transpose=False, near=False)
         ctx.set_nullspace(ctx._nullspace_T, None, transpose=True, near=False)

@@ -70,12 +70,18 @@ class Mat:
     engine fills in place (``assert J.handle == ctx._jac.petscmat.handle``,
     firedrake_ts/solving_utils.py:284)."""
 
-    def __init__(self, rowptr, colidx, values, ncols, halo=None):
+    def __init__(self, rowptr, colidx, values, ncols, halo=None, space=None):
         self.rowptr, self.colidx, self.values = rowptr, colidx, values
         self.nrows = rowptr.numel() - 1
         self.ncols = ncols
         self.halo = halo  # forward exchange for the off-process columns (None on one rank)
-        self._nullspace = None
+        # dof layout of the rows / columns (local column of owned dof (m, i) is m*num_nodes + i for a
+        # blocked space on a partition): needed to find the diagonal
+        self.ncomp = 1 if space is None else space.ncomp
+        self.layout = 0 if space is None or space.layout == "interleaved" else 1
+        self.num_owned_nodes = self.nrows // self.ncomp if space is None else space.num_owned_nodes
+        self.num_nodes = self.num_owned_nodes if space is None else space.num_nodes
+        self._nullspace = self._transpose_nullspace = self._near_nullspace = None
         self._lu = None
 
     @property
@@ -103,7 +109,8 @@ class Mat:
     def diagonal(self):
         from . import linalg
 
-        return linalg.csr_diagonal(self.rowptr, self.colidx, self.values)
+        return linalg.csr_diagonal(self.rowptr, self.colidx, self.values, self.num_owned_nodes, self.num_nodes,
+                                   self.ncomp, self.layout)
 
 
 class DM:
@@ -139,11 +146,16 @@ class ConvergedReason:
     DIVERGED_STEP_REJECTED = -2
 
 
-def ksp_solve(A, rhs: torch.Tensor, k, comm=None) -> torch.Tensor:
+def ksp_solve(A, rhs: torch.Tensor, k, comm=None, P=None) -> torch.Tensor:
     """Solve A x = rhs with the Krylov method / preconditioner named by the KSP ``k``
-    (cg | gmres, jacobi | none | lu).  Shared by the Newton step and by the right-hand-side
-    projection solver (reference solving_utils.py:429-458)."""
+    (cg | gmres | preonly, jacobi | none | lu).  The preconditioner is built from ``P`` when the
+    caller registered a separate preconditioning matrix (``Jp``, reference solving_utils.py:120-122,
+    310-312), otherwise from ``A``.  Shared by the Newton step and by the right-hand-side projection
+    solver (reference solving_utils.py:429-458)."""
     from . import linalg
+
+    if P is None:
+        P = A
 
     def to_local(v):
         return v if A.halo is None else A.halo.owned_to_local(v)
@@ -159,15 +171,33 @@ def ksp_solve(A, rhs: torch.Tensor, k, comm=None) -> torch.Tensor:
         import numpy as np
         import scipy.sparse.linalg as spla
 
-        lu = spla.splu(A.to_scipy().tocsc())
-        sol = lu.solve(rhs.cpu().numpy())
-        k.its = 1
-        return torch.from_numpy(np.ascontiguousarray(sol)).to(rhs.device)
+        lu = spla.splu(P.to_scipy().tocsc())
+
+        def lu_apply(r):
+            return torch.from_numpy(np.ascontiguousarray(lu.solve(r.cpu().numpy()))).to(r.device)
+
+        if P is A or k.type == "preonly":  # direct solve (with P != A: one application of P^-1, as PETSc's preonly)
+            k.its = 1
+            return lu_apply(rhs)
+        x, k.its = linalg.gmres(matvec, rhs, lu_apply, dot, k.rtol, k.atol, k.max_it, k.restart)
+        return x
+    if k.type not in ("cg", "gmres", "preonly"):
+        raise NotImplementedError(f"ksp_type {k.type!r}: the stand-in KSP knows cg, gmres (and preonly with pc_type lu)")
+    if k.type == "preonly":
+        raise NotImplementedError("ksp_type preonly needs pc_type lu")
+    if any(ns is not None for ns in (A._nullspace, A._transpose_nullspace)):
+        raise NotImplementedError("nullspace projection is not part of the stand-in KSP (PETSc's KSP applies it in "
+                                  "the real stack); attach no nullspace or solve with the Firedrake adapter")
     if k.pc_type == "jacobi":
-        dinv = 1.0 / A.diagonal()
+        d = P.diagonal()
+        if bool((d == 0).any()):
+            raise ZeroDivisionError("pc_type jacobi: the matrix has a zero diagonal entry")
+        dinv = 1.0 / d
         prec = lambda r: r * dinv  # noqa: E731
-    else:
+    elif k.pc_type == "none":
         prec = lambda r: r  # noqa: E731
+    else:
+        raise NotImplementedError(f"pc_type {k.pc_type!r}: the stand-in KSP knows jacobi, none and lu")
     if k.type == "cg" and rhs.is_cuda:
         red = None if comm is None else (lambda t: _allreduce_sum(t, comm))
         x, k.its = linalg.pcg_device(matvec, rhs, prec, k.rtol, k.atol, k.max_it, allreduce=red)
@@ -219,6 +249,10 @@ class TS:
         self.equation_type = None
         self.newton_its = 0
         self.linear_its = 0
+
+    def _reached_end(self):
+        """end-time test with an absolute-plus-relative tolerance tied to the step (works for max_time <= 0)"""
+        return self.time >= self.max_time - 1e-12 * max(abs(self.dt), 1e-300) - 1e-14 * abs(self.max_time)
 
     # -- PETSc-like setters / getters -------------------------------------------
     def create(self, comm=None):
@@ -317,7 +351,7 @@ class TS:
 
     # -- linear solve ---------------------------------------------------------------
     def _linear_solve(self, rhs: torch.Tensor) -> torch.Tensor:
-        return ksp_solve(self._J, rhs, self.snes.ksp, self.comm)
+        return ksp_solve(self._J, rhs, self.snes.ksp, self.comm, P=self._P)
 
     # -- the integrator ---------------------------------------------------------------
     def _stage_solve(self, X: Vec, X0: torch.Tensor, ts_time: float, shift: float):
@@ -366,7 +400,7 @@ class TS:
         ct = [sum(row) for row in At]
         Y = Vec(u.array.clone(), self.comm)
         G = self._G if self._G is not None else Y.duplicate()
-        while self.time < self.max_time * (1 - 1e-14) and self.steps < self.max_steps:
+        while not self._reached_end() and self.steps < self.max_steps:
             h = self.dt
             if self.exact_final_time == "matchstep" and self.time + h > self.max_time:
                 h = self.max_time - self.time
@@ -415,14 +449,14 @@ class TS:
                 self._monitor(self, self.steps, self.time, u)
             self._solve_arkimex(u)
             if self.reason == 0:
-                self.reason = (ConvergedReason.CONVERGED_TIME if self.time >= self.max_time * (1 - 1e-14)
+                self.reason = (ConvergedReason.CONVERGED_TIME if self._reached_end()
                                else ConvergedReason.CONVERGED_ITS)
             return
         theta = self.theta
         if self._monitor:
             self._monitor(self, self.steps, self.time, u)
         X = Vec(u.array.clone(), self.comm)
-        while self.time < self.max_time * (1 - 1e-14) and self.steps < self.max_steps:
+        while not self._reached_end() and self.steps < self.max_steps:
             dt = self.dt
             if self.exact_final_time == "matchstep" and self.time + dt > self.max_time:
                 dt = self.max_time - self.time
@@ -441,4 +475,4 @@ class TS:
             self.steps += 1
             if self._monitor:
                 self._monitor(self, self.steps, self.time, u)
-        self.reason = ConvergedReason.CONVERGED_TIME if self.time >= self.max_time * (1 - 1e-14) else ConvergedReason.CONVERGED_ITS
+        self.reason = ConvergedReason.CONVERGED_TIME if self._reached_end() else ConvergedReason.CONVERGED_ITS

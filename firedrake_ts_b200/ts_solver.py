@@ -90,7 +90,15 @@ class DAEProblem(object):
 
         # Use the user-provided Jacobian. If none is provided, derive the Jacobian from the residual
         # (reference ts_solver.py:108: J = shift*derivative(F, udot) + derivative(F, u)).
-        self.J = J or (forms.derivative(F, self.shift) if isinstance(F, forms.Form) else None)
+        # A user-provided J replaces dF/du only; the shift * dF/dudot term always comes from F.  Catalogue
+        # forms carry no symbolic sum, so the user's part is kept beside the total (J_du) and the context
+        # assembles shift * M_F + J_du.
+        self.J_du = J
+        if J is not None and not isinstance(J, forms.Form):
+            raise TypeError("Provided Jacobian is a '%s', not a BaseForm or Slate Tensor" % type(J).__name__)
+        if J is not None and len(J.arguments()) != 2:
+            raise ValueError("Provided Jacobian is not a bilinear form")
+        self.J = forms.derivative(F, self.shift) if isinstance(F, forms.Form) else J
         # reference ts_solver.py:111: dGdu = derivative(G, u)  (no udot term: shift 0)
         self.dGdu = forms.derivative(G, Constant(0.0)) if isinstance(G, forms.Form) else None
 
@@ -185,7 +193,8 @@ class DAESolver(OptionsManager):
                          options_prefix=self.options_prefix, assembler=kwargs.get("assembler", "b200"), comm=comm,
                          project_rhs=kwargs.get("project_rhs", True),
                          rhs_projection_parameters=kwargs.get("rhs_projection_parameters"),
-                         rhs_assembler=kwargs.get("rhs_assembler"), mass_assembler=kwargs.get("mass_assembler"))
+                         rhs_assembler=kwargs.get("rhs_assembler"), mass_assembler=kwargs.get("mass_assembler"),
+                         jac_du_assembler=kwargs.get("jac_du_assembler"), pjac_assembler=kwargs.get("pjac_assembler"))
 
         if ctx.is_mixed:
             # Mixed problem, use jacobi pc if user has not supplied one.

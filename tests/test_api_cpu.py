@@ -177,3 +177,117 @@ def test_krylov_path_agrees_with_direct():
                       solver_parameters={"ksp_type": ksp, "pc_type": "jacobi", "ksp_rtol": 1e-13,
                                          "snes_rtol": 1e-12}).solve()
         assert (u.data - ref).abs().max() < 1e-10
+
+
+def test_user_jacobian_replaces_dF_du_only():
+    """reference ts_solver.py:108: J = shift*derivative(F, udot) + (J or derivative(F, u)).  A user J
+    built from a different stiffness (an approximate Jacobian) changes the matrix but, being only the
+    Newton matrix of a linear problem, not the converged solution."""
+    V, u, u_t, F, bc = heat_1d(12, 2)
+    u.interpolate(lambda x: torch.sin(math.pi * x[:, 0]))
+    u0 = u.data.clone()
+    fts.DAESolver(fts.DAEProblem(F, u, u_t, (0.0, 0.2), bcs=bc), assembler=OracleAssembler(F, [bc]),
+                  solver_parameters=LU).solve()
+    ref = u.data.clone()
+    u.data.copy_(u0)
+    Ku = forms.diffusion(u, u_t, mass=0.0, diffusivity=1.3)  # 30 % too stiff
+    Ju = forms.derivative(Ku, fts.Constant(0.0))
+    problem = fts.DAEProblem(F, u, u_t, (0.0, 0.2), bcs=bc, J=Ju)
+    assert problem.J_du is Ju and len(problem.J.arguments()) == 2
+    s = fts.DAESolver(problem, assembler=OracleAssembler(F, [bc]), jac_du_assembler=OracleAssembler(Ku, [bc]),
+                      mass_assembler=OracleAssembler(forms.mass_form(F), [bc]),
+                      solver_parameters={"pc_type": "lu", "snes_rtol": 1e-14, "snes_atol": 1e-16, "snes_stol": 0.0,
+                                         "snes_max_it": 200})
+    s.solve()
+    assert (u.data - ref).abs().max() < 1e-10
+    assert s.ts.newton_its > s.ts.getStepNumber()  # the inexact matrix needs more than one Newton step
+    # the assembled matrix is shift*M + 1.3 K with unit Dirichlet diagonal
+    A = s._ctx._jac.petscmat.to_scipy().toarray()
+    shift = float(problem.shift)
+    Mm = OracleAssembler(forms.mass_form(F), [bc]).ijacobian(0.0, u.data, u_t.data, 1.0)
+    Kk = OracleAssembler(Ku, [bc]).ijacobian(0.0, u.data, u_t.data, 0.0)
+    import scipy.sparse as sp
+    rp, ci = OracleAssembler(F, [bc]).pattern()
+    want = sp.csr_matrix((shift * Mm.numpy() + Kk.numpy(), ci, rp)).toarray()
+    b = bc.nodes.long()
+    want[b, b] = 1.0
+    assert np.abs(A - want).max() < 1e-12 * np.abs(want).max()
+    with pytest.raises(TypeError, match="Provided Jacobian"):
+        fts.DAEProblem(F, u, u_t, (0, 1), J="J")
+    with pytest.raises(ValueError, match="not a bilinear form"):
+        fts.DAEProblem(F, u, u_t, (0, 1), J=Ku)
+
+
+def test_preconditioner_form_Jp_fills_P():
+    """reference solving_utils.py:120-122, 310-312: Jp is assembled into its own Mat P after J, and the
+    KSP builds its preconditioner from P (here: LU of a lumped-stiffness-like operator inside GMRES)."""
+    V, u, u_t, F, bc = heat_1d(12, 2)
+    u.interpolate(lambda x: torch.sin(math.pi * x[:, 0]))
+    u0 = u.data.clone()
+    fts.DAESolver(fts.DAEProblem(F, u, u_t, (0.0, 0.2), bcs=bc), assembler=OracleAssembler(F, [bc]),
+                  solver_parameters=LU).solve()
+    ref = u.data.clone()
+    u.data.copy_(u0)
+    problem = fts.DAEProblem(F, u, u_t, (0.0, 0.2), bcs=bc)
+    Pf = forms.diffusion(u, u_t, mass=1.0, diffusivity=0.8)
+    problem = fts.DAEProblem(F, u, u_t, (0.0, 0.2), bcs=bc, Jp=forms.derivative(Pf, None))
+    assert not problem.Jp_eq_J
+    seen = []
+    s = fts.DAESolver(problem, assembler=OracleAssembler(F, [bc]), pjac_assembler=OracleAssembler(Pf, [bc]),
+                      post_jacobian_callback=lambda X, Xdot, J: seen.append(J),
+                      solver_parameters={"ksp_type": "gmres", "pc_type": "lu", "ksp_rtol": 1e-14, "snes_rtol": 1e-13})
+    ctx = s._ctx
+    assert ctx._pjac is not ctx._jac and ctx._pjac.petscmat.handle != ctx._jac.petscmat.handle
+    s.solve()
+    assert (u.data - ref).abs().max() < 1e-10
+    assert s.ts.linear_its > s.ts.newton_its  # P != J: GMRES needs more than one iteration
+    shift = float(problem.shift)
+    Pw = OracleAssembler(Pf, [bc]).ijacobian(0.0, u.data, u_t.data, shift).numpy()
+    assert np.abs(ctx._pjac.petscmat.values.numpy() - Pw).max() < 1e-13 * np.abs(Pw).max()
+    assert seen and all(J is ctx._jac.petscmat for J in seen)
+    with pytest.raises(ValueError, match="preconditioner is not a bilinear form"):
+        fts.DAEProblem(F, u, u_t, (0, 1), Jp=Pf)
+
+
+def test_unknown_solver_options_and_nullspaces_are_rejected():
+    V, u, u_t, F, bc = heat_1d(8, 1)
+    for bad in ({"pc_type": "hypre"}, {"pc_type": "fieldsplit"}, {"ksp_type": "bcgs", "pc_type": "jacobi"}):
+        u.data.zero_()
+        s = fts.DAESolver(fts.DAEProblem(F, u, u_t, (0.0, 0.1), bcs=bc), assembler=OracleAssembler(F, [bc]),
+                          solver_parameters=bad)
+        with pytest.raises(NotImplementedError):
+            s.solve()
+    ns = object()
+    s = fts.DAESolver(fts.DAEProblem(F, u, u_t, (0.0, 0.1), bcs=bc), assembler=OracleAssembler(F, [bc]),
+                      nullspace=ns, near_nullspace="near", solver_parameters={"ksp_type": "cg", "pc_type": "jacobi"})
+    m = s._ctx._jac.petscmat
+    assert m._nullspace is ns and m._near_nullspace == "near" and m._transpose_nullspace is None
+    with pytest.raises(NotImplementedError, match="nullspace"):
+        s.solve()
+
+
+def test_negative_time_span_takes_the_right_number_of_steps():
+    V, u, u_t, F, bc = heat_1d(8, 1)
+    s = fts.DAESolver(fts.DAEProblem(F, u, u_t, (-1.0, 0.0), bcs=bc), assembler=OracleAssembler(F, [bc]),
+                      solver_parameters=LU)
+    s.solve()
+    assert s.ts.getStepNumber() == 10 and abs(s.ts.getTime()) < 1e-12
+
+
+def test_mat_diagonal_of_blocked_space_on_a_partition():
+    """local column of owned dof (m, i) is m*num_nodes + i, not m*num_owned + i"""
+    from firedrake_ts_b200 import mesh as M
+    from firedrake_ts_b200.ts import Mat
+    from firedrake_ts_b200.workloads import make_problem
+
+    form, bcs, u, udot = make_problem("cahn_hilliard", 2, 1, 6, partition=M.Partition((2, 1), 0))
+    V = form.space
+    asm = OracleAssembler(form, bcs)
+    rp, ci = asm.pattern()
+    vals = asm.ijacobian(0.0, u.data, udot.data, 3.0)
+    A = Mat(torch.from_numpy(rp), torch.from_numpy(ci), vals, V.num_dofs, space=V)
+    d = A.diagonal().numpy()
+    dense = A.to_scipy().toarray()
+    nown, nn = V.num_owned_nodes, V.num_nodes
+    want = np.array([dense[m * nown + i, m * nn + i] for m in range(2) for i in range(nown)])
+    assert np.array_equal(d, want) and np.all(d[:nown] != 0)
