@@ -46,6 +46,9 @@ def parse():
                     help="mesh size of the CPU runs (default: --impl reference runs the full configuration -n; "
                          "the cpu_baseline sample inside the B200 arm uses n=96)")
     ap.add_argument("--no-configs", action="store_true", help="skip the C1/C2/C3/C5 record (N=1 only)")
+    ap.add_argument("--halo", default="native", choices=["native", "python"],
+                    help="N > 1: ghost exchange inside the library (fdts_ifunction_exchange, default) or driven from "
+                         "Python through torch.distributed P2P ops (round-1 path, kept for comparison)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-nodict", action="store_true")
@@ -217,6 +220,21 @@ def time_other_configs(dev, hbm_peak, reps=5):
     out = {"fp64_peak": {"dfma_tflops": peak_dfma, "dmma_tflops": peak_dmma, "how": "fdts_measure_fp64_peak: "
                          "dependent-free FMA / mma.sync.m8n8k4.f64 chains, all SMs, CUDA events"}}
     for name in ("C1", "C2", "C3", "C5"):
+        try:
+            out[name] = _time_config(name, dev, hbm_peak, peak_dfma, peak_dmma, reps)
+        except Exception as exc:  # a failing side configuration must not take the headline line down
+            out[name] = {"error": f"{type(exc).__name__}: {exc}"}
+        torch.cuda.empty_cache()
+    return out
+
+
+def _time_config(name, dev, hbm_peak, peak_dfma, peak_dmma, reps):
+    import torch
+
+    from firedrake_ts_b200.engine import Engine
+    from firedrake_ts_b200.workloads import CONFIGS, make_problem
+
+    if True:
         family, dim, degree, n, ftile, foffset, mtile = CONFIGS[name]
         form, bcs, u, udot = make_problem(family, dim, degree, n, tile=mtile, device=dev, ftile=ftile or None,
                                           foffset=foffset)
@@ -258,10 +276,7 @@ def time_other_configs(dev, hbm_peak, reps=5):
                                "ifunction_frac": b_if / (t_if * 1e-3) / 1e9 / hbm_peak,
                                "ijacobian_frac": b_ij / (t_ij * 1e-3) / 1e9 / hbm_peak}
         rec["checksum"] = {"sum_F": float(F.sum()), "sum_J": float(J.sum())}
-        out[name] = rec
-        del eng, F, J, form, bcs, u, udot, x, xd, V
-        torch.cuda.empty_cache()
-    return out
+        return rec
 
 
 def run_b200(a):
@@ -303,6 +318,15 @@ def run_b200(a):
     V = form.space
     eng = Engine(form, bcs, device=dev, scatter=2 if ftile else 1)
     halo = HaloExchange(V, eng, group=group, device=dev) if world > 1 else None
+    native = world > 1 and a.halo == "native"
+    if native:
+        eng.halo_setup(group)  # the library's own NCCL communicator: exchange fused with the residual
+
+    def residual_with_exchange():
+        if native:
+            eng.ifunction_exchange(0.0, x, xd, out=F)
+        else:
+            eng.ifunction_overlapped(0.0, x, xd, halo, out=F)
     x, xd = u.data, udot.data
     F = torch.empty(eng.num_rows, dtype=torch.float64, device=dev)
     J = eng.new_values()
@@ -310,7 +334,7 @@ def run_b200(a):
 
     def step():
         if halo is not None:  # ghost exchange hidden behind the interior cells of the residual
-            eng.ifunction_overlapped(0.0, x, xd, halo, out=F)
+            residual_with_exchange()
         else:
             eng.ifunction(0.0, x, xd, out=F)
         eng.ijacobian(0.0, x, xd, shift, out=J)
@@ -334,7 +358,7 @@ def run_b200(a):
     for k in range(a.steps):
         ev[k][0].record()
         if halo is not None:
-            eng.ifunction_overlapped(0.0, x, xd, halo, out=F)
+            residual_with_exchange()
         else:
             eng.ifunction(0.0, x, xd, out=F)
         ev[k][1].record()
@@ -435,7 +459,7 @@ def run_b200(a):
         def e2e_step():
             x[:nown].copy_(xh, non_blocking=True)
             xd[:nown].copy_(xdh, non_blocking=True)
-            eng.ifunction_overlapped(0.0, x, xd, halo, out=F)
+            residual_with_exchange()
             Fh.copy_(F, non_blocking=True)
             eng.ijacobian(0.0, x, xd, shift, out=J)
             Jh.copy_(J, non_blocking=True)
@@ -472,7 +496,7 @@ def run_b200(a):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a.n, a.degree), "partition": "x".join(map(str, M.default_grid(world, 3))),
-                       "l2": "inputs >> L2 (126 MB), no flush", "scatter": "closed-form residual + atomics, "
+                       "l2": "inputs >> L2 (126 MB), no flush", "halo": (a.halo if world > 1 else None), "scatter": "closed-form residual + atomics, "
                        "owner-computes gather Jacobian (plan 2: sector SELL + pattern dictionary)", "shift": shift,
                        "row_blocks": plan_info[0], "index_patterns": plan_info[1]},
             "ms_ifunction": t_if, "ms_ijacobian": t_ij,

@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["fdts_api.cu", "pattern.cu", "inst_heat.cu", "inst_bbm.cu", "inst_burgers.cu", "inst_ch.cu", "inst_diffusion.cu",
-           "kernels_heat.cu", "kernels_heat2.cu", "microbench.cu", "linalg.cu", "gather_plan.cu", "kernels_dmma.cu"]
+           "kernels_heat.cu", "kernels_heat2.cu", "microbench.cu", "linalg.cu", "gather_plan.cu", "kernels_dmma.cu", "halo_nccl.cu"]
 HEADERS = ["fdts_common.cuh", "kernels_generic.cuh", "kargs.cuh", "ref_tables.cuh", "heat_common.cuh",
            "../../include/fdts.h"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -44,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs = list(ex.map(_compile, SOURCES))
     if _stale(LIB, objs):
         subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-                               "-lcudart"])
+                               "-lcudart", "-ldl"])
         if verbose:
             print("linked", LIB)
     return LIB

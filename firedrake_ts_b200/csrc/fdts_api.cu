@@ -264,6 +264,7 @@ extern "C" int fdts_destroy(fdts_handle e) {
   fdts_free_plan(e);
   fdts_free_plan2(e);
   fdts_free_rplan(e);
+  fdts_free_halo(e);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
   return 0;

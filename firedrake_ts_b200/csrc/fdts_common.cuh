@@ -106,7 +106,10 @@ struct ResidualPlan {
   int64_t unique_patterns = 0;
 };
 
+struct fdts_halo;  // halo_nccl.cu
+
 struct fdts_engine {
+  fdts_halo *halo = nullptr;  // NCCL ghost exchange state (fdts_halo_setup)
   fdts_config cfg;  // scalars only are meaningful after create; pointers below are device copies
   int device = 0;
   // mesh / maps (device)
@@ -184,6 +187,7 @@ void fdts_free_plan(fdts_engine *e);
 void fdts_free_plan2(fdts_engine *e);
 int fdts_build_rplan(fdts_engine *e, const int64_t *tile_starts_host, int64_t ntiles);
 void fdts_free_rplan(fdts_engine *e);
+void fdts_free_halo(fdts_engine *e);
 
 // ------------------------------------------------------------------ device helpers
 __device__ __forceinline__ void red_add_f64(double *addr, double v) {

@@ -1,0 +1,301 @@
+// halo_nccl.cu -- ghost-value exchange inside the library, fused with the residual.
+//
+// Replaces PyOP2's global_to_local_begin / _end around the two halves of the residual parloop, which the
+// reference triggers by leaving dat.vec_wo in _TSContext.form_function (firedrake_ts/solving_utils.py:249-252)
+// before ctx._assemble_residual (:258).  One call of fdts_ifunction_exchange issues, without returning to the
+// host language in between:
+//
+//   main stream   pack_all (u and udot, all neighbours, ONE launch)  -> event
+//   comm stream   ncclGroupStart; one ncclSend + one ncclRecv per neighbour (u and udot travel in the same
+//                 message); ncclGroupEnd                              -> event
+//   main stream   residual of the interior cells (touch no ghost node) | wait(event) | unpack_all (ONE launch)
+//                 | residual of the remaining cells
+//
+// so the wire time hides behind the interior cells and the per-step host cost is five launches from C++ instead
+// of a Python-driven sequence of per-neighbour pack kernels + torch.distributed P2P ops (round 1: ~0.17 ms of
+// exposed latency per residual at 8 GPUs).  NCCL is resolved at run time from the libnccl.so.2 the process
+// already uses (dlopen by path, no link-time dependency: the library still loads on a machine without NCCL).
+#include <dlfcn.h>
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "fdts_common.cuh"
+
+namespace {
+
+// the slice of nccl.h used here (ABI-stable since NCCL 2.7)
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclFloat64 = 8 };
+
+struct NcclApi {
+  void *lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+
+int load_nccl(const char *path, NcclApi &api) {
+  api.lib = dlopen(path && *path ? path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!api.lib) {
+    fdts_set_error(std::string("cannot load NCCL (") + (path ? path : "libnccl.so.2") + "): " + dlerror());
+    return 2;
+  }
+#define SYM(field, name)                                                   \
+  *(void **)(&api.field) = dlsym(api.lib, name);                           \
+  if (!api.field) {                                                        \
+    fdts_set_error(std::string("NCCL symbol missing: ") + name);          \
+    return 2;                                                              \
+  }
+  SYM(GetUniqueId, "ncclGetUniqueId")
+  SYM(CommInitRank, "ncclCommInitRank")
+  SYM(CommDestroy, "ncclCommDestroy")
+  SYM(Send, "ncclSend")
+  SYM(Recv, "ncclRecv")
+  SYM(GroupStart, "ncclGroupStart")
+  SYM(GroupEnd, "ncclGroupEnd")
+  SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  return 0;
+}
+
+}  // namespace
+
+struct fdts_halo {
+  NcclApi api;
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1, nn = 0;
+  std::vector<int> nb;
+  std::vector<int64_t> send_off, recv_off;  // nn + 1 each, in nodes
+  int64_t nsend = 0, nrecv = 0;
+  int32_t *send_node = nullptr;   // [nsend] owned node to pack
+  int64_t *send_dst = nullptr;    // [nsend] position of the (vector 0, component 0) copy in sendbuf
+  int32_t *send_cnt = nullptr;    // [nsend] nodes of that neighbour (stride between components)
+  int32_t *recv_node = nullptr;   // [nrecv] ghost node to fill
+  int64_t *recv_src = nullptr;
+  int32_t *recv_cnt = nullptr;
+  double *sendbuf = nullptr, *recvbuf = nullptr;
+  cudaStream_t cs = nullptr;
+  cudaEvent_t ev_packed = nullptr, ev_recv = nullptr;
+};
+
+namespace {
+
+#define NCCL_CHECK(h, call)                                                                        \
+  do {                                                                                             \
+    int r_ = (call);                                                                               \
+    if (r_ != ncclSuccess) {                                                                       \
+      fdts_set_error(std::string(#call) + " failed: " + (h)->api.GetErrorString(r_));              \
+      return 2;                                                                                    \
+    }                                                                                              \
+  } while (0)
+
+// u and udot of every send node, all components: buffer of neighbour r = [vector][component][node]
+__global__ void pack_all(const double *__restrict__ x, const double *__restrict__ xdot,
+                         const int32_t *__restrict__ node, const int64_t *__restrict__ dst,
+                         const int32_t *__restrict__ cnt, int64_t n, int nc, int layout, int64_t nnodes,
+                         double *__restrict__ buf) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const int64_t nd = node[q], d = dst[q], c = cnt[q];
+  for (int m = 0; m < nc; ++m) {
+    const int64_t dof = layout == FDTS_INTERLEAVED ? nd * nc + m : (int64_t)m * nnodes + nd;
+    buf[d + m * c] = x[dof];
+    buf[d + (nc + m) * c] = xdot[dof];
+  }
+}
+
+__global__ void unpack_all(double *__restrict__ x, double *__restrict__ xdot, const int32_t *__restrict__ node,
+                           const int64_t *__restrict__ src, const int32_t *__restrict__ cnt, int64_t n, int nc,
+                           int layout, int64_t nnodes, const double *__restrict__ buf) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const int64_t nd = node[q], s = src[q], c = cnt[q];
+  for (int m = 0; m < nc; ++m) {
+    const int64_t dof = layout == FDTS_INTERLEAVED ? nd * nc + m : (int64_t)m * nnodes + nd;
+    x[dof] = buf[s + m * c];
+    xdot[dof] = buf[s + (nc + m) * c];
+  }
+}
+
+template <typename T>
+int to_device(T **dst, const std::vector<T> &v) {
+  FDTS_CHECK(cudaMalloc((void **)dst, sizeof(T) * (v.size() ? v.size() : 1)));
+  if (!v.empty()) FDTS_CHECK(cudaMemcpy(*dst, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// post the exchange: pack on s, sends / receives on the comm stream; ev_recv fires when the ghosts arrived
+int post_exchange(fdts_engine *e, const double *x, const double *xdot, cudaStream_t s) {
+  fdts_halo *h = e->halo;
+  const int nc = e->cfg.ncomp;
+  if (h->nsend > 0) {
+    pack_all<<<(unsigned)((h->nsend + 255) / 256), 256, 0, s>>>(x, xdot, h->send_node, h->send_dst, h->send_cnt, h->nsend,
+                                                                 nc, e->cfg.layout, e->cfg.num_nodes, h->sendbuf);
+    e->launches++;
+    FDTS_CHECK(cudaGetLastError());
+  }
+  FDTS_CHECK(cudaEventRecord(h->ev_packed, s));
+  FDTS_CHECK(cudaStreamWaitEvent(h->cs, h->ev_packed, 0));
+  NCCL_CHECK(h, h->api.GroupStart());
+  for (int r = 0; r < h->nn; ++r) {
+    const int64_t ns = h->send_off[r + 1] - h->send_off[r], nr = h->recv_off[r + 1] - h->recv_off[r];
+    if (ns > 0)
+      NCCL_CHECK(h, h->api.Send(h->sendbuf + 2 * nc * h->send_off[r], (size_t)(2 * nc * ns), ncclFloat64, h->nb[r], h->comm, h->cs));
+    if (nr > 0)
+      NCCL_CHECK(h, h->api.Recv(h->recvbuf + 2 * nc * h->recv_off[r], (size_t)(2 * nc * nr), ncclFloat64, h->nb[r], h->comm, h->cs));
+  }
+  NCCL_CHECK(h, h->api.GroupEnd());
+  FDTS_CHECK(cudaEventRecord(h->ev_recv, h->cs));
+  return 0;
+}
+
+int finish_exchange(fdts_engine *e, double *x, double *xdot, cudaStream_t s) {
+  fdts_halo *h = e->halo;
+  FDTS_CHECK(cudaStreamWaitEvent(s, h->ev_recv, 0));
+  if (h->nrecv > 0) {
+    unpack_all<<<(unsigned)((h->nrecv + 255) / 256), 256, 0, s>>>(x, xdot, h->recv_node, h->recv_src, h->recv_cnt, h->nrecv,
+                                                                   e->cfg.ncomp, e->cfg.layout, e->cfg.num_nodes, h->recvbuf);
+    e->launches++;
+    FDTS_CHECK(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // namespace
+
+void fdts_free_halo(fdts_engine *e) {
+  fdts_halo *h = e->halo;
+  if (!h) return;
+  void *ptrs[] = {h->send_node, h->send_dst, h->send_cnt, h->recv_node, h->recv_src, h->recv_cnt, h->sendbuf, h->recvbuf};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  if (h->ev_packed) cudaEventDestroy(h->ev_packed);
+  if (h->ev_recv) cudaEventDestroy(h->ev_recv);
+  if (h->cs) cudaStreamDestroy(h->cs);
+  if (h->comm && h->api.CommDestroy) h->api.CommDestroy(h->comm);
+  delete h;
+  e->halo = nullptr;
+}
+
+extern "C" int fdts_nccl_unique_id(const char *nccl_library, void *id128) {
+  if (!id128) return 1;
+  NcclApi api;
+  if (int rc = load_nccl(nccl_library, api)) return rc;
+  ncclUniqueId id;
+  const int r = api.GetUniqueId(&id);
+  if (r != ncclSuccess) {
+    fdts_set_error(std::string("ncclGetUniqueId failed: ") + api.GetErrorString(r));
+    return 2;
+  }
+  memcpy(id128, id.internal, 128);
+  return 0;
+}
+
+extern "C" int fdts_halo_setup(fdts_handle e, const fdts_halo_config *c) {
+  if (!e || !c || c->num_neighbours < 0 || c->nranks < 1 || c->rank < 0 || c->rank >= c->nranks || !c->nccl_unique_id) {
+    fdts_set_error("fdts_halo_setup: bad argument");
+    return 1;
+  }
+  FDTS_CHECK(cudaSetDevice(e->device));
+  fdts_free_halo(e);
+  fdts_halo *h = new fdts_halo;
+  e->halo = h;
+  if (int rc = load_nccl(c->nccl_library, h->api)) return rc;
+  h->rank = c->rank;
+  h->nranks = c->nranks;
+  h->nn = c->num_neighbours;
+  const int nc = e->cfg.ncomp;
+  const int64_t nown = e->cfg.num_owned_nodes, nnodes = e->cfg.num_nodes;
+  h->send_off.assign(1, 0);
+  h->recv_off.assign(1, 0);
+  std::vector<int32_t> snode, scnt, rnode, rcnt;
+  std::vector<int64_t> sdst, rsrc;
+  for (int r = 0; r < h->nn; ++r) {
+    const int peer = c->neighbour_rank[r];
+    if (peer < 0 || peer >= c->nranks) {
+      fdts_set_error("fdts_halo_setup: neighbour rank out of range");
+      return 1;
+    }
+    h->nb.push_back(peer);
+    const int64_t s0 = c->send_offset[r], s1 = c->send_offset[r + 1], ns = s1 - s0, nr = c->recv_count[r];
+    if (ns < 0 || nr < 0 || (nr > 0 && (c->recv_first[r] < nown || c->recv_first[r] + nr > nnodes))) {
+      fdts_set_error("fdts_halo_setup: receive slice outside the ghost tail or negative count");
+      return 1;
+    }
+    const int64_t sbase = 2 * nc * h->send_off[r], rbase = 2 * nc * h->recv_off[r];
+    for (int64_t k = 0; k < ns; ++k) {
+      const int32_t nd = c->send_nodes[s0 + k];
+      if (nd < 0 || nd >= nown) {
+        fdts_set_error("fdts_halo_setup: send node is not an owned node");
+        return 1;
+      }
+      snode.push_back(nd);
+      sdst.push_back(sbase + k);
+      scnt.push_back((int32_t)ns);
+    }
+    for (int64_t k = 0; k < nr; ++k) {
+      rnode.push_back((int32_t)(c->recv_first[r] + k));
+      rsrc.push_back(rbase + k);
+      rcnt.push_back((int32_t)nr);
+    }
+    h->send_off.push_back(h->send_off[r] + ns);
+    h->recv_off.push_back(h->recv_off[r] + nr);
+  }
+  h->nsend = h->send_off[h->nn];
+  h->nrecv = h->recv_off[h->nn];
+  if (to_device(&h->send_node, snode) || to_device(&h->send_dst, sdst) || to_device(&h->send_cnt, scnt) ||
+      to_device(&h->recv_node, rnode) || to_device(&h->recv_src, rsrc) || to_device(&h->recv_cnt, rcnt))
+    return 2;
+  FDTS_CHECK(cudaMalloc(&h->sendbuf, sizeof(double) * (2 * nc * h->nsend + 1)));
+  FDTS_CHECK(cudaMalloc(&h->recvbuf, sizeof(double) * (2 * nc * h->nrecv + 1)));
+  FDTS_CHECK(cudaStreamCreateWithFlags(&h->cs, cudaStreamNonBlocking));
+  FDTS_CHECK(cudaEventCreateWithFlags(&h->ev_packed, cudaEventDisableTiming));
+  FDTS_CHECK(cudaEventCreateWithFlags(&h->ev_recv, cudaEventDisableTiming));
+  ncclUniqueId id;
+  memcpy(id.internal, c->nccl_unique_id, 128);
+  NCCL_CHECK(h, h->api.CommInitRank(&h->comm, c->nranks, id, c->rank));  // collective over the ranks
+  return 0;
+}
+
+extern "C" int fdts_halo_exchange(fdts_handle e, double *x, double *xdot, void *stream) {
+  if (!e || !x || !xdot) return 1;
+  if (!e->halo) {
+    fdts_set_error("fdts_halo_exchange: no halo (fdts_halo_setup)");
+    return 3;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (int rc = post_exchange(e, x, xdot, s)) return rc;
+  return finish_exchange(e, x, xdot, s);
+}
+
+extern "C" int fdts_ifunction_exchange(fdts_handle e, double t, double *x, double *xdot, double *f, void *stream) {
+  if (!e || !x || !xdot || !f) {
+    fdts_set_error("null argument");
+    return 1;
+  }
+  if (!e->halo) {
+    fdts_set_error("fdts_ifunction_exchange: no halo (fdts_halo_setup)");
+    return 3;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t ni = e->cfg.num_interior_cells, ncell = e->cfg.num_cells;
+  if (int rc = post_exchange(e, x, xdot, s)) return rc;
+  // interior cells read owned values only: they run while the messages are on the wire (flag 1: zero f first)
+  if (ni > 0) {
+    if (int rc = fdts_ifunction_range(e, t, x, xdot, f, 0, ni, 1, stream)) return rc;
+  } else {
+    FDTS_CHECK(cudaMemsetAsync(f, 0, sizeof(double) * e->cfg.num_owned_nodes * e->cfg.ncomp, s));
+  }
+  if (int rc = finish_exchange(e, x, xdot, s)) return rc;
+  if (ni < ncell) return fdts_ifunction_range(e, t, x, xdot, f, ni, ncell, 0, stream);
+  return 0;
+}

@@ -25,7 +25,7 @@ SYMBOLS = [
     "fdts_get_node_csr", "fdts_set_param", "fdts_set_option", "fdts_get_option", "fdts_ifunction", "fdts_ijacobian",
     "fdts_ifunction_range", "fdts_ijacobian_range", "fdts_ifunction_host", "fdts_ijacobian_host", "fdts_halo_pack",
     "fdts_halo_unpack", "fdts_launch_count", "fdts_measure_fp64_peak", "fdts_csr_spmv", "fdts_csr_spmv_warp", "fdts_csr_diagonal", "fdts_set_row_blocks",
-    "fdts_set_cell_tiles",
+    "fdts_set_cell_tiles", "fdts_nccl_unique_id", "fdts_halo_setup", "fdts_halo_exchange", "fdts_ifunction_exchange",
 ]
 
 
@@ -50,6 +50,34 @@ class _Config(C.Structure):
 class _Sizes(C.Structure):
     _fields_ = [("num_rows", C.c_int64), ("num_cols", C.c_int64), ("nnz", C.c_int64), ("node_nnz", C.c_int64),
                 ("max_row_nodes", C.c_int32), ("reserved", C.c_int32)]
+
+
+class _HaloConfig(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("num_neighbours", C.c_int32), ("reserved", C.c_int32),
+                ("neighbour_rank", C.c_void_p), ("send_offset", C.c_void_p), ("send_nodes", C.c_void_p),
+                ("recv_first", C.c_void_p), ("recv_count", C.c_void_p), ("nccl_library", C.c_char_p),
+                ("nccl_unique_id", C.c_void_p)]
+
+
+def nccl_library_path():
+    """the libnccl.so.2 this process already uses (torch's bundled one once torch.distributed/NCCL is loaded),
+    else the wheel's copy; None lets the dynamic loader decide"""
+    try:
+        with open("/proc/self/maps") as f:
+            for line in f:
+                if "libnccl.so" in line:
+                    return line.split()[-1]
+    except OSError:
+        pass
+    try:
+        import nvidia.nccl as _n
+
+        cand = os.path.join(os.path.dirname(_n.__file__), "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            return cand
+    except ImportError:
+        pass
+    return None
 
 
 def load_library():
@@ -90,6 +118,10 @@ def load_library():
         lib.fdts_csr_diagonal.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                           C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         lib.fdts_measure_fp64_peak.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_double)]
+        lib.fdts_nccl_unique_id.argtypes = [C.c_char_p, C.c_void_p]
+        lib.fdts_halo_setup.argtypes = [C.c_void_p, C.POINTER(_HaloConfig)]
+        lib.fdts_halo_exchange.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.fdts_ifunction_exchange.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _LIB = lib
     return _LIB
 
@@ -160,6 +192,7 @@ class Engine:
         self.max_row_nodes, self.max_degree = s.max_row_nodes, s.reserved
         self.num_cells, self.num_interior_cells = m.num_cells, m.num_interior_cells
         self._lib = lib
+        self.has_native_halo = False
         if plan_version is not None:
             self.set_option("plan_version", plan_version)
         if dedup is not None:
@@ -304,6 +337,75 @@ class Engine:
             assert not a.is_cuda and a.dtype == torch.float64 and a.is_contiguous()
         _check(self._lib.fdts_ijacobian_host(self._h, float(t), x.data_ptr(), xdot.data_ptr(), float(shift),
                                              out.data_ptr()), "fdts_ijacobian_host")
+        return out
+
+    # halo: exchange inside the library (NCCL send/recv grouped per call, fused with the residual) -----------
+    @staticmethod
+    def nccl_unique_id():
+        buf = C.create_string_buffer(128)
+        path = nccl_library_path()
+        _check(load_library().fdts_nccl_unique_id(path.encode() if path else None, buf), "fdts_nccl_unique_id")
+        return buf.raw
+
+    def halo_setup_raw(self, rank, nranks, neighbours, send_lists, recv_slices, unique_id):
+        """neighbours: ranks; send_lists[r]: owned node ids to pack for r (the receiver's ghost order);
+        recv_slices[r] = (first local node, count).  Collective over the ranks (ncclCommInitRank)."""
+        nb = np.asarray(list(neighbours), dtype=np.int32)
+        off, nodes, first, count = [0], [], [], []
+        for r in nb.tolist():
+            lst = np.asarray(send_lists.get(r, np.zeros(0)), dtype=np.int32).reshape(-1)
+            nodes.append(lst)
+            off.append(off[-1] + lst.size)
+            f, c = recv_slices.get(r, (self.V.num_owned_nodes, 0))
+            first.append(int(f))
+            count.append(int(c))
+        off = np.asarray(off, dtype=np.int64)
+        nodes = np.ascontiguousarray(np.concatenate(nodes) if nodes else np.zeros(0), dtype=np.int32)
+        first, count = np.asarray(first, dtype=np.int64), np.asarray(count, dtype=np.int64)
+        idbuf = C.create_string_buffer(bytes(unique_id), 128)
+        path = nccl_library_path()
+        cfg = _HaloConfig()
+        cfg.rank, cfg.nranks, cfg.num_neighbours = int(rank), int(nranks), int(nb.size)
+        cfg.neighbour_rank, cfg.send_offset = nb.ctypes.data, off.ctypes.data
+        cfg.send_nodes, cfg.recv_first, cfg.recv_count = nodes.ctypes.data, first.ctypes.data, count.ctypes.data
+        cfg.nccl_library = path.encode() if path else None
+        cfg.nccl_unique_id = C.cast(idbuf, C.c_void_p)
+        with torch.cuda.device(self.device):
+            _check(self._lib.fdts_halo_setup(self._h, C.byref(cfg)), "fdts_halo_setup")
+        self.has_native_halo = True
+
+    def halo_setup(self, group=None):
+        """open the library's own NCCL communicator over the ranks of ``group`` (default: WORLD) for the
+        ghost exchange of this engine's space; collective."""
+        import torch.distributed as dist
+
+        V = self.V
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        assert rank == V.mesh.partition.rank and world == V.mesh.partition.size
+        box = [self.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        nbs = sorted(set(V.recv_slices) | set(V.send_lists))
+        self.halo_setup_raw(rank, world, nbs, {r: v.cpu().numpy() for r, v in V.send_lists.items()},
+                            dict(V.recv_slices), box[0])
+
+    def halo_exchange(self, x, xdot):
+        """refresh the ghost entries of the local vectors x and xdot (stream-ordered)"""
+        self._chk_vec(x, self.num_cols, "x")
+        self._chk_vec(xdot, self.num_cols, "xdot")
+        with torch.cuda.device(self.device):
+            _check(self._lib.fdts_halo_exchange(self._h, x.data_ptr(), xdot.data_ptr(), _stream()), "fdts_halo_exchange")
+
+    def ifunction_exchange(self, t, x, xdot, out=None):
+        """IFunction including the ghost exchange of x and xdot, hidden behind the interior cells; one
+        library call (fdts_ifunction_exchange)"""
+        self._chk_vec(x, self.num_cols, "x")
+        self._chk_vec(xdot, self.num_cols, "xdot")
+        if out is None:
+            out = torch.empty(self.num_rows, dtype=torch.float64, device=self.device)
+        self._chk_vec(out, self.num_rows, "F")
+        with torch.cuda.device(self.device):
+            _check(self._lib.fdts_ifunction_exchange(self._h, float(t), x.data_ptr(), xdot.data_ptr(), out.data_ptr(),
+                                                     _stream()), "fdts_ifunction_exchange")
         return out
 
     # halo helpers ----------------------------------------------------------------

@@ -113,11 +113,22 @@ class _TSContext:
             rowptr, colidx = torch.from_numpy(rp).to(dev), torch.from_numpy(ci).to(dev)
             values = torch.zeros(colidx.numel(), dtype=torch.float64, device=dev)
         self._halo = None
+        self._native_halo = False
+        self._ghosts_fresh = True
         if V.mesh.partition.size > 1:
             from .halo import HaloExchange
 
             self._halo = HaloExchange(V, self.engine if assembler == "b200" else None, group=comm,
                                       device=self._device)
+            # B200 engine on a CUDA device with NCCL: the exchange runs inside the library (its own communicator),
+            # fused with the residual; the torch.distributed path stays for CPU/gloo runs and for mat-vecs
+            self._native_halo = False
+            if assembler == "b200" and self._device.type == "cuda" and self.appctx.get("native_halo", True):
+                import torch.distributed as dist
+
+                if dist.is_available() and dist.is_initialized() and dist.get_backend(comm) == "nccl":
+                    self.engine.halo_setup(comm)
+                    self._native_halo = True
         # residual Cofunction and Jacobian Matrix stand-ins (base class: _F, _jac, _pjac)
         self._F = Vec(torch.zeros(V.num_owned_dofs, dtype=torch.float64, device=self._device), comm)
         self._jac = _Assembled(Mat(rowptr, colidx, values, V.num_dofs, halo=self._halo, space=V))
@@ -180,6 +191,12 @@ class _TSContext:
     # -- the two assemblers that replace get_assembler(...).assemble ----------------
     def _b200_assemble_residual(self, tensor=None):
         tensor = tensor if tensor is not None else self._F
+        if not self._ghosts_fresh:
+            # exchange deferred by form_function: one library call packs, sends/receives on the communication
+            # stream, assembles the interior cells meanwhile, unpacks and assembles the remaining cells
+            self._ghosts_fresh = True
+            self.engine.ifunction_exchange(float(self._time), self._x.data, self._xdot.data, out=tensor.array)
+            return tensor
         out = self.engine.ifunction(float(self._time), self._x.data, self._xdot.data, out=tensor.array)
         if out is not tensor.array:
             tensor.array.copy_(torch.as_tensor(out))
@@ -234,10 +251,19 @@ class _TSContext:
                 slots.append(int(rowptr[r]) + k)
         return torch.tensor(slots, dtype=torch.int64, device=rowptr.device)
 
-    def _refresh_halo(self):
-        if self._halo is not None:
-            self._halo.forward(self._x.data)
-            self._halo.forward(self._xdot.data)
+    def _refresh_halo(self, defer=False):
+        """ghost update of u and udot (PyOP2 does it when the reference leaves dat.vec_wo, :249-252).  With the
+        library's own exchange and ``defer`` the update is folded into the residual assembly that follows."""
+        if self._halo is None:
+            return
+        if self._native_halo:
+            if defer:
+                self._ghosts_fresh = False
+            else:
+                self.engine.halo_exchange(self._x.data, self._xdot.data)
+            return
+        self._halo.forward(self._x.data)
+        self._halo.forward(self._xdot.data)
 
     # -- registration (reference :115-122) ----------------------------------------------
     def set_ifunction(self, ts):
@@ -353,7 +379,8 @@ class _TSContext:
         # X may not be the same vector as the vec behind self._x, so copy guess in from X.
         ctx._x.set_owned(X.array)
         ctx._xdot.set_owned(Xdot.array)
-        ctx._refresh_halo()
+        # a user pre-callback may read the ghosts: exchange first in that case, otherwise inside the assembly
+        ctx._refresh_halo(defer=ctx._pre_function_callback is None)
         ctx._time.assign(t)
 
         if ctx._pre_function_callback is not None:

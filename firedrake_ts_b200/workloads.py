@@ -10,7 +10,7 @@ from .function import DirichletBC, Function
 
 # name -> (family, dim, degree, full-size n, function-space tile, tile offset, mesh tile)
 CONFIGS = {
-    "C1": ("heat", 2, 1, 4096, 16, 0, 16),
+    "C1": ("heat", 2, 1, 4096, 14, 0, 14),  # 14 x 14 row blocks: 15^2 = 225 vertices per block (limit 254)
     "C2": ("burgers", 2, 2, 2048, 0, 0, 8),
     "C3": ("cahn_hilliard", 2, 1, 4096, 0, 0, 16),
     "C4": ("heat", 3, 2, 184, 6, 0, 3),

@@ -148,6 +148,34 @@ int fdts_ijacobian_host(fdts_handle h, double t, const double *x_host, const dou
 int fdts_halo_pack(fdts_handle h, const double *x, const int32_t *nodes, int64_t count, double *buf, void *stream);
 int fdts_halo_unpack(fdts_handle h, double *x, int64_t first_node, int64_t count, const double *buf, void *stream);
 
+/* Ghost exchange inside the library (K5 fused around ncclSend/ncclRecv).
+ * Replaces PyOP2's global_to_local_begin/_end halves that the reference triggers by leaving dat.vec_wo in
+ * _TSContext.form_function / form_jacobian (firedrake_ts/solving_utils.py:249-252, 294-297) on the communicator
+ * set up at firedrake_ts/ts_solver.py:233.  One rank per GPU; the library opens its own NCCL communicator
+ * (ncclCommInitRank is collective: every rank calls fdts_halo_setup with the same 128-byte id, which rank 0
+ * obtains from fdts_nccl_unique_id and the host layer broadcasts).  nccl_library: path of the libnccl.so.2
+ * the process already uses (NULL: the loader's default).  A rank may name itself as a neighbour. */
+typedef struct {
+  int32_t rank, nranks;
+  int32_t num_neighbours;
+  int32_t reserved;
+  const int32_t *neighbour_rank; /* [num_neighbours] */
+  const int64_t *send_offset;    /* [num_neighbours + 1] offsets into send_nodes */
+  const int32_t *send_nodes;     /* host: owned node ids to pack, per neighbour in the receiver's ghost order */
+  const int64_t *recv_first;     /* [num_neighbours] first local (ghost) node of the neighbour's slice */
+  const int64_t *recv_count;     /* [num_neighbours] */
+  const char *nccl_library;
+  const void *nccl_unique_id;    /* 128 bytes */
+} fdts_halo_config;
+int fdts_nccl_unique_id(const char *nccl_library, void *id128);
+int fdts_halo_setup(fdts_handle h, const fdts_halo_config *cfg);
+/* refresh the ghost entries of the local vectors x and xdot (one message per neighbour carries both);
+ * stream-ordered: returns after enqueueing, the ghosts are valid for later work on `stream` */
+int fdts_halo_exchange(fdts_handle h, double *x, double *xdot, void *stream);
+/* IFunction with the exchange hidden behind the interior cells: pack -> grouped send/recv on the library's
+ * communication stream -> interior cells -> wait -> unpack -> remaining cells, all enqueued by one call */
+int fdts_ifunction_exchange(fdts_handle h, double t, double *x, double *xdot, double *f, void *stream);
+
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t fdts_launch_count(fdts_handle h);
 

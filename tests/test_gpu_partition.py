@@ -229,6 +229,7 @@ def test_headline_row_blocks_match_oracle(n, degree):
     nb = starts.numel() - 1
     per = int(round(nb ** (1 / 3)))
     # blocks are numbered with the slowest dimension outermost: pick blocks by their lattice position
+    Fscale, Jscale = float(F.abs().max()), float(J.abs().max())
     picks = {"corner": 0, "edge": per // 2, "face": (per // 2) * per + per // 2,
              "interior": ((per // 2) * per + per // 2) * per + per // 2, "last": nb - 1}
     et = fem.element_tables(3, degree, form.qdegree, V.variant)
@@ -243,7 +244,9 @@ def test_headline_row_blocks_match_oracle(n, degree):
                      w=et.w, bc_nodes=bc_local, **kw)
         ul, udl = u.data[l2g.cuda()].cpu(), udot.data[l2g.cuda()].cpu()
         Fo = orc.ifunction(0.0, ul, udl)
-        assert rel_err(F[r0:r1].cpu().numpy(), Fo) < TOL, name
+        # near the Dirichlet boundary the residual of this state is tiny by cancellation: the tolerance is
+        # relative to the largest entry of the whole vector, as in every other parity test
+        assert np.abs(F[r0:r1].cpu().numpy() - Fo).max() < TOL * Fscale, name
         orp, oci = orc.pattern()
         Jo = orc.ijacobian(0.0, ul, udl, shift)
         s0, s1 = int(rp[r0]), int(rp[r1])
@@ -255,5 +258,61 @@ def test_headline_row_blocks_match_oracle(n, degree):
         # same column set per row; compare values after sorting both by (row, global column)
         oo = np.lexsort((gcols, rows_l))
         assert np.array_equal(gcols[oo], ecols), name
-        assert rel_err(evals, Jo[oo]) < TOL, name
+        assert np.abs(evals - Jo[oo]).max() < TOL * Jscale, name
         assert np.abs(evals).max() > 0
+
+
+@pytest.mark.parametrize("family,dim,degree,n,grid", [("heat", 3, 2, 5, (2, 1, 1)), ("burgers", 2, 2, 5, (2, 1)),
+                                                       ("cahn_hilliard", 2, 1, 7, (1, 2))])
+def test_native_nccl_exchange_single_rank_loopback(family, dim, degree, n, grid):
+    """fdts_halo_setup / fdts_halo_exchange / fdts_ifunction_exchange on ONE GPU: the rank names itself as its
+    only neighbour (NCCL allows send/recv to self inside a group), sends k of its owned nodes and receives them
+    into its k ghost slots.  Checks pack_all -> ncclSend/ncclRecv on the library's communication stream ->
+    unpack_all and the event ordering against torch indexing, then the fused residual (exchange hidden behind
+    the interior cells) against the plain residual on the exchanged state.  ncomp 1, 2; both layouts."""
+    from firedrake_ts_b200.engine import Engine
+
+    form, bcs, u, udot = make_problem(family, dim, degree, n, partition=M.Partition(tuple(grid), 0), tile=2)
+    V = form.space
+    eng = Engine(form, bcs, device="cuda:0")
+    k, nown, nc = V.num_ghost_nodes, V.num_owned_nodes, V.ncomp
+    assert k > 0
+    g = torch.Generator().manual_seed(3)
+    send = torch.randperm(nown, generator=g)[:k].to(torch.int32)
+    eng.halo_setup_raw(0, 1, [0], {0: send.numpy()}, {0: (nown, k)}, Engine.nccl_unique_id())
+    x, xd = u.data.cuda(), udot.data.cuda()
+
+    def want(v):
+        w = v.clone()
+        for m in range(nc):
+            w[V.dof_index(torch.arange(nown, nown + k), m).cuda()] = v[V.dof_index(send.long(), m).cuda()]
+        return w
+
+    xw, xdw = want(x), want(xd)
+    for _ in range(3):  # repeated exchanges reuse the buffers and events
+        x2, xd2 = x.clone(), xd.clone()
+        eng.halo_exchange(x2, xd2)
+        assert torch.equal(x2, xw) and torch.equal(xd2, xdw)
+    Fref = eng.ifunction(0.0, xw, xdw)
+    for _ in range(3):
+        x2, xd2 = x.clone(), xd.clone()
+        F = eng.ifunction_exchange(0.0, x2, xd2)
+        assert torch.equal(x2, xw) and torch.equal(xd2, xdw)
+        assert rel_err(F.cpu().numpy(), Fref.cpu().numpy()) < 1e-14
+    assert rel_err(Fref.cpu().numpy(), eng.ifunction(0.0, x, xd).cpu().numpy()) > 1e-6  # the exchange mattered
+
+
+def test_multi_gpu_native_exchange():
+    """two real ranks over NCCL (needs >= 2 GPUs on the box; the driver's single-GPU test box skips it):
+    tests/mgpu_check.py under torchrun."""
+    import os
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(here, "mgpu_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "MGPU_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
