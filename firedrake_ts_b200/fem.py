@@ -242,6 +242,22 @@ _TET_RULES = {
 }
 
 
+def _grundmann_moeller(dim: int, s: int):
+    """Grundmann-Moeller rule of index s on the reference simplex: exact for total degree 2s+1 with
+    C(s + dim + 1, dim + 1) points (SIAM J. Numer. Anal. 15 (1978)).  Some weights are negative
+    (sum |w| / sum w = 12 for s = 3, 25 for s = 4 in 3-D), harmless at the 1e-12 parity bar."""
+    d = dim
+    pts, wts = [], []
+    for i in range(s + 1):
+        m = d + 2 * s - 2 * i + 1
+        w = ((-1) ** i) * 2.0 ** (-2 * s) * float(m) ** (2 * s + 1) / (math.factorial(i) * math.factorial(d + 2 * s + 1 - i))
+        for beta in itertools.product(range(s - i + 1), repeat=d + 1):
+            if sum(beta) == s - i:
+                pts.append([(2 * b + 1) / m for b in beta[1:]])
+                wts.append(w)  # times d! / d! : weights sum to the reference volume 1/d!
+    return np.array(pts), np.array(wts)
+
+
 @functools.lru_cache(maxsize=None)
 def quadrature(dim: int, degree: int):
     """Rule exact for polynomials of total degree <= ``degree`` on the reference
@@ -258,6 +274,10 @@ def quadrature(dim: int, degree: int):
             if d >= degree:
                 return _sym_tet(_TET_RULES[d])
     n = degree // 2 + 1
+    if dim == 3 and degree >= 6:
+        # high-order tetrahedra (P3 heat: degree 6, P3 BBM / P2 Cahn-Hilliard: degree 8): 35 / 70 points
+        # instead of the 64 / 125 of the collapsed rule below -- the quadrature kernels are compute bound there
+        return _grundmann_moeller(3, degree // 2)
     if dim == 1:
         x, w = _gauss_jacobi_01(n, 0)
         return x[:, None].copy(), w.copy()
