@@ -107,10 +107,10 @@ def run_reference(a):
     build_oracle()
     cores = os.cpu_count() or 1
     # the SAME configuration as the B200 arm (-n, default 184 = C4); bounded by the number of timed pairs:
-    # one pair of the oracle port takes ~50 s at C4 on 16 cores, so 2 timed pairs + 1 warm-up + set-up
+    # one pair of the oracle port takes ~35 s at C4 on 16 cores, so 3 timed pairs + 1 warm-up + set-up
     # stay within a few minutes
     n = a.cpu_n or a.n
-    steps, warmup = max(1, min(a.steps, 2 if n > 100 else 4)), (0 if n > 100 else min(a.warmup, 1))
+    steps, warmup = max(1, min(a.steps, 3 if n > 100 else 4)), min(a.warmup, 1)
     t, cores = cpu_pair_seconds(n, a.degree, steps, warmup, cores)
     dofs = (a.degree * n + 1) ** 3
     value = dofs * steps / t

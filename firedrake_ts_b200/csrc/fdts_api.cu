@@ -258,7 +258,7 @@ extern "C" int fdts_destroy(fdts_handle e) {
   cudaSetDevice(e->device);
   void *ptrs[] = {e->coords, e->cell_coord, e->cell_node, e->B, e->w, e->R, e->M0, e->isbc, e->bc_nodes,
                   e->bc_diag_slot, e->nrowptr, e->ncolidx, e->pos8, e->adj_ptr, e->adj_cell, e->h2d_x, e->h2d_xdot,
-                  e->d_f, e->d_vals, e->cell_rowmask, e->pos8_cm, e->scr_x, e->scr_xdot};
+                  e->d_f, e->d_vals, e->cell_rowmask, e->pos8_cm, e->scr_x, e->scr_xdot, e->bbm_T};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   fdts_free_plan(e);
@@ -360,7 +360,7 @@ extern "C" int fdts_set_option(fdts_handle e, const char *key, int64_t value) {
     return 0;
   }
   if (!strcmp(key, "dmma")) {
-    e->opt_dmma = value ? 1 : 0;
+    e->opt_dmma = value < 0 ? 0 : (value > 2 ? 2 : value);  // 2 tensor contraction, 1 quadrature DMMA, 0 generic
     return 0;
   }
   if (!strcmp(key, "overlap")) {
@@ -410,6 +410,10 @@ extern "C" int fdts_get_option(fdts_handle e, const char *key, int64_t *value) {
   if (!e || !key || !value) return 1;
   if (!strcmp(key, "scatter")) {
     *value = e->opt_scatter;
+    return 0;
+  }
+  if (!strcmp(key, "dmma")) {
+    *value = e->opt_dmma;
     return 0;
   }
   const bool v2 = e->plan2.ready;

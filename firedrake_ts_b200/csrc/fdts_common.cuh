@@ -147,7 +147,8 @@ struct fdts_engine {
   int64_t opt_sector = 4;        // plan 2: slots per store group (4 or 2)
   int64_t opt_optimize = 1;      // plan 2: bank-conflict-aware column order for the unique patterns
   int64_t opt_residual_tiles = 1; // residual: tile kernel (pre-reduced atomics) when a cell-tile plan exists (fdts_set_cell_tiles; the Python layer only builds one on request: the kernel is slower than the per-cell one today)
-  int64_t opt_dmma = 1;          // BBM P2/P3: fp64 tensor-core element-matrix contraction instead of the generic Jacobian kernel
+  int64_t opt_dmma = 2;          // BBM P2/P3 Jacobian on the fp64 tensor cores: 2 = reference-tensor contraction (default), 1 = quadrature formulation, 0 = generic kernel
+  double *bbm_T = nullptr;       // reference tensor of the tensor-contraction BBM Jacobian (built on first use)
   int64_t opt_overlap = 0;       // plan 2: warp-specialised kernel (element matrices of block b+1 overlap the gather of block b; needs two staging buffers in smem; slower than the two-phase kernel on every block shape measured so far)
   int64_t opt_threads = 512;     // plan 2: threads per persistent CTA (512: 128 registers per thread, or 1024)
   int64_t opt_debug = 0;         // development only (timing experiments with phases switched off)

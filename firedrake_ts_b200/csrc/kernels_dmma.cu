@@ -162,6 +162,204 @@ __global__ void __launch_bounds__(DMMA_WARPS * 32, 1) bbm_jacobian_dmma(const KA
   }
 }
 
+
+// ------------------------------------------------------------------ tensor-contraction variant (default)
+// On an affine cell the BBM Jacobian is LINEAR in a short coefficient vector of the cell:
+//   A_ij = sum_kappa c_kappa T[kappa][i][j],
+//   kappa = (k, a):  c = |detJ| Jinv[a][0] u_k        T = int (d_a phi_k phi_j + phi_k d_a phi_j) phi_i      (u_x phi_j + u psi_j) phi_i
+//   then             c = |detJ| shift                  T = int phi_j phi_i                                   shift * mass
+//                    c = |detJ| Jinv[a][0]             T = int d_a phi_j phi_i                               psi_j phi_i
+//                    c = |detJ| shift Jinv[a][0] Jinv[b][0] (a <= b)   T = int d_a phi_j d_b phi_i (+ a<->b) shift psi_j psi_i
+// with psi = d/dx_0.  The reference tensor T (K x nd^2, K = nd*dim + 1 + dim + dim(dim+1)/2: 70 x 400 for P3
+// tetrahedra) is built once from the engine's own B / w tables and lives in shared memory (row stride = 4 mod 8
+// doubles: conflict-free fragment loads); the element matrices of 16 cells per warp are then ONE small GEMM
+//   A[entry][cell] = T^T[entry][kappa] c[kappa][cell]
+// on the fp64 tensor pipe (mma.sync.m8n8k4: M = 8 entries, N = 8 cells, K = 4 kappas), i.e. 2 K nd^2 flops per
+// cell (57.6 kflop for P3 tetrahedra) instead of the 2 nq nd^2 x 3 of the quadrature formulation (168 kflop with
+// the 70-point rule, 300 kflop with the 125-point rule of round 1), and no per-cell tabulation work at all.
+// The C fragment of a lane holds one entry for two cells; it goes out with one REDG per value through the
+// cell-major slot map.  Exact for the same reason the quadrature kernels are: all integrands are polynomials.
+template <int DIM, int ND>
+struct BbmTensorShape {
+  static constexpr int NL = 1 + DIM + DIM * (DIM + 1) / 2;   // state-independent rows
+  static constexpr int K = ND * DIM + NL;
+  static constexpr int KS = (K + 3) / 4;                      // k-steps
+  static constexpr int M = ND * ND, MT = (M + 7) / 8, STRIDE = MT * 8 + 4;
+};
+
+template <int DIM, int ND>
+__global__ void bbm_build_tensor(const double *__restrict__ B, const double *__restrict__ w, int nq, double *__restrict__ T) {
+  using S = BbmTensorShape<DIM, ND>;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= S::K * S::STRIDE) return;
+  const int kap = t / S::STRIDE, m = t - kap * S::STRIDE;
+  double v = 0.0;
+  if (m < S::M) {
+    const int i = m / ND, j = m - i * ND;
+    for (int q = 0; q < nq; ++q) {
+      const double *b = B + (size_t)q * (DIM + 1) * ND;  // b[al * ND + node]
+      const double pi = b[i], pj = b[j];
+      double f;
+      if (kap < ND * DIM) {
+        const int k = kap / DIM, a = kap - k * DIM;
+        f = (b[(1 + a) * ND + k] * pj + b[k] * b[(1 + a) * ND + j]) * pi;
+      } else {
+        int l = kap - ND * DIM;
+        if (l == 0) {
+          f = pj * pi;
+        } else if (l <= DIM) {
+          f = b[l * ND + j] * pi;
+        } else {
+          l -= 1 + DIM;
+          int a = 0;
+          while (l >= DIM - a) { l -= DIM - a; ++a; }
+          const int bb = a + l;
+          f = b[(1 + a) * ND + j] * b[(1 + bb) * ND + i];
+          if (bb != a) f += b[(1 + bb) * ND + j] * b[(1 + a) * ND + i];
+        }
+      }
+      v = fma(w[q], f, v);
+    }
+  }
+  T[t] = v;
+}
+
+constexpr int BT_WARPS = 16;
+
+template <int DIM, int ND>
+__global__ void __launch_bounds__(BT_WARPS * 32, 1) bbm_jacobian_tensor(const KArgs a, const double *__restrict__ T,
+                                                                        const uint8_t *__restrict__ pos8_cm) {
+  using S = BbmTensorShape<DIM, ND>;
+  extern __shared__ double sm[];
+  for (int i = threadIdx.x; i < S::K * S::STRIDE; i += blockDim.x) sm[i] = T[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g4 = lane >> 2, t4 = lane & 3;
+  const int64_t ngroups = (a.c1 - a.c0 + 15) / 16;
+  for (int64_t grp = (int64_t)blockIdx.x * BT_WARPS + warp; grp < ngroups; grp += (int64_t)gridDim.x * BT_WARPS) {
+    const int64_t cbase = a.c0 + grp * 16;
+    // ---- coefficient fragments: lane (g4, t4) holds c[kappa = 4 s + t4] of cells cbase + g4 and cbase + 8 + g4
+    double bf[2][S::KS];
+    uint32_t colbc[2], rowmask[2];
+#pragma unroll
+    for (int tl = 0; tl < 2; ++tl) {
+      const int64_t c = cbase + 8 * tl + g4;
+      const bool live = c < a.c1;
+      double adet = 0.0, ca[DIM];
+#pragma unroll
+      for (int b = 0; b < DIM; ++b) ca[b] = 0.0;
+      uint32_t bcm = 0;
+      if (live) {
+        int32_t cc[DIM + 1];
+#pragma unroll
+        for (int v = 0; v <= DIM; ++v) cc[v] = a.cell_coord_t[(int64_t)v * a.ncells_total + c];
+        Geom<DIM> g;
+        compute_geometry<DIM>(a.coords, cc, g);
+        adet = g.adet;
+#pragma unroll
+        for (int b = 0; b < DIM; ++b) ca[b] = g.Jinv[b][0];
+        // Dirichlet columns of the cell: the 4 lanes of a cell split its nodes
+        for (int j = t4; j < ND; j += 4)
+          if (a.isbc[a.cell_node_t[(int64_t)j * a.ncells_total + c]]) bcm |= 1u << j;
+      }
+      bcm |= __shfl_xor_sync(0xffffffffu, bcm, 1);
+      bcm |= __shfl_xor_sync(0xffffffffu, bcm, 2);
+      colbc[tl] = bcm;
+      rowmask[tl] = live ? a.rowmask[c] : 0u;
+#pragma unroll
+      for (int s = 0; s < S::KS; ++s) {
+        const int kap = 4 * s + t4;
+        double v = 0.0;
+        if (live && kap < S::K) {
+          if (kap < ND * DIM) {
+            const int k = kap / DIM, b = kap - k * DIM;
+            v = adet * ca[b] * __ldg(a.x + a.cell_node_t[(int64_t)k * a.ncells_total + c]);
+          } else {
+            int l = kap - ND * DIM;
+            if (l == 0) {
+              v = adet * a.shift;
+            } else if (l <= DIM) {
+              v = adet * ca[l - 1];
+            } else {
+              l -= 1 + DIM;
+              int p = 0;
+              while (l >= DIM - p) { l -= DIM - p; ++p; }
+              v = adet * a.shift * ca[p] * ca[p + l];
+            }
+          }
+        }
+        bf[tl][s] = v;
+      }
+    }
+    // ---- scatter bookkeeping: this lane stores entries of cells cbase + 8 tl + 2 t4 + h
+    int64_t cell_s[2][2];
+    uint32_t cbc_s[2][2], rm_s[2][2];
+#pragma unroll
+    for (int tl = 0; tl < 2; ++tl)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int n = 2 * t4 + h;  // cell inside the tile; its masks sit in the lanes with g4 == n
+        cell_s[tl][h] = cbase + 8 * tl + n;
+        cbc_s[tl][h] = __shfl_sync(0xffffffffu, colbc[tl], 4 * n);
+        rm_s[tl][h] = __shfl_sync(0xffffffffu, rowmask[tl], 4 * n);
+      }
+    int cur_i = -1;
+    int64_t rp[2][2];
+    for (int mt = 0; mt < S::MT; ++mt) {
+      double C[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+      const double *tp = sm + 8 * mt + g4;
+#pragma unroll
+      for (int s = 0; s < S::KS; ++s) {
+        const int kap = 4 * s + t4;
+        const double av = kap < S::K ? tp[(size_t)kap * S::STRIDE] : 0.0;
+        dmma_m8n8k4(C[0], av, bf[0][s]);
+        dmma_m8n8k4(C[1], av, bf[1][s]);
+      }
+      const int m = 8 * mt + g4;
+      if (m < S::M) {
+        const int i = m / ND, j = m - i * ND;
+        if (i != cur_i) {  // row pointers of local row i for the lane's four cells (changes every ND entries)
+          cur_i = i;
+#pragma unroll
+          for (int tl = 0; tl < 2; ++tl)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const bool ok = (rm_s[tl][h] >> i) & 1u;
+              rp[tl][h] = ok ? a.nrowptr[a.cell_node_t[(int64_t)i * a.ncells_total + cell_s[tl][h]]] : -1;
+            }
+        }
+#pragma unroll
+        for (int tl = 0; tl < 2; ++tl)
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            if (rp[tl][h] >= 0 && !((cbc_s[tl][h] >> j) & 1u)) {
+              const int pos = pos8_cm[(size_t)cell_s[tl][h] * (ND * ND) + m];
+              red_add_f64(a.out + rp[tl][h] + pos, C[tl][h]);
+            }
+      }
+    }
+  }
+}
+
+template <int DIM, int ND>
+int launch_bbm_tensor(fdts_engine *e, const KArgs &a, cudaStream_t s) {
+  using S = BbmTensorShape<DIM, ND>;
+  const size_t tbytes = sizeof(double) * S::K * S::STRIDE;
+  if (tbytes > 227 * 1024) return 3;
+  if (!e->bbm_T) {
+    if (cudaMalloc(&e->bbm_T, tbytes) != cudaSuccess) return 2;
+    bbm_build_tensor<DIM, ND><<<(S::K * S::STRIDE + 255) / 256, 256, 0, s>>>(e->B, e->w, e->cfg.nq, e->bbm_T);
+  }
+  auto kern = bbm_jacobian_tensor<DIM, ND>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tbytes) != cudaSuccess) return 2;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t want = ((a.c1 - a.c0 + 15) / 16 + BT_WARPS - 1) / BT_WARPS;
+  kern<<<(unsigned)(want < sms ? want : sms), BT_WARPS * 32, tbytes, s>>>(a, e->bbm_T, e->pos8_cm);
+  return cudaGetLastError() == cudaSuccess ? 0 : 2;
+}
+
 }  // namespace
 
 // returns 0 when the DMMA kernel handled the call, 3 when it does not apply (caller falls back)
@@ -177,6 +375,14 @@ int fdts_bbm_jacobian_dmma(fdts_engine *e, const KArgs &a, cudaStream_t s) {
       return 2;
     }
     pos8_cell_major<<<(unsigned)((nc * nd * nd + 255) / 256), 256, 0, s>>>(e->pos8, nc, nd * nd, e->pos8_cm);
+  }
+  if (e->opt_dmma >= 2) {  // tensor-contraction formulation (default)
+    int rc = 3;
+    if (dim == 3 && nd == 20) rc = launch_bbm_tensor<3, 20>(e, a, s);
+    if (dim == 3 && nd == 10) rc = launch_bbm_tensor<3, 10>(e, a, s);
+    if (dim == 2 && nd == 10) rc = launch_bbm_tensor<2, 10>(e, a, s);
+    if (rc == 2) fdts_set_error(std::string("tensor-contraction Jacobian launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    if (rc != 3) return rc;
   }
   const int nqp = (a.nq + 7) & ~7;
   const size_t smem = sizeof(double) * ((size_t)(dim + 1) * nqp * DMMA_STRIDE + nqp + (size_t)DMMA_WARPS * 3 * nqp);

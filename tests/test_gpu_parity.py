@@ -167,22 +167,39 @@ def test_residual_tile_kernel(dim, degree, n, tile):
     assert rel_err(F2.cpu().numpy(), Fo) < TOL
 
 
-@pytest.mark.parametrize("dim,degree,n", [(3, 3, 3), (3, 2, 4), (2, 3, 6)])
-def test_bbm_dmma_jacobian(dim, degree, n):
-    """fp64 tensor-core (DMMA) element-matrix contraction of the BBM Jacobian against the oracle and
-    against the generic quadrature kernel (option dmma=0); state-dependent weights, no Dirichlet rows."""
+@pytest.mark.parametrize("with_bc", [False, True])
+@pytest.mark.parametrize("dim,degree,n", [(3, 3, 3), (3, 2, 4), (2, 3, 6), (3, 3, 2)])
+def test_bbm_dmma_jacobian(dim, degree, n, with_bc):
+    """fp64 tensor-core (DMMA) BBM Jacobians against the oracle and against the generic quadrature kernel:
+    option dmma = 2 (default) contracts the reference tensor with the cell's coefficient vector (one small
+    GEMM per 16 cells), dmma = 1 is the quadrature formulation, dmma = 0 the generic kernel.  State-dependent,
+    with and without Dirichlet rows / columns; cell counts that do not fill the last group of 16."""
     from firedrake_ts_b200.engine import Engine
+    from firedrake_ts_b200.function import DirichletBC
     from oracle import Oracle
 
     form, bcs, u, udot = make_problem("bbm", dim, degree, n, tile=2)
+    if with_bc:
+        bcs = [DirichletBC(form.space, 0.0, "on_boundary")]
     x, xd = u.data.cuda(), udot.data.cuda()
     eng = Engine(form, bcs, device="cuda:0")
+    assert eng.get_option("dmma") == 2
     Jo = Oracle.from_form(form, bcs).ijacobian(0.0, u.data, udot.data, 12.5)
+    J2 = eng.ijacobian(0.0, x, xd, 12.5)
+    assert rel_err(J2.cpu().numpy(), Jo) < TOL
+    eng.set_option("dmma", 1)
     J1 = eng.ijacobian(0.0, x, xd, 12.5)
     assert rel_err(J1.cpu().numpy(), Jo) < TOL
     eng.set_option("dmma", 0)
     J0 = eng.ijacobian(0.0, x, xd, 12.5)
-    assert rel_err(J1.cpu().numpy(), J0.cpu().numpy()) < TOL
+    assert rel_err(J2.cpu().numpy(), J0.cpu().numpy()) < TOL
+    # cell ranges (the halo split of the scaling path) add up
+    eng.set_option("dmma", 2)
+    mid = (eng.num_cells // 3) | 1
+    Js = torch.empty_like(J2)
+    eng.ijacobian_range(0.0, x, xd, 12.5, Js, 0, mid, 1)
+    eng.ijacobian_range(0.0, x, xd, 12.5, Js, mid, eng.num_cells, 2)
+    assert rel_err(Js.cpu().numpy(), Jo) < TOL
 
 
 def test_pattern_dictionary_compaction():

@@ -29,6 +29,7 @@ ap.add_argument("--threads", type=int, default=512)
 ap.add_argument("--rtiles", type=int, default=0)
 ap.add_argument("--dedup", type=int, default=1)
 ap.add_argument("--foffset", type=int, default=0)
+ap.add_argument("--dmma", type=int, default=-1)
 a = ap.parse_args()
 
 if a.peak:
@@ -59,8 +60,8 @@ if a.scatter == 2:
           "vmax", eng.get_option("plan_vertices_max"), "residual tiles", eng.get_option("residual_tiles"),
           "patterns", eng.get_option("residual_patterns"), flush=True)
 x, xd = u.data, udot.data
-if a.debug:
-    eng.set_option("debug", a.debug)
+if a.dmma >= 0:
+    eng.set_option("dmma", a.dmma)
 F = torch.empty(eng.num_rows, dtype=torch.float64, device="cuda")
 J = eng.new_values()
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
