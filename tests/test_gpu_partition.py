@@ -222,6 +222,11 @@ def test_headline_row_blocks_match_oracle(n, degree):
     V, msh = form.space, form.space.mesh
     eng = Engine(form, bcs, device="cuda:0", scatter=2)
     shift = 10.0
+    # a rough state: with the smooth seeded u of make_problem the stiffness terms (~h) cancel to ~h^3 at
+    # this mesh size and the comparison would measure the conditioning of the sum, not the kernels
+    g = torch.Generator(device="cuda").manual_seed(5)
+    u.data.copy_(torch.randn(u.data.shape, generator=g, device="cuda", dtype=torch.float64))
+    u.data[bcs[0].nodes.long().cuda()] = 0.0
     F = eng.ifunction(0.0, u.data, udot.data)
     J = eng.ijacobian(0.0, u.data, udot.data, shift)
     rp, ci = eng.csr()
