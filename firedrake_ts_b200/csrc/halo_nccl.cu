@@ -226,8 +226,10 @@ extern "C" int fdts_halo_setup(fdts_handle e, const fdts_halo_config *c) {
       return 1;
     }
     h->nb.push_back(peer);
-    const int64_t s0 = c->send_offset[r], s1 = c->send_offset[r + 1], ns = s1 - s0, nr = c->recv_count[r];
-    if (ns < 0 || nr < 0 || (nr > 0 && (c->recv_first[r] < nown || c->recv_first[r] + nr > nnodes))) {
+    const bool lists = c->recv_nodes != nullptr && c->recv_offset != nullptr;
+    const int64_t s0 = c->send_offset[r], s1 = c->send_offset[r + 1], ns = s1 - s0;
+    const int64_t nr = lists ? c->recv_offset[r + 1] - c->recv_offset[r] : c->recv_count[r];
+    if (ns < 0 || nr < 0 || (!lists && nr > 0 && (c->recv_first[r] < nown || c->recv_first[r] + nr > nnodes))) {
       fdts_set_error("fdts_halo_setup: receive slice outside the ghost tail or negative count");
       return 1;
     }
@@ -243,7 +245,12 @@ extern "C" int fdts_halo_setup(fdts_handle e, const fdts_halo_config *c) {
       scnt.push_back((int32_t)ns);
     }
     for (int64_t k = 0; k < nr; ++k) {
-      rnode.push_back((int32_t)(c->recv_first[r] + k));
+      const int64_t gn = lists ? (int64_t)c->recv_nodes[c->recv_offset[r] + k] : c->recv_first[r] + k;
+      if (gn < nown || gn >= nnodes) {
+        fdts_set_error("fdts_halo_setup: receive node is not a ghost node");
+        return 1;
+      }
+      rnode.push_back((int32_t)gn);
       rsrc.push_back(rbase + k);
       rcnt.push_back((int32_t)nr);
     }

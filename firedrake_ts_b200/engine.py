@@ -56,7 +56,7 @@ class _HaloConfig(C.Structure):
     _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("num_neighbours", C.c_int32), ("reserved", C.c_int32),
                 ("neighbour_rank", C.c_void_p), ("send_offset", C.c_void_p), ("send_nodes", C.c_void_p),
                 ("recv_first", C.c_void_p), ("recv_count", C.c_void_p), ("nccl_library", C.c_char_p),
-                ("nccl_unique_id", C.c_void_p)]
+                ("nccl_unique_id", C.c_void_p), ("recv_offset", C.c_void_p), ("recv_nodes", C.c_void_p)]
 
 
 def nccl_library_path():
@@ -347,9 +347,10 @@ class Engine:
         _check(load_library().fdts_nccl_unique_id(path.encode() if path else None, buf), "fdts_nccl_unique_id")
         return buf.raw
 
-    def halo_setup_raw(self, rank, nranks, neighbours, send_lists, recv_slices, unique_id):
+    def halo_setup_raw(self, rank, nranks, neighbours, send_lists, recv_slices, unique_id, recv_lists=None):
         """neighbours: ranks; send_lists[r]: owned node ids to pack for r (the receiver's ghost order);
-        recv_slices[r] = (first local node, count).  Collective over the ranks (ncclCommInitRank)."""
+        recv_slices[r] = (first local node, count), or recv_lists[r] = explicit ghost node ids (numberings
+        whose ghosts are not grouped by owner).  Collective over the ranks (ncclCommInitRank)."""
         nb = np.asarray(list(neighbours), dtype=np.int32)
         off, nodes, first, count = [0], [], [], []
         for r in nb.tolist():
@@ -370,6 +371,11 @@ class Engine:
         cfg.send_nodes, cfg.recv_first, cfg.recv_count = nodes.ctypes.data, first.ctypes.data, count.ctypes.data
         cfg.nccl_library = path.encode() if path else None
         cfg.nccl_unique_id = C.cast(idbuf, C.c_void_p)
+        if recv_lists is not None:
+            rl = [np.asarray(recv_lists.get(r, np.zeros(0)), dtype=np.int32).reshape(-1) for r in nb.tolist()]
+            roff = np.concatenate([[0], np.cumsum([x.size for x in rl])]).astype(np.int64)
+            rnodes = np.ascontiguousarray(np.concatenate(rl) if rl else np.zeros(0), dtype=np.int32)
+            cfg.recv_offset, cfg.recv_nodes = roff.ctypes.data, rnodes.ctypes.data
         with torch.cuda.device(self.device):
             _check(self._lib.fdts_halo_setup(self._h, C.byref(cfg)), "fdts_halo_setup")
         self.has_native_halo = True

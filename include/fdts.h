@@ -166,6 +166,10 @@ typedef struct {
   const int64_t *recv_count;     /* [num_neighbours] */
   const char *nccl_library;
   const void *nccl_unique_id;    /* 128 bytes */
+  /* optional (NULL: the contiguous slices above): explicit ghost node lists, for numberings whose ghosts are not
+   * grouped by owner (PyOP2's): recv_nodes[recv_offset[r] .. recv_offset[r+1]) in the sender's packing order */
+  const int64_t *recv_offset;    /* [num_neighbours + 1] */
+  const int32_t *recv_nodes;     /* host */
 } fdts_halo_config;
 int fdts_nccl_unique_id(const char *nccl_library, void *id128);
 int fdts_halo_setup(fdts_handle h, const fdts_halo_config *cfg);
