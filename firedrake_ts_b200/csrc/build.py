@@ -35,11 +35,36 @@ def _compile(src):
     return obj
 
 
+def build_dev(verbose: bool = False) -> str:
+    """development build with the timing switches compiled in (-DFDTS_DEV_SWITCHES): libfdts_b200_dev.so,
+    used only by tools/ through FDTS_B200_LIB; its results are wrong by design when a switch is on."""
+    bdir = os.path.join(HERE, "build", "dev")
+    os.makedirs(bdir, exist_ok=True)
+    lib = os.path.join(HERE, "libfdts_b200_dev.so")
+
+    def comp(src):
+        obj = os.path.join(bdir, src.replace(".cu", ".o"))
+        deps = [os.path.join(HERE, src)] + [os.path.join(HERE, h) for h in HEADERS]
+        if _stale(obj, deps):
+            with open(obj + ".log", "w") as f:
+                subprocess.check_call([NVCC, *FLAGS, "-DFDTS_DEV_SWITCHES", "-c", os.path.join(HERE, src), "-o", obj],
+                                      stdout=f, stderr=f)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(comp, SOURCES))
+    if _stale(lib, objs):
+        subprocess.check_call([NVCC, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+                               "-lcudart", "-ldl"])
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     if force:
         for f in os.listdir(os.path.join(HERE, "build")):
-            os.remove(os.path.join(HERE, "build", f))
+            if os.path.isfile(os.path.join(HERE, "build", f)):
+                os.remove(os.path.join(HERE, "build", f))
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(_compile, SOURCES))
     if _stale(LIB, objs):
@@ -51,4 +76,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
+    if "--dev" in sys.argv:
+        print(build_dev(verbose=True))
+    else:
+        build(force="--force" in sys.argv, verbose=True)

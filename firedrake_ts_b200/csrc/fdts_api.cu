@@ -134,6 +134,9 @@ KArgs fdts_make_kargs(fdts_engine *e, const double *x, const double *xdot, doubl
   a.p0 = e->cfg.params[0];
   a.p1 = e->cfg.params[1];
   a.p2 = e->cfg.params[2];
+#ifdef FDTS_DEV_SWITCHES
+  a.dbg = (int32_t)e->opt_debug;
+#endif
   return a;
 }
 
@@ -194,20 +197,27 @@ extern "C" int fdts_create(const fdts_config *cfg, fdts_handle *out) {
   e->device = cfg->device;
   const int d = cfg->dim, nd = cfg->nd, ms = cfg->memspace;
   const int64_t nc = cfg->num_cells;
+  const bool quad = cfg->cell_type == FDTS_QUADRILATERAL;
+  if (cfg->cell_type != FDTS_SIMPLEX && !(quad && d == 2 && cfg->degree == 1 && nd == 4)) {
+    fdts_set_error("unsupported cell type (quadrilaterals: Q1 in two dimensions)");
+    delete e;
+    return 1;
+  }
+  const int ncv = quad ? 4 : d + 1;  // coordinate nodes per cell
   int rc = 0;
   int32_t *tmp_cc = nullptr, *tmp_cn = nullptr;
   do {
     if ((rc = upload(&e->coords, cfg->coords, (size_t)cfg->num_coord_nodes * d, ms))) break;
-    if ((rc = upload(&tmp_cc, cfg->cell_coord, (size_t)nc * (d + 1), ms))) break;
+    if ((rc = upload(&tmp_cc, cfg->cell_coord, (size_t)nc * ncv, ms))) break;
     if ((rc = upload(&tmp_cn, cfg->cell_node, (size_t)nc * nd, ms))) break;
-    if (cudaMalloc(&e->cell_coord, sizeof(int32_t) * (size_t)(nc * (d + 1) + 1)) != cudaSuccess ||
+    if (cudaMalloc(&e->cell_coord, sizeof(int32_t) * (size_t)(nc * ncv + 1)) != cudaSuccess ||
         cudaMalloc(&e->cell_node, sizeof(int32_t) * (size_t)(nc * nd + 1)) != cudaSuccess) {
       fdts_set_error("out of device memory for the cell maps");
       rc = 2;
       break;
     }
     if (nc > 0) {
-      transpose_i32<<<GRID(nc * (d + 1), 256), 256>>>(tmp_cc, nc, d + 1, e->cell_coord);
+      transpose_i32<<<GRID(nc * ncv, 256), 256>>>(tmp_cc, nc, ncv, e->cell_coord);
       transpose_i32<<<GRID(nc * nd, 256), 256>>>(tmp_cn, nc, nd, e->cell_node);
     }
     if ((rc = upload(&e->B, cfg->B, (size_t)cfg->nq * (d + 1) * nd, ms))) break;
@@ -235,7 +245,7 @@ extern "C" int fdts_create(const fdts_config *cfg, fdts_handle *out) {
         rc = 2;
         break;
       }
-      e->variant = fdts_heat_match_tables(d, cfg->degree, Rh.data());
+      e->variant = quad ? -1 : fdts_heat_match_tables(d, cfg->degree, Rh.data());
       // default path: closed form + atomics for the heat family when the tables match
       e->opt_scatter = ((cfg->family == FDTS_HEAT || cfg->family == FDTS_DIFFUSION) && cfg->ncomp == 1 && e->variant >= 0) ? 1 : 0;
     }
@@ -324,6 +334,10 @@ extern "C" int fdts_set_option(fdts_handle e, const char *key, int64_t value) {
       fdts_set_error("scatter must be 0 (generic, atomic), 1 (closed form, atomic) or 2 (owner-computes gather)");
       return 1;
     }
+    if (value > 0 && e->cfg.cell_type != FDTS_SIMPLEX) {
+      fdts_set_error("closed-form paths (scatter 1, 2) exist for simplices only");
+      return 1;
+    }
     e->opt_scatter = value;
     return 0;
   }
@@ -389,8 +403,32 @@ extern "C" int fdts_set_option(fdts_handle e, const char *key, int64_t value) {
   return 1;
 }
 
+// PETSc hands the callbacks GLOBAL vectors (owned dofs only); the kernels read LOCAL vectors (owned + ghost).
+// Interleaved spaces: the owned dofs are the head of the local vector.  Blocked (mixed V*V) spaces: field m
+// occupies [m*num_owned, (m+1)*num_owned) of the global and [m*num_nodes, ...) of the local vector.
+extern "C" int fdts_owned_to_local(fdts_handle e, const double *owned, double *local, void *stream) {
+  if (!e || !owned || !local) {
+    fdts_set_error("null argument");
+    return 1;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t nown = (size_t)e->cfg.num_owned_nodes, nn = (size_t)e->cfg.num_nodes, nc = (size_t)e->cfg.ncomp;
+  if (nown == 0) return 0;
+  if (e->cfg.layout == FDTS_INTERLEAVED || nc == 1) {
+    FDTS_CHECK(cudaMemcpyAsync(local, owned, sizeof(double) * nown * nc, cudaMemcpyDeviceToDevice, s));
+  } else {
+    FDTS_CHECK(cudaMemcpy2DAsync(local, sizeof(double) * nn, owned, sizeof(double) * nown, sizeof(double) * nown, nc,
+                                 cudaMemcpyDeviceToDevice, s));
+  }
+  return 0;
+}
+
 extern "C" int fdts_set_row_blocks(fdts_handle e, const int64_t *starts_host, int64_t nblocks) {
   if (!e || !starts_host) return 1;
+  if (e->cfg.cell_type != FDTS_SIMPLEX) {
+    fdts_set_error("gather plans are built for simplices (the quadrilateral path uses the quadrature kernels)");
+    return 1;
+  }
   FDTS_CHECK(cudaSetDevice(e->device));
   if (e->opt_plan_version == 2) {
     fdts_free_plan(e);
@@ -402,6 +440,10 @@ extern "C" int fdts_set_row_blocks(fdts_handle e, const int64_t *starts_host, in
 
 extern "C" int fdts_set_cell_tiles(fdts_handle e, const int64_t *starts_host, int64_t ntiles) {
   if (!e || !starts_host) return 1;
+  if (e->cfg.cell_type != FDTS_SIMPLEX) {
+    fdts_set_error("residual tile plans are built for simplices");
+    return 1;
+  }
   FDTS_CHECK(cudaSetDevice(e->device));
   return fdts_build_rplan(e, starts_host, ntiles);
 }

@@ -30,6 +30,9 @@ struct KArgs {
   int32_t nq;
   double shift;
   double p0, p1, p2;
+#ifdef FDTS_DEV_SWITCHES  // timing experiments only (results wrong); never compiled into the shipped library
+  int32_t dbg;
+#endif
 };
 
 template <int DIM, int NC>
@@ -152,6 +155,54 @@ __device__ __forceinline__ void eval_point(const double *__restrict__ Bq, const 
     }
 }
 
+// Geometry of cell type CELL: simplices are affine (computed once per cell, before the quadrature loop);
+// quadrilaterals carry the isoparametric Q1 map, J[k][a] = sum_v x_v[k] d phi_v / d xi_a at every point
+// (reference examples/cahn-hilliard.py:14-16).  NV = coordinate nodes per cell.
+template <int DIM, int CELL>
+struct CellGeom {
+  static constexpr int NV = CELL == FDTS_QUADRILATERAL ? 4 : DIM + 1;
+  double X[CELL == FDTS_QUADRILATERAL ? 4 : 1][DIM];  // vertex coordinates (quadrilaterals only)
+  Geom<DIM> g;
+  __device__ __forceinline__ void load(const double *__restrict__ coords, const int32_t *__restrict__ cell_coord_t,
+                                       int64_t ncells_total, int64_t c) {
+    int32_t cc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) cc[v] = cell_coord_t[v * ncells_total + c];
+    if constexpr (CELL == FDTS_QUADRILATERAL) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) X[v][k] = __ldg(coords + (int64_t)cc[v] * DIM + k);
+    } else {
+      compute_geometry<DIM>(coords, cc, g);
+    }
+  }
+  // Bq: tabulation at the point, Bq[(1 + a) * ND + v] = d phi_v / d xi_a
+  template <int ND>
+  __device__ __forceinline__ void at_point(const double *__restrict__ Bq) {
+    if constexpr (CELL == FDTS_QUADRILATERAL) {
+      static_assert(DIM == 2 && ND == 4, "quadrilaterals: Q1 in two dimensions");
+      double J[2][2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          double t = 0.0;
+#pragma unroll
+          for (int v = 0; v < 4; ++v) t += X[v][k] * Bq[(1 + a) * ND + v];
+          J[k][a] = t;
+        }
+      const double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+      const double r = 1.0 / det;
+      g.Jinv[0][0] = J[1][1] * r;
+      g.Jinv[0][1] = -J[0][1] * r;
+      g.Jinv[1][0] = -J[1][0] * r;
+      g.Jinv[1][1] = J[0][0] * r;
+      g.adet = fabs(det);
+    }
+  }
+};
+
 template <int DIM, int ND>
 __device__ __forceinline__ void load_tables(double *sB, double *sw, const KArgs &a) {
   const int nB = a.nq * (DIM + 1) * ND;
@@ -161,7 +212,7 @@ __device__ __forceinline__ void load_tables(double *sB, double *sw, const KArgs 
 }
 
 // ---------------------------------------------------------------- K1 residual
-template <int FAM, int DIM, int ND, int NC, int LAYOUT>
+template <int FAM, int DIM, int ND, int NC, int LAYOUT, int CELL = FDTS_SIMPLEX>
 __global__ void __launch_bounds__(128) residual_kernel(const KArgs a) {
   extern __shared__ double smem[];
   double *sB = smem;
@@ -169,13 +220,12 @@ __global__ void __launch_bounds__(128) residual_kernel(const KArgs a) {
   load_tables<DIM, ND>(sB, sw, a);
   const int64_t c = a.c0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.c1) return;
-  int32_t cc[DIM + 1], nodes[ND];
-#pragma unroll
-  for (int v = 0; v <= DIM; ++v) cc[v] = a.cell_coord_t[v * a.ncells_total + c];
+  int32_t nodes[ND];
 #pragma unroll
   for (int i = 0; i < ND; ++i) nodes[i] = a.cell_node_t[i * a.ncells_total + c];
-  Geom<DIM> g;
-  compute_geometry<DIM>(a.coords, cc, g);
+  CellGeom<DIM, CELL> cg;
+  cg.load(a.coords, a.cell_coord_t, a.ncells_total, c);
+  Geom<DIM> &g = cg.g;
   double ul[ND * NC], udl[ND * NC], Fe[ND * NC];
 #pragma unroll
   for (int i = 0; i < ND; ++i)
@@ -188,6 +238,7 @@ __global__ void __launch_bounds__(128) residual_kernel(const KArgs a) {
     }
   for (int q = 0; q < a.nq; ++q) {
     const double *Bq = sB + q * (DIM + 1) * ND;
+    cg.template at_point<ND>(Bq);
     Point<DIM, NC> s;
     eval_point<DIM, ND, NC>(Bq, g, ul, udl, s);
     double f0[NC], f1[NC][DIM];
@@ -225,7 +276,7 @@ __global__ void __launch_bounds__(128) residual_kernel(const KArgs a) {
 }
 
 // ---------------------------------------------------------------- K2 Jacobian
-template <int FAM, int DIM, int ND, int NC, int LAYOUT>
+template <int FAM, int DIM, int ND, int NC, int LAYOUT, int CELL = FDTS_SIMPLEX>
 __global__ void __launch_bounds__(128) jacobian_kernel(const KArgs a) {
   constexpr int NE = ND * NC;
   constexpr int RB = (48 / NE) < 1 ? 1 : ((48 / NE) > ND ? ND : (48 / NE));  // row nodes per pass
@@ -235,13 +286,12 @@ __global__ void __launch_bounds__(128) jacobian_kernel(const KArgs a) {
   load_tables<DIM, ND>(sB, sw, a);
   const int64_t c = a.c0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.c1) return;
-  int32_t cc[DIM + 1], nodes[ND];
-#pragma unroll
-  for (int v = 0; v <= DIM; ++v) cc[v] = a.cell_coord_t[v * a.ncells_total + c];
+  int32_t nodes[ND];
 #pragma unroll
   for (int i = 0; i < ND; ++i) nodes[i] = a.cell_node_t[i * a.ncells_total + c];
-  Geom<DIM> g;
-  compute_geometry<DIM>(a.coords, cc, g);
+  CellGeom<DIM, CELL> cg;
+  cg.load(a.coords, a.cell_coord_t, a.ncells_total, c);
+  Geom<DIM> &g = cg.g;
   double ul[ND * NC], udl[ND * NC];
 #pragma unroll
   for (int i = 0; i < ND; ++i)
@@ -265,6 +315,7 @@ __global__ void __launch_bounds__(128) jacobian_kernel(const KArgs a) {
         for (int e = 0; e < NE; ++e) acc[r][m][e] = 0.0;
     for (int q = 0; q < a.nq; ++q) {
       const double *Bq = sB + q * (DIM + 1) * ND;
+      cg.template at_point<ND>(Bq);
       Point<DIM, NC> s;
       eval_point<DIM, ND, NC>(Bq, g, ul, udl, s);
       const double wq = sw[q] * g.adet;
@@ -324,7 +375,7 @@ __global__ void __launch_bounds__(128) jacobian_kernel(const KArgs a) {
   }
 }
 
-template <int FAM, int DIM, int ND, int NC, int LAYOUT>
+template <int FAM, int DIM, int ND, int NC, int LAYOUT, int CELL = FDTS_SIMPLEX>
 int launch_generic(bool jac, const KArgs &a, cudaStream_t s) {
   const int64_t n = a.c1 - a.c0;
   if (n <= 0) return 0;
@@ -332,11 +383,11 @@ int launch_generic(bool jac, const KArgs &a, cudaStream_t s) {
   const int64_t blocks = (n + threads - 1) / threads;
   const size_t smem = sizeof(double) * (size_t)a.nq * ((DIM + 1) * ND + 1);
   if (jac) {
-    auto k = jacobian_kernel<FAM, DIM, ND, NC, LAYOUT>;
+    auto k = jacobian_kernel<FAM, DIM, ND, NC, LAYOUT, CELL>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<(unsigned)blocks, threads, smem, s>>>(a);
   } else {
-    auto k = residual_kernel<FAM, DIM, ND, NC, LAYOUT>;
+    auto k = residual_kernel<FAM, DIM, ND, NC, LAYOUT, CELL>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<(unsigned)blocks, threads, smem, s>>>(a);
   }
@@ -345,7 +396,11 @@ int launch_generic(bool jac, const KArgs &a, cudaStream_t s) {
 
 // scalar families: dims 1-3, degrees 1-3
 template <int FAM>
-int dispatch_scalar(bool jac, int dim, int degree, const KArgs &a, cudaStream_t s) {
+int dispatch_scalar(bool jac, int dim, int degree, const KArgs &a, cudaStream_t s, int cell_type = FDTS_SIMPLEX) {
+  if (cell_type == FDTS_QUADRILATERAL) {
+    if (dim == 2 && degree == 1) return launch_generic<FAM, 2, 4, 1, 0, FDTS_QUADRILATERAL>(jac, a, s);
+    return 3;
+  }
 #define CASE(D, K, N) \
   if (dim == D && degree == K) return launch_generic<FAM, D, N, 1, 0>(jac, a, s);
   CASE(1, 1, 2) CASE(1, 2, 3) CASE(1, 3, 4)

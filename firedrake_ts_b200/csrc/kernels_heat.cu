@@ -68,15 +68,44 @@ __global__ void __launch_bounds__(128) heat_residual_atomic(const KArgs a) {
   for (int i = 0; i < ND; ++i) nodes[i] = a.cell_node_t[i * a.ncells_total + c];
   const uint32_t rowok = a.rowmask[c];
   Geom<DIM> g;
+#ifdef FDTS_DEV_SWITCHES
+  if (FDTS_DEV(a, 64)) {  // experiment: no coordinate gathers
+    double X[DIM + 1][DIM];
+#pragma unroll
+    for (int v = 0; v <= DIM; ++v)
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) X[v][k] = 1e-3 * (double)(cc[v] % (97 + 13 * k)) + (v == k + 1 ? 1.0 : 0.0);
+    geometry_from_vertices<DIM>(X, g);
+  } else
+#endif
   compute_geometry<DIM>(a.coords, cc, g);
   double gm[NP];
   metric<DIM>(g, gm);
   double u[ND], ud[ND];
+#ifdef FDTS_DEV_SWITCHES
+  if (FDTS_DEV(a, 32)) {  // experiment: no state gathers
+#pragma unroll
+    for (int i = 0; i < ND; ++i) {
+      u[i] = 1e-9 * (double)nodes[i];
+      ud[i] = 2e-9 * (double)nodes[i];
+    }
+  } else
+#endif
 #pragma unroll
   for (int i = 0; i < ND; ++i) {
     u[i] = __ldg(a.x + nodes[i]);
     ud[i] = __ldg(a.xdot + nodes[i]);
   }
+#ifdef FDTS_DEV_SWITCHES
+  if (FDTS_DEV(a, 128)) {  // experiment: sum-factorised element vector
+    double f[ND];
+    heat_element_residual<DIM, DEG, VAR, ND, NP>(gm, g.adet, a.p0, u, ud, f);
+#pragma unroll
+    for (int i = 0; i < ND; ++i)
+      if (((rowok >> i) & 1u) && (!FDTS_DEV(a, 16) || f[i] == 1.2345e300)) red_add_f64(a.out + nodes[i], f[i]);
+    return;
+  }
+#endif
   static_for<ND>([&](auto I) {
     constexpr int i = decltype(I)::value;
     double mass = -a.p0 * T::M0[i];
@@ -96,6 +125,9 @@ __global__ void __launch_bounds__(128) heat_residual_atomic(const KArgs a) {
       });
       f = fma(gm[p], s, f);
     });
+#ifdef FDTS_DEV_SWITCHES
+    if (FDTS_DEV(a, 16) && f != 1.2345e300) return;  // experiment: no atomics (the value stays live)
+#endif
     if ((rowok >> i) & 1u) red_add_f64(a.out + nodes[i], f);
   });
 }

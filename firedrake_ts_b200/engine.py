@@ -17,7 +17,8 @@ import torch
 from . import fem
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libfdts_b200.so")
+# FDTS_B200_LIB: development override (tools/ load the build with the timing switches compiled in)
+LIB_PATH = os.environ.get("FDTS_B200_LIB") or os.path.join(_HERE, "csrc", "libfdts_b200.so")
 _LIB = None
 
 SYMBOLS = [
@@ -26,6 +27,7 @@ SYMBOLS = [
     "fdts_ifunction_range", "fdts_ijacobian_range", "fdts_ifunction_host", "fdts_ijacobian_host", "fdts_halo_pack",
     "fdts_halo_unpack", "fdts_launch_count", "fdts_measure_fp64_peak", "fdts_csr_spmv", "fdts_csr_spmv_warp", "fdts_csr_diagonal", "fdts_set_row_blocks",
     "fdts_set_cell_tiles", "fdts_nccl_unique_id", "fdts_halo_setup", "fdts_halo_exchange", "fdts_ifunction_exchange",
+    "fdts_owned_to_local",
 ]
 
 
@@ -37,7 +39,7 @@ class _Config(C.Structure):
     _fields_ = [
         ("dim", C.c_int32), ("degree", C.c_int32), ("nd", C.c_int32), ("ncomp", C.c_int32), ("layout", C.c_int32),
         ("family", C.c_int32), ("nq", C.c_int32), ("memspace", C.c_int32), ("device", C.c_int32),
-        ("reserved", C.c_int32),
+        ("cell_type", C.c_int32),
         ("num_cells", C.c_int64), ("num_interior_cells", C.c_int64), ("num_nodes", C.c_int64),
         ("num_owned_nodes", C.c_int64), ("num_coord_nodes", C.c_int64),
         ("coords", C.c_void_p), ("cell_coord", C.c_void_p), ("cell_node", C.c_void_p),
@@ -121,6 +123,7 @@ def load_library():
         lib.fdts_nccl_unique_id.argtypes = [C.c_char_p, C.c_void_p]
         lib.fdts_halo_setup.argtypes = [C.c_void_p, C.POINTER(_HaloConfig)]
         lib.fdts_halo_exchange.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.fdts_owned_to_local.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.fdts_ifunction_exchange.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _LIB = lib
     return _LIB
@@ -155,7 +158,8 @@ class Engine:
         dev = torch.device(device if device is not None else (m.device if m.device.type == "cuda" else "cuda:0"))
         self.device = dev
         self.form, self.V = form, V
-        et = fem.element_tables(V.dim, V.degree, form.qdegree, V.variant)
+        cell = getattr(m, "cell", "simplex")
+        et = fem.element_tables(V.dim, V.degree, form.qdegree, V.variant, cell)
         bc_nodes = torch.zeros(0, dtype=torch.int32)
         if bcs:
             bc_nodes = torch.unique(torch.cat([bc.nodes.to(torch.int64).cpu() for bc in bcs])).to(torch.int32)
@@ -173,6 +177,7 @@ class Engine:
         cfg.layout = 0 if V.layout == "interleaved" else 1
         cfg.family, cfg.nq, cfg.memspace = form.family, et.nq, 1
         cfg.device = dev.index or 0
+        cfg.cell_type = 1 if cell == "quadrilateral" else 0
         cfg.num_cells, cfg.num_interior_cells = m.num_cells, m.num_interior_cells
         cfg.num_nodes, cfg.num_owned_nodes = V.num_nodes, V.num_owned_nodes
         cfg.num_coord_nodes = m.num_coord_nodes

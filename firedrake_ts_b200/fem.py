@@ -39,12 +39,59 @@ EDGES = {
 FACES = {3: [(1, 2, 3), (0, 2, 3), (0, 1, 3), (0, 1, 2)]}
 
 
-def num_nodes(dim: int, degree: int) -> int:
+def num_nodes(dim: int, degree: int, cell: str = "simplex") -> int:
+    if cell == "quadrilateral":
+        return (degree + 1) ** dim
     return math.comb(degree + dim, dim)
 
 
+# ---------------------------------------------------------------------------
+# quadrilateral Q1 (reference examples/cahn-hilliard.py:14-16: UnitSquareMesh(96, 96, quadrilateral=True),
+# "Lagrange" 1).  Firedrake builds Q1 as the tensor product of two interval P1 elements, so the local node
+# order is the tensor-product order with the SECOND factor fastest: node l = 2*ix + iy sits at the
+# reference vertex (ix, iy) of [0,1]^2, and phi_l = a_ix(xi) a_iy(eta) with a_0(t) = 1 - t, a_1(t) = t.
+# The coordinate field is the same Q1 element (isoparametric bilinear map).
+# ---------------------------------------------------------------------------
+QUAD_VERTICES = [(0, 0), (0, 1), (1, 0), (1, 1)]
+
+
+def _check_quad(dim, degree):
+    if dim != 2 or degree != 1:
+        raise NotImplementedError("quadrilateral cells: Q1 in two dimensions only")
+
+
+def _tabulate_quad(points: np.ndarray) -> np.ndarray:
+    points = np.atleast_2d(np.asarray(points, dtype=float))
+    out = np.zeros((3, points.shape[0], 4))
+    for q, (x, y) in enumerate(points):
+        ax, ay = (1.0 - x, x), (1.0 - y, y)
+        dx, dy = (-1.0, 1.0), (-1.0, 1.0)
+        for l, (ix, iy) in enumerate(QUAD_VERTICES):
+            out[0, q, l] = ax[ix] * ay[iy]
+            out[1, q, l] = dx[ix] * ay[iy]
+            out[2, q, l] = ax[ix] * dy[iy]
+    return out
+
+
+def _quadrature_quad(degree: int):
+    """tensor Gauss-Legendre rule on [0,1]^2, exact for degree ``degree`` in each variable."""
+    n = max(int(degree), 1) // 2 + 1
+    x, w = _gauss_jacobi_01(n, 0)
+    pts = np.array([(x[i], x[j]) for i in range(n) for j in range(n)])
+    wts = np.array([w[i] * w[j] for i in range(n) for j in range(n)])
+    return pts, wts
+
+
 @functools.lru_cache(maxsize=None)
-def lattice_weights(dim: int, degree: int) -> np.ndarray:
+def lattice_weights(dim: int, degree: int, cell: str = "simplex") -> np.ndarray:
+    if cell == "quadrilateral":
+        _check_quad(dim, degree)
+        return np.eye(4, dtype=np.int64)  # Q1: the nodes are the cell's vertices
+    return _lattice_weights_simplex(dim, degree)
+
+
+@functools.lru_cache(maxsize=None)
+def _lattice_weights_simplex(dim: int, degree: int) -> np.ndarray:
     """Integer matrix W (nd x (dim+1)): ``degree`` times the barycentric
     coordinates of the *equispaced* Lagrange nodes in local (FIAT) order.
 
@@ -126,7 +173,10 @@ def _nodes_bary_mp(dim: int, degree: int, variant: str):
     return out
 
 
-def nodes_barycentric(dim: int, degree: int, variant: str = "gll") -> np.ndarray:
+def nodes_barycentric(dim: int, degree: int, variant: str = "gll", cell: str = "simplex") -> np.ndarray:
+    if cell == "quadrilateral":
+        _check_quad(dim, degree)
+        return np.eye(4)
     return np.array([[float(x) for x in b] for b in _nodes_bary_mp(dim, degree, variant)])
 
 
@@ -153,9 +203,12 @@ def _basis_coeffs(dim: int, degree: int, variant: str):
     return Vinv.T, mons
 
 
-def tabulate(dim: int, degree: int, points: np.ndarray, variant: str = "gll") -> np.ndarray:
+def tabulate(dim: int, degree: int, points: np.ndarray, variant: str = "gll", cell: str = "simplex") -> np.ndarray:
     """Return B[a, q, i]: a = 0 value of phi_i at point q, a = 1..dim the
     derivative with respect to reference coordinate xi_{a-1}."""
+    if cell == "quadrilateral":
+        _check_quad(dim, degree)
+        return _tabulate_quad(points)
     C, mons = _basis_coeffs(dim, degree, variant)
     points = np.atleast_2d(np.asarray(points, dtype=float))
     nq = points.shape[0]
@@ -259,7 +312,14 @@ def _grundmann_moeller(dim: int, s: int):
 
 
 @functools.lru_cache(maxsize=None)
-def quadrature(dim: int, degree: int):
+def quadrature(dim: int, degree: int, cell: str = "simplex"):
+    if cell == "quadrilateral":
+        return _quadrature_quad(degree)
+    return _quadrature_simplex(dim, degree)
+
+
+@functools.lru_cache(maxsize=None)
+def _quadrature_simplex(dim: int, degree: int):
     """Rule exact for polynomials of total degree <= ``degree`` on the reference
     simplex.  Returns (points[nq, dim], weights[nq]).  On affine cells every
     integrand of the supported forms is polynomial, so any exact rule gives the
@@ -312,22 +372,22 @@ class ElementTables:
     M0  : (nd,)            sum_q w_q B[q,0,i]   (integral of phi_i)
     """
 
-    def __init__(self, dim: int, degree: int, qdegree: int, variant: str = "gll"):
-        self.dim, self.degree, self.qdegree, self.variant = dim, degree, qdegree, variant
-        self.nd = num_nodes(dim, degree)
-        pts, w = quadrature(dim, qdegree)
+    def __init__(self, dim: int, degree: int, qdegree: int, variant: str = "gll", cell: str = "simplex"):
+        self.dim, self.degree, self.qdegree, self.variant, self.cell = dim, degree, qdegree, variant, cell
+        self.nd = num_nodes(dim, degree, cell)
+        pts, w = quadrature(dim, qdegree, cell)
         self.points, self.w = pts, np.ascontiguousarray(w)
         self.nq = len(w)
-        T = tabulate(dim, degree, pts, variant)  # (dim+1, nq, nd)
+        T = tabulate(dim, degree, pts, variant, cell)  # (dim+1, nq, nd)
         self.B = np.ascontiguousarray(np.transpose(T, (1, 0, 2)))
-        pr, wr = quadrature(dim, max(2 * degree, 1))
-        Tr = tabulate(dim, degree, pr, variant)
+        pr, wr = quadrature(dim, max(2 * degree, 1), cell)
+        Tr = tabulate(dim, degree, pr, variant, cell)
         self.R = np.ascontiguousarray(np.einsum("q,aqi,bqj->abij", wr, Tr, Tr))
         self.M0 = np.ascontiguousarray(np.einsum("q,qi->i", wr, Tr[0]))
-        self.nodes_bary = nodes_barycentric(dim, degree, variant)
-        self.W = lattice_weights(dim, degree)
+        self.nodes_bary = nodes_barycentric(dim, degree, variant, cell)
+        self.W = lattice_weights(dim, degree, cell)
 
 
 @functools.lru_cache(maxsize=None)
-def element_tables(dim: int, degree: int, qdegree: int, variant: str = "gll") -> ElementTables:
-    return ElementTables(dim, degree, qdegree, variant)
+def element_tables(dim: int, degree: int, qdegree: int, variant: str = "gll", cell: str = "simplex") -> ElementTables:
+    return ElementTables(dim, degree, qdegree, variant, cell)

@@ -167,9 +167,13 @@ class SimplexMesh:
     """
 
     def __init__(self, shape, lengths=None, periodic=False, partition: Partition | None = None,
-                 tile=0, device="cpu"):
+                 tile=0, device="cpu", quadrilateral=False):
         self.shape = tuple(int(s) for s in shape)
         self.dim = len(self.shape)
+        # quadrilateral=True: one Q1 cell per lattice square (reference examples/cahn-hilliard.py:14,
+        # UnitSquareMesh(96, 96, quadrilateral=True)); vertices in the tensor-product order of fem.QUAD_VERTICES
+        self.cell = "quadrilateral" if quadrilateral else "simplex"
+        assert not quadrilateral or self.dim == 2, "quadrilateral cells: two dimensions only"
         self.lengths = tuple(float(x) for x in (lengths or [1.0] * self.dim))
         self.periodic = bool(periodic)
         assert not self.periodic or self.dim == 1, "periodic meshes: 1-D only"
@@ -216,10 +220,12 @@ class SimplexMesh:
     def _build_cells(self):
         dim, dev = self.dim, self.device
         cube = self._cube_list()  # (ncube, dim) global cube coords
-        tmpl = torch.tensor(_CELLS[dim], device=dev, dtype=torch.int64)  # (cpc, dim+1, dim)
+        cells = [fem.QUAD_VERTICES] if self.cell == "quadrilateral" else _CELLS[dim]
+        tmpl = torch.tensor(cells, device=dev, dtype=torch.int64)  # (cpc, nverts, dim)
         self.cells_per_cube = tmpl.shape[0]
-        # (ncube, cpc, dim+1, dim) -> (nc, dim+1, dim): global vertex-lattice coordinates
-        self.cell_vlat = (cube[:, None, None, :] + tmpl[None]).reshape(-1, dim + 1, dim)
+        self.nverts = tmpl.shape[1]  # coordinate nodes per cell: dim+1 (simplex) or 4 (quadrilateral)
+        # (ncube, cpc, nverts, dim) -> (nc, nverts, dim): global vertex-lattice coordinates
+        self.cell_vlat = (cube[:, None, None, :] + tmpl[None]).reshape(-1, self.nverts, dim)
         self.num_cells = self.cell_vlat.shape[0]
         self.num_interior_cells = self.num_interior_cubes * self.cells_per_cube
         # coordinate field: P1 (DG-like copy of the last vertex for periodic meshes)
@@ -266,7 +272,7 @@ class SimplexMesh:
     # -- counts ------------------------------------------------------------
     @property
     def global_num_cells(self):
-        return int(np.prod(self.shape)) * len(_CELLS[self.dim])
+        return int(np.prod(self.shape)) * self.cells_per_cube
 
 
 class FunctionSpace:
@@ -289,7 +295,7 @@ class FunctionSpace:
         self.dim = mesh.dim
         self.tile = (tuple(t * degree for t in mesh.tile) if tile is None else _tile_tuple(tile, mesh.dim))
         self.tile_offset = int(tile_offset)
-        self.nd = fem.num_nodes(self.dim, degree)
+        self.nd = fem.num_nodes(self.dim, degree, mesh.cell)
         self._build()
 
     # lattice helpers --------------------------------------------------------
@@ -395,7 +401,7 @@ class FunctionSpace:
     def _build(self):
         m, k, dev = self.mesh, self.degree, self.mesh.device
         dim = m.dim
-        W = torch.tensor(fem.lattice_weights(dim, k), device=dev, dtype=torch.int64)  # (nd, dim+1)
+        W = torch.tensor(fem.lattice_weights(dim, k, m.cell), device=dev, dtype=torch.int64)  # (nd, nverts)
         gd = torch.tensor(self._gdims(), device=dev, dtype=torch.int64)
         cols = []
         for l in range(self.nd):
@@ -422,13 +428,13 @@ class FunctionSpace:
         """node coordinates, global ids and boundary flags for local nodes."""
         m, k, dev = self.mesh, self.degree, self.mesh.device
         dim = m.dim
-        bary = torch.tensor(fem.nodes_barycentric(dim, k, self.variant), device=dev, dtype=torch.float64)
-        W = torch.tensor(fem.lattice_weights(dim, k), device=dev, dtype=torch.int64)
+        bary = torch.tensor(fem.nodes_barycentric(dim, k, self.variant, m.cell), device=dev, dtype=torch.float64)
+        W = torch.tensor(fem.lattice_weights(dim, k, m.cell), device=dev, dtype=torch.int64)
         h = torch.tensor([m.lengths[a] / m.shape[a] for a in range(dim)], dtype=torch.float64, device=dev)
         nn = self.num_nodes
         self.node_coords = torch.zeros((nn, dim), dtype=torch.float64, device=dev)
         lat = torch.zeros((nn, dim), dtype=torch.int64, device=dev)
-        vx = m.cell_vlat.to(torch.float64) * h  # (nc, dim+1, dim)
+        vx = m.cell_vlat.to(torch.float64) * h  # (nc, nverts, dim)
         gd = torch.tensor(self._gdims(), device=dev, dtype=torch.int64)
         for l in range(self.nd):
             idx = self.cell_node_map[:, l].to(torch.int64)
@@ -561,8 +567,8 @@ def PeriodicIntervalMesh(n, length, **kw):
     return SimplexMesh((n,), lengths=(length,), periodic=True, **kw)
 
 
-def UnitSquareMesh(nx, ny=None, **kw):
-    return SimplexMesh((nx, ny or nx), **kw)
+def UnitSquareMesh(nx, ny=None, quadrilateral=False, **kw):
+    return SimplexMesh((nx, ny or nx), quadrilateral=quadrilateral, **kw)
 
 
 def UnitCubeMesh(nx, ny=None, nz=None, **kw):

@@ -51,6 +51,10 @@ typedef struct fdts_engine *fdts_handle;
 enum { FDTS_HEAT = 0, FDTS_BURGERS = 1, FDTS_BBM = 2, FDTS_CAHN_HILLIARD = 3, FDTS_DIFFUSION = 4 };
 enum { FDTS_INTERLEAVED = 0, FDTS_BLOCKED = 1 };
 enum { FDTS_MEM_HOST = 0, FDTS_MEM_DEVICE = 1 };
+/* FDTS_QUADRILATERAL: Q1 cells with the isoparametric bilinear map (reference examples/cahn-hilliard.py:14-16,
+ * UnitSquareMesh(96, 96, quadrilateral=True)); local node / vertex l = 2*ix + iy (tensor-product order, second
+ * factor fastest); cell_coord has 4 columns and B is the Q1 tabulation at the tensor Gauss points. */
+enum { FDTS_SIMPLEX = 0, FDTS_QUADRILATERAL = 1 };
 
 typedef struct {
   int32_t dim;       /* 1, 2, 3 */
@@ -62,14 +66,14 @@ typedef struct {
   int32_t nq;        /* quadrature points */
   int32_t memspace;  /* where the arrays below live: FDTS_MEM_HOST / FDTS_MEM_DEVICE */
   int32_t device;    /* CUDA device ordinal */
-  int32_t reserved;
+  int32_t cell_type; /* FDTS_SIMPLEX / FDTS_QUADRILATERAL (dim 2, degree 1) */
   int64_t num_cells;          /* local cells, interior cells first */
   int64_t num_interior_cells; /* cells touching no ghost node */
   int64_t num_nodes;          /* local nodes: owned first, then ghosts */
   int64_t num_owned_nodes;
   int64_t num_coord_nodes;
   const double *coords;       /* num_coord_nodes x dim */
-  const int32_t *cell_coord;  /* num_cells x (dim+1) */
+  const int32_t *cell_coord;  /* num_cells x (dim+1); quadrilaterals: num_cells x 4 */
   const int32_t *cell_node;   /* num_cells x nd */
   const double *B;            /* nq x (dim+1) x nd   basis values / reference derivatives */
   const double *w;            /* nq */
@@ -179,6 +183,11 @@ int fdts_halo_exchange(fdts_handle h, double *x, double *xdot, void *stream);
 /* IFunction with the exchange hidden behind the interior cells: pack -> grouped send/recv on the library's
  * communication stream -> interior cells -> wait -> unpack -> remaining cells, all enqueued by one call */
 int fdts_ifunction_exchange(fdts_handle h, double t, double *x, double *xdot, double *f, void *stream);
+
+/* global (owned dofs, what PETSc's TS passes to form_function / form_jacobian as X, Xdot) -> head of the local
+ * (owned + ghost) vector the kernels read; replaces the `X.copy(v)` into ctx._x.dat.vec_wo of the reference
+ * (firedrake_ts/solving_utils.py:249-252, 294-297); follow with fdts_halo_exchange on more than one rank */
+int fdts_owned_to_local(fdts_handle h, const double *owned, double *local, void *stream);
 
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t fdts_launch_count(fdts_handle h);

@@ -36,6 +36,7 @@ class _Problem(C.Structure):
         ("B", C.c_void_p), ("w", C.c_void_p),
         ("params", C.c_double * 4),
         ("num_bc_nodes", C.c_int64), ("bc_nodes", C.c_void_p),
+        ("cell_type", C.c_int32),
     ]
 
 
@@ -59,7 +60,7 @@ class Oracle:
     """CPU restatement of one assembly problem (same inputs as engine.Engine)."""
 
     def __init__(self, *, dim, nd, ncomp, layout, family, params, coords, cell_coord, cell_node, B, w,
-                 num_nodes, num_owned_nodes, bc_nodes=None):
+                 num_nodes, num_owned_nodes, bc_nodes=None, cell_type=0):
         self._keep = dict(
             coords=_np(coords, np.float64), cell_coord=_np(cell_coord, np.int32), cell_node=_np(cell_node, np.int32),
             B=_np(B, np.float64), w=_np(w, np.float64),
@@ -78,6 +79,8 @@ class Oracle:
         for i, v in enumerate(list(params)[:4]):
             p.params[i] = float(v)
         p.num_bc_nodes = len(k["bc"])
+        p.cell_type = int(cell_type)
+        assert k["cell_coord"].shape[1] == (4 if cell_type == 1 else dim + 1)
         self.p = p
         self.ncomp, self.nd = ncomp, nd
         self.num_nodes, self.num_owned_nodes = num_nodes, num_owned_nodes
@@ -89,14 +92,15 @@ class Oracle:
         from firedrake_ts_b200 import fem
         V = form.space
         m = V.mesh
-        et = fem.element_tables(V.dim, V.degree, form.qdegree, V.variant)
+        et = fem.element_tables(V.dim, V.degree, form.qdegree, V.variant, m.cell)
         bc_nodes = None
         if bcs:
             import torch
             bc_nodes = torch.unique(torch.cat([bc.nodes.to(torch.int64) for bc in bcs])).to(torch.int32)
         return cls(dim=V.dim, nd=V.nd, ncomp=V.ncomp, layout=V.layout, family=form.family, params=form.params,
                    coords=m.coords, cell_coord=m.cell_coord_map, cell_node=V.cell_node_map, B=et.B, w=et.w,
-                   num_nodes=V.num_nodes, num_owned_nodes=V.num_owned_nodes, bc_nodes=bc_nodes)
+                   num_nodes=V.num_nodes, num_owned_nodes=V.num_owned_nodes, bc_nodes=bc_nodes,
+                   cell_type=1 if m.cell == "quadrilateral" else 0)
 
     # -- residual ---------------------------------------------------------
     def ifunction(self, t, u, udot):

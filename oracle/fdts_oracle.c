@@ -44,13 +44,16 @@ typedef struct {
   int32_t dim, nd, ncomp, layout, family, nq;
   int64_t num_cells, num_nodes, num_owned_nodes, num_coord_nodes;
   const double *coords;        /* num_coord_nodes x dim */
-  const int32_t *cell_coord;   /* num_cells x (dim+1) */
+  const int32_t *cell_coord;   /* num_cells x (dim+1), quadrilaterals: x 4 */
   const int32_t *cell_node;    /* num_cells x nd */
   const double *B;             /* nq x (dim+1) x nd */
   const double *w;             /* nq */
   double params[4];
   int64_t num_bc_nodes;
   const int32_t *bc_nodes;     /* node ids with Dirichlet conditions (all components) */
+  int32_t cell_type;           /* 0 simplex (affine), 1 quadrilateral with the isoparametric Q1 map
+                                  (examples/cahn-hilliard.py:14: UnitSquareMesh(..., quadrilateral=True));
+                                  cell_coord then has 4 columns and B's derivative rows are the map's */
 } oracle_problem;
 
 static inline int64_t dof_local(const oracle_problem *p, int64_t node, int comp) {
@@ -60,15 +63,29 @@ static inline int64_t dof_owned(const oracle_problem *p, int64_t node, int comp)
   return p->layout == LAYOUT_INTERLEAVED ? node * p->ncomp + comp : (int64_t)comp * p->num_owned_nodes + node;
 }
 
-/* affine geometry: Jinv[a][k] = d xi_a / d x_k, returns |det J| */
-static double geometry(const oracle_problem *p, int64_t c, double Jinv[MAXD][MAXD]) {
+/* geometry at quadrature point q: Jinv[a][k] = d xi_a / d x_k, returns |det J|.
+ * Simplices: affine, J[k][a] = x_a[k] - x_0[k] (the same at every point).  Quadrilaterals: the coordinate
+ * field is Q1 on the cell's 4 vertices, J[k][a] = sum_v x_v[k] d phi_v / d xi_a at the point. */
+static double geometry(const oracle_problem *p, int64_t c, int q, double Jinv[MAXD][MAXD]) {
   const int d = p->dim;
-  double X[MAXD + 1][MAXD];
-  for (int v = 0; v <= d; ++v)
-    for (int k = 0; k < d; ++k) X[v][k] = p->coords[(int64_t)p->cell_coord[c * (d + 1) + v] * d + k];
-  double J[MAXD][MAXD]; /* J[k][a] = x_a[k] - x_0[k] */
-  for (int k = 0; k < d; ++k)
-    for (int a = 0; a < d; ++a) J[k][a] = X[a + 1][k] - X[0][k];
+  double X[4][MAXD];
+  double J[MAXD][MAXD];
+  if (p->cell_type == 1) {
+    const double *Bq = p->B + (int64_t)q * (d + 1) * p->nd;
+    for (int v = 0; v < 4; ++v)
+      for (int k = 0; k < d; ++k) X[v][k] = p->coords[(int64_t)p->cell_coord[c * 4 + v] * d + k];
+    for (int k = 0; k < d; ++k)
+      for (int a = 0; a < d; ++a) {
+        double s = 0.0;
+        for (int v = 0; v < 4; ++v) s += X[v][k] * Bq[(1 + a) * p->nd + v];
+        J[k][a] = s;
+      }
+  } else {
+    for (int v = 0; v <= d; ++v)
+      for (int k = 0; k < d; ++k) X[v][k] = p->coords[(int64_t)p->cell_coord[c * (d + 1) + v] * d + k];
+    for (int k = 0; k < d; ++k)
+      for (int a = 0; a < d; ++a) J[k][a] = X[a + 1][k] - X[0][k];
+  }
   double det;
   if (d == 1) {
     det = J[0][0];
@@ -142,10 +159,11 @@ static inline double dotd(const double *a, const double *b, int d) {
 static void element_residual(const oracle_problem *p, int64_t c, const double *ul, const double *udl, double *Fe) {
   const int d = p->dim, nd = p->nd, nc = p->ncomp;
   double Jinv[MAXD][MAXD];
-  double adet = geometry(p, c, Jinv);
   for (int i = 0; i < nd * nc; ++i) Fe[i] = 0.0;
   qpoint s;
+  double adet = 0.0;
   for (int q = 0; q < p->nq; ++q) {
+    if (q == 0 || p->cell_type == 1) adet = geometry(p, c, q, Jinv); /* affine cells: once per cell */
     eval_qpoint(p, q, adet, Jinv, ul, udl, &s);
     for (int i = 0; i < nd; ++i) {
       const double ph = s.phi[i];
@@ -183,10 +201,11 @@ static void element_jacobian(const oracle_problem *p, int64_t c, const double *u
                              double *Ae) {
   const int d = p->dim, nd = p->nd, nc = p->ncomp, ne = nd * nc;
   double Jinv[MAXD][MAXD];
-  double adet = geometry(p, c, Jinv);
   for (int i = 0; i < ne * ne; ++i) Ae[i] = 0.0;
   qpoint s;
+  double adet = 0.0;
   for (int q = 0; q < p->nq; ++q) {
+    if (q == 0 || p->cell_type == 1) adet = geometry(p, c, q, Jinv); /* affine cells: once per cell */
     eval_qpoint(p, q, adet, Jinv, ul, udl, &s);
     for (int i = 0; i < nd; ++i)
       for (int j = 0; j < nd; ++j) {

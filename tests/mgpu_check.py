@@ -61,6 +61,56 @@ def main():
         torch.cuda.synchronize()
         dist.barrier()
 
+    # the Firedrake adapter on the partition: PETSc-shaped global Vecs (owned dofs) in, ghosts refreshed through
+    # the star-forest neighbour lists (explicit ghost node lists) and the library's NCCL exchange
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from firedrake_ts_b200 import adapter_firedrake as A
+    from fake_petsc import (FakeBC, FakeFiredrakeSpace, FakeMat, FakeProblem, FakeTS, FakeVec, StubRefTSContext,
+                            fake_dmhooks, sf_graph_of)
+
+    class Comm:  # mpi4py-shaped communicator over torch.distributed
+        rank, size = rank, world
+
+        @staticmethod
+        def alltoall(lists):
+            box = [None] * world
+            dist.all_gather_object(box, lists)
+            return [box[o][rank] for o in range(world)]
+
+        @staticmethod
+        def bcast(obj, root=0):
+            b = [obj]
+            dist.broadcast_object_list(b, src=root)
+            return b[0]
+
+    for family, dim, degree, n in (("heat", 3, 2, 6), ("cahn_hilliard", 2, 1, 10)):
+        part = M.Partition(M.default_grid(world, dim), rank)
+        form, bcs, u, udot = make_problem(family, dim, degree, n, partition=part, tile=2, device=dev)
+        V = form.space
+        eng = Engine(form, bcs, device=dev)
+        rp, ci = eng.csr()
+        Vfd = FakeFiredrakeSpace(V, comm=Comm, sf_graph=sf_graph_of(V))
+        problem = FakeProblem(Vfd, V.num_owned_dofs, bcs=[FakeBC(bc.nodes.cpu().numpy()) for bc in bcs], device=dev)
+        jac = FakeMat(rp.cpu().numpy(), ci.cpu().numpy(), device=dev)
+        cls = A.make_context_class(StubRefTSContext, hooks=fake_dmhooks, values_pointer=lambda m: m.values.data_ptr())
+        ctx = cls(problem, appctx={"b200_form": (form.family, form.params)}, jac=jac)
+        assert ctx._b200.nranks == world and ctx._b200.engine.has_native_halo
+
+        def owned(vec):  # global (owned-dof) view of a local vector
+            if V.layout == "interleaved":
+                return vec[: V.num_owned_dofs].clone()
+            return torch.cat([vec[m * V.num_nodes: m * V.num_nodes + V.num_owned_nodes] for m in range(V.ncomp)])
+
+        X, Xd, F = FakeVec(array=owned(u.data)), FakeVec(array=owned(udot.data)), FakeVec(V.num_owned_dofs, device=dev)
+        ts = FakeTS(ctx)
+        cls.form_function(ts, 0.0, X, Xd, F)
+        assert rel_err(F.array.cpu().numpy(), eng.ifunction(0.0, u.data, udot.data).cpu().numpy()) < 1e-14, (family, rank)
+        assert torch.equal(ctx._b200.x, u.data) and torch.equal(ctx._b200.xdot, udot.data), (family, rank, "ghosts")
+        cls.form_jacobian(ts, 0.0, X, Xd, 10.0, jac, jac)
+        assert rel_err(jac.values.cpu().numpy(), eng.ijacobian(0.0, u.data, udot.data, 10.0).cpu().numpy()) < 1e-14
+        torch.cuda.synchronize()
+        dist.barrier()
+
     # DAESolver on the partition vs single rank
     n = 6
     part = M.Partition(M.default_grid(world, 2), rank)

@@ -86,6 +86,24 @@ def test_cahn_hilliard_trajectory():
     assert (uo - ug).abs().max() < TRAJ_TOL * max(1.0, float(uo.abs().max()))
 
 
+def test_cahn_hilliard_literal_quadrilateral_trajectory():
+    """examples/cahn-hilliard.py:14-16 as written: UnitSquareMesh(n, n, quadrilateral=True), Q1 x Q1."""
+    def build():
+        msh = fts.UnitSquareMesh(10, 10, quadrilateral=True)
+        ME = fts.FunctionSpace(msh, 1, ncomp=2, layout="blocked")
+        u, u_t = fts.Function(ME), fts.Function(ME)
+        rng = np.random.default_rng(11)
+        u.sub(0).copy_(torch.from_numpy(0.63 + 0.2 * (0.5 - rng.random(ME.num_nodes))))
+        return forms.cahn_hilliard(u, u_t, lmbda=1.0e-2), [], u, u_t
+
+    dt = 5.0e-6
+    params = {"pc_type": "lu", "snes_rtol": 1e-9, "snes_atol": 1e-10, "snes_stol": 1e-16, "snes_max_it": 30}
+    (uo, so, _), (ug, sg, s) = run_both(build, (0.0, 2 * dt), params, dt=dt)
+    assert so == sg == 2
+    assert (uo - ug).abs().max() < TRAJ_TOL * max(1.0, float(uo.abs().max()))
+    assert s._ctx.engine.launch_count > 0
+
+
 def test_bbm_trajectory():
     def build():
         msh = fts.PeriodicIntervalMesh(100, 100.0)

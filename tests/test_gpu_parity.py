@@ -241,3 +241,31 @@ def test_imex_split_forms(dim, degree, n):
     isbc_diag = np.abs(out["F"][1] - out["G"][1] - out["heat"][1])  # Dirichlet rows: 1 - 1 vs 1
     assert np.sort(isbc_diag)[-1] <= 1.0 + 1e-12 and np.count_nonzero(isbc_diag > 1e-10) == sum(
         int(b.nodes.numel()) for b in bcs)
+
+
+@pytest.mark.parametrize("family", ["heat", "diffusion", "cahn_hilliard"])
+@pytest.mark.parametrize("warp", [0.0, 0.03])
+@pytest.mark.parametrize("tile", [0, 2])
+def test_quadrilateral_engine_matches_oracle(family, warp, tile):
+    """Q1 (x Q1) on quadrilaterals, affine and non-affine cells (reference examples/cahn-hilliard.py:14-16):
+    pattern bit-exact, values 1e-12."""
+    from firedrake_ts_b200.engine import Engine, EngineError
+    from oracle import Oracle
+
+    form, bcs, u, udot = make_problem(family, 2, 1, 9, tile=tile, quadrilateral=True, warp=warp)
+    orc = Oracle.from_form(form, bcs)
+    eng = Engine(form, bcs, device="cuda:0")
+    rp, ci = orc.pattern()
+    grp, gci = eng.csr()
+    assert np.array_equal(grp.cpu().numpy(), rp)
+    assert np.array_equal(gci.cpu().numpy(), ci)
+    x, xd = u.data.cuda(), udot.data.cuda()
+    F = eng.ifunction(0.0, x, xd).cpu().numpy()
+    assert rel_err(F, orc.ifunction(0.0, u.data, udot.data)) < TOL
+    Jv = eng.ijacobian(0.0, x, xd, 10.0).cpu().numpy()
+    assert rel_err(Jv, orc.ijacobian(0.0, u.data, udot.data, 10.0)) < TOL
+    # the simplex-only fast paths refuse loudly
+    with pytest.raises(EngineError):
+        eng.set_option("scatter", 2)
+    with pytest.raises(EngineError):
+        eng.set_row_blocks(torch.tensor([0, eng.num_rows]))

@@ -60,6 +60,8 @@ if a.scatter == 2:
           "vmax", eng.get_option("plan_vertices_max"), "residual tiles", eng.get_option("residual_tiles"),
           "patterns", eng.get_option("residual_patterns"), flush=True)
 x, xd = u.data, udot.data
+if a.debug:
+    eng.set_option("debug", a.debug)  # needs the development build (FDTS_B200_LIB=.../libfdts_b200_dev.so)
 if a.dmma >= 0:
     eng.set_option("dmma", a.dmma)
 F = torch.empty(eng.num_rows, dtype=torch.float64, device="cuda")
