@@ -8,8 +8,9 @@ Same names, argument meaning and error behaviour as the reference's
 ``_time``/``_shift`` Constants.  What changes is what sits behind
 ``_assemble_residual`` / ``_assemble_jac``: the B200 engine (engine.Engine)
 writing straight into the device-resident Vec / AIJ value arrays, plus a halo
-exchange in place of PyOP2's.  The IMEX RHS branch (solving_utils.py:320-384),
-``split`` and ``compute_operators`` are out of scope.
+exchange in place of PyOP2's.  The IMEX RHS branch (solving_utils.py:320-384) and ``split``
+(:145-233, field sub-contexts of mixed spaces for fieldsplit preconditioners) are here as well;
+``compute_operators`` is out of scope.
 """
 from __future__ import annotations
 
@@ -354,6 +355,26 @@ class _TSContext:
             if self.project_rhs:
                 self._rhs_projection_solver.solve(self._projected_G, self._G_vec)
 
+    # -- field sub-contexts (reference :145-233) ---------------------------------------------------
+    def split(self, fields):
+        r"""Contexts of the sub-problems on ``fields`` (an iterable of field-index tuples) of a mixed space:
+        each one assembles the rows ``field`` of F and the diagonal block (field, field) of J, with the other
+        fields of the solution entering as coefficients (their data are shared with this context's
+        Functions, as the reference shares the Dats).  Cached per ``fields`` like the reference's
+        ``self._splits``.  The engine assembles the monolithic system once and the sub-context reads its
+        rows / its block out of it, so no second set of kernels is needed."""
+        fields = tuple(tuple(int(i) for i in f) for f in fields)
+        splits = self._splits.get(fields)
+        if splits is not None:
+            return splits
+        V = self._x.function_space()
+        nfields = V.ncomp if self.is_mixed else 1
+        for f in fields:
+            if not f or any(i < 0 or i >= nfields for i in f) or len(set(f)) != len(f):
+                raise ValueError(f"split: field tuple {f} is not a subset of the {nfields} fields of the space")
+        splits = [_SplitContext(self, f) for f in fields]
+        return self._splits.setdefault(fields, splits)
+
     def set_nullspace(self, nullspace, ises=None, transpose=False, near=False):
         # three separate attachments, as MatSetNullSpace / MatSetTransposeNullSpace / MatSetNearNullSpace
         # keep them (reference solving_utils.py:314-317 re-attaches all three after every assembly)
@@ -489,3 +510,117 @@ class _TSContext:
         ctx.set_nullspace(ctx._nullspace, None, transpose=False, near=False)
         ctx.set_nullspace(ctx._nullspace_T, None, transpose=True, near=False)
         ctx.set_nullspace(ctx._near_nullspace, None, transpose=False, near=True)
+
+
+class _SplitContext:
+    """Sub-problem of a mixed problem on the fields ``field`` (reference ``_TSContext.split``,
+    solving_utils.py:145-233): same callback protocol as ``_TSContext``; ``_x`` / ``_xdot`` are Functions on the
+    sub-space whose values are written through to the parent's Functions; ``_jac`` holds the diagonal block
+    (field, field) of the parent's AIJ pattern."""
+
+    def __init__(self, parent, field):
+        from . import mesh as M
+        from .function import Function
+
+        self.parent, self.field = parent, tuple(field)
+        self._problem = parent._problem
+        self.appctx, self.comm = parent.appctx, parent.comm
+        self.mat_type, self.pmat_type = parent.mat_type, parent.pmat_type
+        V = parent._x.function_space()
+        nf = len(self.field)
+        dev = parent._device
+        self._pre_jacobian_callback = self._pre_function_callback = None
+        self._post_jacobian_callback = self._post_function_callback = None
+        self._jacobian_assembled = False
+        self._time, self._shift = parent._time, parent._shift
+        self.Jp = None
+        if not parent.is_mixed:  # scalar / vector space: the only field is the whole problem
+            self.space = V
+            self.rows = torch.arange(V.num_owned_dofs, device=dev)
+            self.cols_local = torch.arange(V.num_dofs, device=dev)
+        else:
+            cache = V.__dict__.setdefault("_sub_spaces", {})
+            if nf not in cache:
+                cache[nf] = M.FunctionSpace(V.mesh, V.degree, ncomp=nf, layout="blocked" if nf > 1 else "interleaved",
+                                            variant=V.variant, tile=V.tile, tile_offset=V.tile_offset)
+            self.space = cache[nf]
+            nown, nn = V.num_owned_nodes, V.num_nodes
+            self.rows = torch.cat([torch.arange(m * nown, (m + 1) * nown, device=dev) for m in self.field])
+            self.cols_local = torch.cat([torch.arange(m * nn, (m + 1) * nn, device=dev) for m in self.field])
+        Vs = self.space
+        self._x, self._xdot = Function(Vs, device=dev), Function(Vs, device=dev)
+        self._pull()
+        # diagonal block of the parent's pattern: entries in the rows of `field` whose column lies in `field`
+        pm = parent._jac.petscmat
+        rp, ci = pm.rowptr, pm.colidx.to(torch.int64)
+        newcol = torch.full((V.num_dofs,), -1, dtype=torch.int64, device=ci.device)
+        newcol[self.cols_local.to(ci.device)] = torch.arange(self.cols_local.numel(), device=ci.device)
+        rows = self.rows.to(rp.device)
+        lens = rp[rows + 1] - rp[rows]
+        start = torch.repeat_interleave(rp[rows], lens)
+        within = torch.arange(int(lens.sum()), device=rp.device) - torch.repeat_interleave(torch.cumsum(lens, 0) - lens, lens)
+        entry = start + within  # parent CSR slots of all entries in the selected rows, row by row
+        keep = newcol[ci[entry]] >= 0
+        rowid = torch.repeat_interleave(torch.arange(rows.numel(), device=rp.device), lens)[keep]
+        self.slots = entry[keep]
+        sub_rp = torch.zeros(rows.numel() + 1, dtype=torch.int64, device=rp.device)
+        sub_rp[1:] = torch.cumsum(torch.bincount(rowid, minlength=rows.numel()), 0)
+        sub_ci = newcol[ci[self.slots]].to(torch.int32)
+        values = torch.zeros(self.slots.numel(), dtype=torch.float64, device=pm.values.device)
+        halo = None
+        if parent._halo is not None:
+            from .halo import HaloExchange
+
+            halo = HaloExchange(Vs, None, group=parent.comm, device=dev)
+        self._halo = halo
+        self._F = Vec(torch.zeros(rows.numel(), dtype=torch.float64, device=dev), parent.comm)
+        self._jac = _Assembled(Mat(sub_rp, sub_ci, values, Vs.num_dofs, halo=halo, space=Vs))
+        self._pjac = self._jac
+
+    # values of the sub-Functions <-> the parent's Functions (local vectors, ghosts included)
+    def _pull(self):
+        self._x.data.copy_(self.parent._x.data[self.cols_local])
+        self._xdot.data.copy_(self.parent._xdot.data[self.cols_local])
+
+    def _push(self):
+        self.parent._x.data[self.cols_local] = self._x.data
+        self.parent._xdot.data[self.cols_local] = self._xdot.data
+
+    def extract_jacobian_block(self):
+        """copy the block out of the parent's assembled Jacobian (no assembly)"""
+        self._jac.petscmat.values.copy_(self.parent._jac.petscmat.values[self.slots])
+        return self._jac
+
+    def set_ifunction(self, ts):
+        ts.setIFunction(self.form_function, self._F)
+
+    def set_ijacobian(self, ts):
+        ts.setIJacobian(self.form_jacobian, J=self._jac.petscmat, P=self._pjac.petscmat)
+
+    def _assemble_parent(self, t, X, Xdot):
+        p = self.parent
+        self._x.set_owned(X.array)
+        self._xdot.set_owned(Xdot.array)
+        self._push()
+        p._refresh_halo()
+        p._time.assign(t)
+
+    @staticmethod
+    def form_function(ts, t, X, Xdot, F):
+        ctx = dmhooks.get_appctx(ts.getDM())
+        p = ctx.parent
+        ctx._assemble_parent(t, X, Xdot)
+        p._assemble_residual(tensor=p._F)
+        ctx._F.array.copy_(p._F.array[ctx.rows])
+        ctx._F.copy(F)
+
+    @staticmethod
+    def form_jacobian(ts, t, X, Xdot, shift, J, P):
+        ctx = dmhooks.get_appctx(ts.getDM())
+        p = ctx.parent
+        assert J.handle == ctx._jac.petscmat.handle
+        ctx._jacobian_assembled = True
+        ctx._assemble_parent(t, X, Xdot)
+        p._shift.assign(shift)
+        p._assemble_jac(p._jac)
+        ctx.extract_jacobian_block()

@@ -136,6 +136,8 @@ class KSP:
         self.type, self.pc_type = "gmres", "jacobi"
         self.rtol, self.atol, self.max_it, self.restart = 1e-5, 1e-50, 10000, 30
         self.its = 0
+        self.options = {}       # the full option dictionary (fieldsplit_* sub-options are read from it)
+        self.prec = None        # pc_type fieldsplit: the block preconditioner built by the TS for this solve
 
 
 class ConvergedReason:
@@ -196,8 +198,13 @@ def ksp_solve(A, rhs: torch.Tensor, k, comm=None, P=None) -> torch.Tensor:
         prec = lambda r: r * dinv  # noqa: E731
     elif k.pc_type == "none":
         prec = lambda r: r  # noqa: E731
+    elif k.pc_type == "fieldsplit":
+        if k.prec is None:
+            raise NotImplementedError("pc_type fieldsplit needs the field sub-contexts of a mixed problem "
+                                      "(_TSContext.split); it is set up by TS for the Newton systems only")
+        prec = k.prec
     else:
-        raise NotImplementedError(f"pc_type {k.pc_type!r}: the stand-in KSP knows jacobi, none and lu")
+        raise NotImplementedError(f"pc_type {k.pc_type!r}: the stand-in KSP knows jacobi, none, lu and fieldsplit")
     if k.type == "cg" and rhs.is_cuda:
         red = None if comm is None else (lambda t: _allreduce_sum(t, comm))
         x, k.its = linalg.pcg_device(matvec, rhs, prec, k.rtol, k.atol, k.max_it, allreduce=red)
@@ -348,10 +355,65 @@ class TS:
         k.atol = float(o.get("ksp_atol", k.atol))
         k.max_it = int(o.get("ksp_max_it", k.max_it))
         k.restart = int(o.get("ksp_gmres_restart", k.restart))
+        k.options = o
 
     # -- linear solve ---------------------------------------------------------------
     def _linear_solve(self, rhs: torch.Tensor) -> torch.Tensor:
-        return ksp_solve(self._J, rhs, self.snes.ksp, self.comm, P=self._P)
+        k = self.snes.ksp
+        if k.pc_type == "fieldsplit":
+            k.prec = self._fieldsplit_preconditioner()
+        return ksp_solve(self._J, rhs, k, self.comm, P=self._P)
+
+    def _fieldsplit_preconditioner(self):
+        """PCFIELDSPLIT over the fields of a mixed space, one split per field: the diagonal blocks come from
+        the context's field sub-contexts (``_TSContext.split``, reference solving_utils.py:145-233, which
+        PETSc reaches through the DM's field decomposition).  ``pc_fieldsplit_type`` additive (block Jacobi) or
+        multiplicative (block Gauss-Seidel, PETSc's default); ``fieldsplit_<i>_pc_type`` jacobi | lu per block
+        (one application each, i.e. ``fieldsplit_<i>_ksp_type preonly``).  Schur factorisations, which need a
+        user Schur preconditioner as in examples/cahn-hilliard.py:73-112, are not part of the stand-in."""
+        from . import dmhooks
+
+        ctx = dmhooks.get_appctx(self.dm)
+        k = self.snes.ksp
+        kind = k.options.get("pc_fieldsplit_type", "multiplicative")
+        if kind not in ("additive", "multiplicative"):
+            raise NotImplementedError(f"pc_fieldsplit_type {kind!r}: additive and multiplicative only")
+        V = ctx._x.function_space()
+        nf = V.ncomp if getattr(ctx, "is_mixed", False) else 1
+        splits = ctx.split(tuple((i,) for i in range(nf)))
+        applies = []
+        for i, sc in enumerate(splits):
+            B = sc.extract_jacobian_block().petscmat
+            pct = k.options.get(f"fieldsplit_{i}_pc_type", "jacobi")
+            if pct == "jacobi":
+                d = B.diagonal()
+                if bool((d == 0).any()):
+                    raise ZeroDivisionError(f"fieldsplit_{i}_pc_type jacobi: zero diagonal entry in block {i}")
+                applies.append(lambda r, dinv=1.0 / d: r * dinv)
+            elif pct == "lu":
+                assert self.comm is None, "fieldsplit_<i>_pc_type lu is a single-rank test facility"
+                import numpy as np
+                import scipy.sparse.linalg as spla
+
+                n = B.nrows
+                lu = spla.splu(B.to_scipy()[:, :n].tocsc())
+                applies.append(lambda r, lu=lu: torch.from_numpy(np.ascontiguousarray(lu.solve(r.cpu().numpy()))).to(r.device))
+            else:
+                raise NotImplementedError(f"fieldsplit_{i}_pc_type {pct!r}: jacobi and lu only")
+        A = self._J
+        rows = [sc.rows for sc in splits]
+
+        def prec(r):
+            z = torch.zeros_like(r)
+            res = r
+            for i, ap in enumerate(applies):
+                z[rows[i]] = ap(res[rows[i]])
+                if kind == "multiplicative" and i + 1 < len(applies):
+                    zl = z if A.halo is None else A.halo.owned_to_local(z)
+                    res = r - A.mult(zl)
+            return z
+
+        return prec
 
     # -- the integrator ---------------------------------------------------------------
     def _stage_solve(self, X: Vec, X0: torch.Tensor, ts_time: float, shift: float):

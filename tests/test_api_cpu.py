@@ -291,3 +291,77 @@ def test_mat_diagonal_of_blocked_space_on_a_partition():
     nown, nn = V.num_owned_nodes, V.num_nodes
     want = np.array([dense[m * nown + i, m * nn + i] for m in range(2) for i in range(nown)])
     assert np.array_equal(d, want) and np.all(d[:nown] != 0)
+
+
+def test_split_field_subcontexts():
+    """reference solving_utils.py:145-233: sub-contexts on the fields of the mixed Cahn-Hilliard space assemble
+    the field's rows of F and the diagonal block of J with the other field as a coefficient; cached per
+    field tuple; the sub-Functions write through to the parent's."""
+    from firedrake_ts_b200.ts import DM, Vec
+    from firedrake_ts_b200.workloads import make_problem
+    from oracle import Oracle
+
+    form, bcs, u, udot = make_problem("cahn_hilliard", 2, 1, 5)
+    problem = fts.DAEProblem(form, u, udot, (0.0, 1e-5))
+    solver = fts.DAESolver(problem, assembler=OracleAssembler(form, bcs), solver_parameters={"ts_dt": 5e-6})
+    ctx = solver._ctx
+    splits = ctx.split(((0,), (1,)))
+    assert ctx.split([[0], [1]]) is splits and len(splits) == 2
+    with pytest.raises(ValueError):
+        ctx.split(((2,),))
+    orc = Oracle.from_form(form, bcs)
+    V = form.space
+    nn = V.num_nodes
+    x0, xd0 = u.data.clone(), udot.data.clone()
+    Ffull = orc.ifunction(0.0, x0, xd0)
+    Jfull = orc.ijacobian(0.0, x0, xd0, 3.0)
+    rp, ci = orc.pattern()
+    import scipy.sparse as sp
+
+    A = sp.csr_matrix((Jfull, ci, rp), shape=(2 * nn, 2 * nn)).toarray()
+    for m, sc in enumerate(splits):
+        assert sc.space.ncomp == 1 and sc.space.num_nodes == nn
+        ts = solver.ts.__class__()
+        dm = DM()
+        dm._appctx.append(sc)
+        ts.setDM(dm)
+        X, Xd = Vec(x0[m * nn:(m + 1) * nn].clone()), Vec(xd0[m * nn:(m + 1) * nn].clone())
+        Fv = Vec(torch.zeros(nn, dtype=torch.float64))
+        sc.form_function(ts, 0.0, X, Xd, Fv)
+        assert np.allclose(Fv.array.numpy(), Ffull[m * nn:(m + 1) * nn], rtol=1e-13, atol=1e-15)
+        sc.form_jacobian(ts, 0.0, X, Xd, 3.0, sc._jac.petscmat, sc._pjac.petscmat)
+        B = sc._jac.petscmat.to_scipy().toarray()
+        assert np.allclose(B, A[m * nn:(m + 1) * nn, m * nn:(m + 1) * nn], rtol=1e-13, atol=1e-15)
+        # a changed sub-state is seen by the parent (shared data) and changes the other field's residual
+        X.array += 0.01
+        sc.form_function(ts, 0.0, X, Xd, Fv)
+        assert torch.allclose(u.data[m * nn:(m + 1) * nn], X.array)
+        u.data.copy_(x0)
+        udot.data.copy_(xd0)
+    # the pair of fields is the whole problem
+    both = ctx.split(((0, 1),))[0]
+    assert both._jac.petscmat.values.numel() == len(Jfull)
+
+
+@pytest.mark.parametrize("kind", ["additive", "multiplicative"])
+def test_fieldsplit_preconditioner_solves_cahn_hilliard(kind):
+    """GMRES preconditioned by PCFIELDSPLIT over (c, mu) with LU on the diagonal blocks reproduces the direct
+    solve of the literal example's first steps."""
+    from firedrake_ts_b200.workloads import make_problem
+
+    def run(params):
+        form, bcs, u, udot = make_problem("cahn_hilliard", 2, 1, 6, quadrilateral=True)
+        u.data[form.space.num_nodes:] = 0.0
+        problem = fts.DAEProblem(form, u, udot, (0.0, 1e-5))
+        s = fts.DAESolver(problem, assembler=OracleAssembler(form, bcs), solver_parameters=dict(params, ts_dt=5e-6))
+        s.solve()
+        return u.data.clone(), s
+
+    base = {"snes_rtol": 1e-10, "snes_atol": 1e-11}
+    ud, _ = run(dict(base, pc_type="lu"))
+    uf, s = run(dict(base, ksp_type="gmres", ksp_rtol=1e-12, pc_type="fieldsplit", pc_fieldsplit_type=kind,
+                     fieldsplit_0_pc_type="lu", fieldsplit_1_pc_type="lu"))
+    assert s.ts.getStepNumber() == 2
+    assert (ud - uf).abs().max() < 1e-8 * max(1.0, float(ud.abs().max()))
+    with pytest.raises(NotImplementedError):
+        run(dict(base, pc_type="fieldsplit", pc_fieldsplit_type="schur"))

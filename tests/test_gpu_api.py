@@ -268,3 +268,49 @@ def test_csr_spmv_kernels(family, dim, degree, n):
     for kernel in ("stream", "warp"):
         y = linalg.csr_spmv(rp, ci, J, x.cuda(), kernel=kernel).cpu().numpy()
         assert np.abs(y - ref).max() < 1e-13 * scale, kernel
+
+
+def test_split_subcontexts_on_gpu():
+    """_TSContext.split on the B200 engine: rows of F / diagonal blocks of J of each field of the mixed
+    Cahn-Hilliard space against the oracle (reference solving_utils.py:145-233)."""
+    import scipy.sparse as sp
+
+    from firedrake_ts_b200.ts import DM, TS, Vec
+    from oracle import Oracle
+
+    form, bcs, u, udot = make_problem("cahn_hilliard", 2, 1, 7, quadrilateral=True)
+    orc = Oracle.from_form(form, bcs)
+    x0, xd0 = u.data.clone(), udot.data.clone()
+    Ffull = orc.ifunction(0.0, x0, xd0)
+    rp, ci = orc.pattern()
+    nn = form.space.num_nodes
+    A = sp.csr_matrix((orc.ijacobian(0.0, x0, xd0, 3.0), ci, rp), shape=(2 * nn, 2 * nn)).toarray()
+    solver = fts.DAESolver(fts.DAEProblem(form, u, udot, (0.0, 1e-5)), solver_parameters={"ts_dt": 5e-6})
+    ctx = solver._ctx
+    for m, sc in enumerate(ctx.split(((0,), (1,)))):
+        ts, dm = TS(), DM()
+        dm._appctx.append(sc)
+        ts.setDM(dm)
+        X, Xd = Vec(x0[m * nn:(m + 1) * nn].cuda()), Vec(xd0[m * nn:(m + 1) * nn].cuda())
+        Fv = Vec(torch.zeros(nn, dtype=torch.float64, device="cuda"))
+        sc.form_function(ts, 0.0, X, Xd, Fv)
+        assert np.abs(Fv.array.cpu().numpy() - Ffull[m * nn:(m + 1) * nn]).max() < 1e-12 * np.abs(Ffull).max()
+        sc.form_jacobian(ts, 0.0, X, Xd, 3.0, sc._jac.petscmat, sc._pjac.petscmat)
+        B = sc._jac.petscmat.to_scipy().toarray()
+        assert np.abs(B - A[m * nn:(m + 1) * nn, m * nn:(m + 1) * nn]).max() < 1e-12 * np.abs(A).max()
+        assert sc._jac.petscmat.values.is_cuda
+
+
+def test_fieldsplit_solve_on_gpu():
+    def build():
+        form, bcs, u, udot = make_problem("cahn_hilliard", 2, 1, 8, quadrilateral=True)
+        u.data[form.space.num_nodes:] = 0.0
+        return form, bcs, u, udot
+
+    dt = 5.0e-6
+    params = {"snes_rtol": 1e-10, "snes_atol": 1e-11, "ksp_type": "gmres", "ksp_rtol": 1e-12,
+              "pc_type": "fieldsplit", "pc_fieldsplit_type": "multiplicative", "fieldsplit_0_pc_type": "lu",
+              "fieldsplit_1_pc_type": "lu"}
+    (uo, so, _), (ug, sg, s) = run_both(build, (0.0, 2 * dt), params, dt=dt)
+    assert so == sg == 2
+    assert (uo - ug).abs().max() < 1e-8 * max(1.0, float(uo.abs().max()))
