@@ -219,7 +219,7 @@ def time_other_configs(dev, hbm_peak, reps=5):
     peak_dmma = measure_fp64_peak(dev.index or 0, True) / 1e3
     out = {"fp64_peak": {"dfma_tflops": peak_dfma, "dmma_tflops": peak_dmma, "how": "fdts_measure_fp64_peak: "
                          "dependent-free FMA / mma.sync.m8n8k4.f64 chains, all SMs, CUDA events"}}
-    for name in ("C1", "C2", "C3", "C5"):
+    for name in ("C1", "C2", "C3", "C3q", "C5"):
         try:
             out[name] = _time_config(name, dev, hbm_peak, peak_dfma, peak_dmma, reps)
         except Exception as exc:  # a failing side configuration must not take the headline line down
@@ -236,8 +236,9 @@ def _time_config(name, dev, hbm_peak, peak_dfma, peak_dmma, reps):
 
     if True:
         family, dim, degree, n, ftile, foffset, mtile = CONFIGS[name]
+        quad = name.endswith("q")
         form, bcs, u, udot = make_problem(family, dim, degree, n, tile=mtile, device=dev, ftile=ftile or None,
-                                          foffset=foffset)
+                                          foffset=foffset, quadrilateral=quad)
         V = form.space
         eng = Engine(form, bcs, device=dev, scatter=2 if (family == "heat" and ftile) else None)
         x, xd = u.data, udot.data
@@ -257,10 +258,10 @@ def _time_config(name, dev, hbm_peak, peak_dfma, peak_dmma, reps):
         torch.cuda.synchronize()
         t_if, t_ij = ev[0].elapsed_time(ev[1]) / reps, ev[1].elapsed_time(ev[2]) / reps
         nc, nv = V.mesh.num_cells, V.mesh.num_coord_nodes
-        maps = 4 * nc * V.nd + 4 * nc * (dim + 1) + 8 * dim * nv
+        maps = 4 * nc * V.nd + 4 * nc * V.mesh.nverts + 8 * dim * nv
         b_if = maps + 3 * 8 * V.num_dofs
         b_ij = maps + (0 if family == "heat" else 8 * V.num_dofs) + 8 * eng.nnz
-        rec = {"workload": f"{family} P{degree} dim {dim} n={n}: {nc} cells, {V.num_dofs} DOFs, {eng.nnz} non-zeros",
+        rec = {"workload": f"{family} {'Q' if quad else 'P'}{degree} dim {dim} n={n}: {nc} cells, {V.num_dofs} DOFs, {eng.nnz} non-zeros",
                "ms_ifunction": t_if, "ms_ijacobian": t_ij, "value": V.num_dofs / ((t_if + t_ij) * 1e-3), "unit": UNIT,
                "algorithmic_bytes": {"ifunction": b_if, "ijacobian": b_ij}}
         if name == "C5":
@@ -438,14 +439,17 @@ def run_b200(a):
         eng.ifunction_host(0.0, xh, xdh, Fh)
         eng.ijacobian_host(0.0, xh, xdh, shift, Jh)
         torch.cuda.synchronize()
+        moved0 = (eng.get_option("h2d_bytes"), eng.get_option("d2h_bytes"))  # counted by the library per copy
         t0 = time.perf_counter()
         for _ in range(ksteps):
             eng.ifunction_host(0.0, xh, xdh, Fh)
             eng.ijacobian_host(0.0, xh, xdh, shift, Jh)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / ksteps
-        e2e = {"value": ndofs / dt, "unit": UNIT, "h2d_bytes_per_step": 4 * 8 * V.num_dofs,
-               "d2h_bytes_per_step": 8 * eng.num_rows + 8 * eng.nnz, "steps": ksteps, "ms_per_step": dt * 1e3,
+        e2e = {"value": ndofs / dt, "unit": UNIT,
+               "h2d_bytes_per_step": (eng.get_option("h2d_bytes") - moved0[0]) // ksteps,
+               "d2h_bytes_per_step": (eng.get_option("d2h_bytes") - moved0[1]) // ksteps,
+               "steps": ksteps, "ms_per_step": dt * 1e3,
                "checksum": float(Fh.sum()) + float(Jh[:1000].sum())}
     elif world > 1 and not a.no_e2e:
         # every rank owns host copies of its Vec/Mat (the reference's VECMPI/MATMPIAIJ in host memory): per step the

@@ -38,16 +38,23 @@ def _compile(src):
 def build_dev(verbose: bool = False) -> str:
     """development build with the timing switches compiled in (-DFDTS_DEV_SWITCHES): libfdts_b200_dev.so,
     used only by tools/ through FDTS_B200_LIB; its results are wrong by design when a switch is on."""
-    bdir = os.path.join(HERE, "build", "dev")
+    # FDTS_DEV_DEFS="-DX=1 -DY=2" FDTS_DEV_TAG=x: an experiment variant (own object directory and library name)
+    extra = os.environ.get("FDTS_DEV_DEFS", "").split()
+    tag = os.environ.get("FDTS_DEV_TAG", "")
+    bdir = os.path.join(HERE, "build", "dev" + tag)
     os.makedirs(bdir, exist_ok=True)
-    lib = os.path.join(HERE, "libfdts_b200_dev.so")
+    lib = os.path.join(HERE, f"libfdts_b200_dev{tag}.so")
+
+    only = os.environ.get("FDTS_DEV_SRCS", "").split()  # variant: recompile these, take the rest from build/dev
 
     def comp(src):
+        if tag and only and src not in only:
+            return os.path.join(HERE, "build", "dev", src.replace(".cu", ".o"))
         obj = os.path.join(bdir, src.replace(".cu", ".o"))
         deps = [os.path.join(HERE, src)] + [os.path.join(HERE, h) for h in HEADERS]
         if _stale(obj, deps):
             with open(obj + ".log", "w") as f:
-                subprocess.check_call([NVCC, *FLAGS, "-DFDTS_DEV_SWITCHES", "-c", os.path.join(HERE, src), "-o", obj],
+                subprocess.check_call([NVCC, *FLAGS, "-DFDTS_DEV_SWITCHES", *extra, "-c", os.path.join(HERE, src), "-o", obj],
                                       stdout=f, stderr=f)
         return obj
 

@@ -55,8 +55,16 @@ __global__ void __launch_bounds__(128) heat_jacobian_atomic(const KArgs a) {
   });
 }
 
+#ifndef RES_NT
+#define RES_NT 128
+#endif
+#ifdef RES_MINB  // experiment builds only (firedrake_ts_b200/csrc/build.py --dev with FDTS_DEV_DEFS)
+#define RES_BOUNDS __launch_bounds__(RES_NT, RES_MINB)
+#else
+#define RES_BOUNDS __launch_bounds__(RES_NT)
+#endif
 template <int DIM, int DEG, int VAR>
-__global__ void __launch_bounds__(128) heat_residual_atomic(const KArgs a) {
+__global__ void RES_BOUNDS heat_residual_atomic(const KArgs a) {
   using T = RefT<DIM, DEG, VAR>;
   constexpr int ND = T::ND, NP = T::NP;
   const int64_t c = a.c0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -136,12 +144,13 @@ template <int DIM, int DEG, int VAR>
 int launch_atomic(int which, const KArgs &a, cudaStream_t s) {
   const int64_t n = a.c1 - a.c0;
   if (n <= 0) return 0;
-  const int threads = 128;
-  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
-  if (which == 0)
-    heat_residual_atomic<DIM, DEG, VAR><<<blocks, threads, 0, s>>>(a);
-  else
-    heat_jacobian_atomic<DIM, DEG, VAR><<<blocks, threads, 0, s>>>(a);
+  if (which == 0) {
+    const int threads = RES_NT;
+    heat_residual_atomic<DIM, DEG, VAR><<<(unsigned)((n + threads - 1) / threads), threads, 0, s>>>(a);
+  } else {
+    const int threads = 128;
+    heat_jacobian_atomic<DIM, DEG, VAR><<<(unsigned)((n + threads - 1) / threads), threads, 0, s>>>(a);
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 

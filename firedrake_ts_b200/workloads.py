@@ -13,6 +13,8 @@ CONFIGS = {
     "C1": ("heat", 2, 1, 4096, 14, 0, 14),  # 14 x 14 row blocks: 15^2 = 225 vertices per block (limit 254)
     "C2": ("burgers", 2, 2, 2048, 0, 0, 8),
     "C3": ("cahn_hilliard", 2, 1, 4096, 0, 0, 16),
+    # the literal mesh of examples/cahn-hilliard.py:14 (quadrilateral Q1 x Q1) at the size of C3
+    "C3q": ("cahn_hilliard", 2, 1, 4096, 0, 0, 16),
     "C4": ("heat", 3, 2, 184, 6, 0, 3),
     "C5": ("bbm", 3, 3, 96, 0, 0, 2),
 }

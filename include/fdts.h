@@ -122,7 +122,8 @@ int fdts_set_cell_tiles(fdts_handle h, const int64_t *starts_host, int64_t ntile
  * schedule options (set before fdts_set_row_blocks; they never change a value beyond rounding):
  *   "plan_version" 2 (default: sector-grouped SELL + pattern dictionary) | 1 (windowed SELL, residual lists)
  *   "dedup" 1|0 share identical block tables; "optimize" 1|0 bank-conflict-aware ordering of the shared tables
- *   "sector" 4|2|1 CSR slots per store group; "threads" 512|1024 per persistent CTA
+ *   "sector" 4|2|1 CSR slots per store group (not set: 4, or 2 when fewer than 3/4 of the blocks repeat a pattern;
+ *   read back as "plan_sector"); "threads" 512|1024 per persistent CTA
  *   "overlap" 0|1 warp-specialised Jacobian kernel; "residual_tiles" 1|0 use the tile plan when one exists
  *   "gather_residual" 0|1 (plan 1); "persist" 1|0 (plan 1)
  * read-only: "plan_cells_max", "plan_contributions", "plan_blocks", "plan_version", "plan_patterns",
@@ -142,7 +143,9 @@ int fdts_ifunction_range(fdts_handle h, double t, const double *x, const double 
 int fdts_ijacobian_range(fdts_handle h, double t, const double *x, const double *xdot, double shift, double *vals,
                          int64_t cell_begin, int64_t cell_end, int32_t flags, void *stream);
 
-/* host-buffer variants: pinned or pageable host pointers; H2D / D2H copies are part of the call */
+/* host-buffer variants: pinned or pageable host pointers; H2D / D2H copies are part of the call (the Jacobian of the
+ * linear families does not read the state, so fdts_ijacobian_host uploads nothing for them); the bytes moved so far
+ * are read back with fdts_get_option "h2d_bytes" / "d2h_bytes" */
 int fdts_ifunction_host(fdts_handle h, double t, const double *x_host, const double *xdot_host, double *f_host);
 int fdts_ijacobian_host(fdts_handle h, double t, const double *x_host, const double *xdot_host, double shift,
                         double *vals_host);

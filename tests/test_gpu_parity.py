@@ -99,8 +99,8 @@ def test_pattern_dictionary(n, ftile):
     mt = tuple(t // 2 for t in ftile) if isinstance(ftile, tuple) else ftile // 2
     form, bcs, u, udot = make_problem("heat", 3, 2, n, tile=mt, ftile=ftile)
     x, xd = u.data.cuda(), udot.data.cuda()
-    e1 = Engine(form, bcs, device="cuda:0", scatter=2, plan_version=2, dedup=1, options={"optimize": 0})
-    e0 = Engine(form, bcs, device="cuda:0", scatter=2, plan_version=2, dedup=0)
+    e1 = Engine(form, bcs, device="cuda:0", scatter=2, plan_version=2, dedup=1, options={"optimize": 0, "sector": 4})
+    e0 = Engine(form, bcs, device="cuda:0", scatter=2, plan_version=2, dedup=0, options={"sector": 4})
     nb = e1.get_option("plan_blocks")
     assert e0.get_option("plan_patterns") == nb
     assert e1.get_option("plan_patterns") < nb
@@ -210,7 +210,12 @@ def test_pattern_dictionary_compaction():
     form, bcs, u, udot = make_problem("heat", 3, 2, 24, tile=3, ftile=6, device="cuda:0")
     x, xd = u.data, udot.data
     e1 = Engine(form, bcs, device="cuda:0", scatter=2, plan_version=2, dedup=1, options={"optimize": 0})
-    e0 = Engine(form, bcs, device="cuda:0", scatter=2, plan_version=2, dedup=0)
+    e0 = Engine(form, bcs, device="cuda:0", scatter=2, plan_version=2, dedup=0, options={"sector": 4})
+    # store-group width left to the engine: 32-byte groups while the dictionary pays, 16-byte groups for a
+    # mesh without repeated blocks (its index tables stream from HBM; less SELL padding)
+    ea = Engine(form, bcs, device="cuda:0", scatter=2, plan_version=2, dedup=0)
+    assert e1.get_option("plan_sector") == 4 and e0.get_option("plan_sector") == 4 and ea.get_option("plan_sector") == 2
+    assert rel_err(ea.ijacobian(0.0, x, xd, 10.0).cpu().numpy(), e0.ijacobian(0.0, x, xd, 10.0).cpu().numpy()) < TOL
     assert e1.get_option("plan_compacted") == 1 and e0.get_option("plan_compacted") == 0
     assert e1.get_option("plan_patterns") * 4 <= e1.get_option("plan_blocks")
     assert torch.equal(e1.ijacobian(0.0, x, xd, 10.0), e0.ijacobian(0.0, x, xd, 10.0))
