@@ -251,7 +251,8 @@ def test_preconditioner_form_Jp_fills_P():
 
 def test_unknown_solver_options_and_nullspaces_are_rejected():
     V, u, u_t, F, bc = heat_1d(8, 1)
-    for bad in ({"pc_type": "hypre"}, {"pc_type": "fieldsplit"}, {"ksp_type": "bcgs", "pc_type": "jacobi"}):
+    for bad in ({"pc_type": "hypre"}, {"pc_type": "fieldsplit", "pc_fieldsplit_type": "schur"},
+                {"pc_type": "fieldsplit", "fieldsplit_0_pc_type": "hypre"}, {"ksp_type": "bcgs", "pc_type": "jacobi"}):
         u.data.zero_()
         s = fts.DAESolver(fts.DAEProblem(F, u, u_t, (0.0, 0.1), bcs=bc), assembler=OracleAssembler(F, [bc]),
                           solver_parameters=bad)
