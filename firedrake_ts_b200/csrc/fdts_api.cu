@@ -371,7 +371,7 @@ extern "C" int fdts_set_option(fdts_handle e, const char *key, int64_t value) {
     return 0;
   }
   if (!strcmp(key, "residual_tiles")) {
-    e->opt_residual_tiles = value < 0 ? 0 : (value > 2 ? 2 : value);  // 0 off, 1 staged inputs, 2 direct gathers
+    e->opt_residual_tiles = value < 0 ? 0 : (value > 3 ? 3 : value);  // 0 off, 1 staged inputs, 2 direct gathers, 3 direct gathers + reduction tables in shared memory
     return 0;
   }
   if (!strcmp(key, "dmma")) {

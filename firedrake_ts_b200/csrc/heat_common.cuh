@@ -50,6 +50,7 @@ struct RTArgs {
   int32_t direct;
   double p0;
   int32_t cmaxp, umaxp, ndp, zaddr, off_su, off_sud, off_vtab;
+  int32_t off_sidx, off_sgd, off_scls, off_stn;  // variant 3: the tile's reduction tables in shared memory
 };
 
 

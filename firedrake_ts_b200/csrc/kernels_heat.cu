@@ -804,7 +804,7 @@ static int launch_heat_impl(fdts_engine *e, int which, const double *x, const do
       r.tnode = p.tnode; r.bvcoords = p.bvcoords; r.x = x; r.xdot = xdot; r.out = out; r.p0 = e->cfg.params[0];
       r.cmaxp = p.cmaxp; r.umaxp = p.umaxp; r.ndp = p.ndp; r.zaddr = p.zaddr;
       r.tstart = p.tstart_dev; r.cell_node_t = e->cell_node; r.cell_coord_t = e->cell_coord; r.coords = e->coords;
-      r.nc = e->cfg.num_cells; r.direct = e->opt_residual_tiles == 2 ? 1 : 0;
+      r.nc = e->cfg.num_cells; r.direct = e->opt_residual_tiles >= 2 ? (int)e->opt_residual_tiles - 1 : 0;
       int rc = 3;
       rc = fdts_heat_residual_tiles(dim, deg, var, r, p, lo - ts, hi - ts, s);
       if (rc == 2) fdts_set_error(std::string("residual tile kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));

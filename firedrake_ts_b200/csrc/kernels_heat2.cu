@@ -455,6 +455,100 @@ __global__ void __launch_bounds__(NT, MINB) heat_residual_tiles_direct(const RTA
   }
 }
 
+// variant 3: like the direct variant, but the tile's reduction tables (SELL addresses, slice classes, node
+// ids) are fetched into shared memory with cp.async while the element vectors are computed, so the
+// pre-reduction after the barrier reads shared memory only (in the direct variant every step of the sweep
+// waits for a dependent L2 access: ~10 k cycles per tile, which made it slower than the per-cell kernel)
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+
+template <int DIM, int DEG, int VAR, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) heat_residual_tiles_direct3(const RTArgs a) {
+  using T = RefT<DIM, DEG, VAR>;
+  constexpr int ND = T::ND, NP = T::NP, NDP = ND | 1, NWARPS = NT / 32;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double *stage = reinterpret_cast<double *>(smraw);
+  uint32_t *sidx = reinterpret_cast<uint32_t *>(smraw + a.off_sidx);
+  uint16_t *sgd = reinterpret_cast<uint16_t *>(smraw + a.off_sgd);
+  uint2 *scls = reinterpret_cast<uint2 *>(smraw + a.off_scls);
+  int32_t *stn = reinterpret_cast<int32_t *>(smraw + a.off_stn);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t t = a.t0 + blockIdx.x;
+  const BlockDesc2 d = a.tdesc[t];
+  const int64_t c0 = a.tstart[t];
+  const int64_t pat = d.pattern;
+  {  // tables: issued now, complete behind the element-vector phase
+    const unsigned char *g = reinterpret_cast<const unsigned char *>(a.cidx + d.idx_off);
+    for (int q = threadIdx.x; q < d.nidx / 8; q += NT) cp_async16(reinterpret_cast<unsigned char *>(sidx) + q * 16, g + q * 16);
+    g = reinterpret_cast<const unsigned char *>(a.gdst + d.meta_off * 32);
+    for (int q = threadIdx.x; q < d.nsl * 4; q += NT) cp_async16(reinterpret_cast<unsigned char *>(sgd) + q * 16, g + q * 16);
+    const uint32_t *gc = reinterpret_cast<const uint32_t *>(a.cmeta + d.cls_off);
+    for (int q = threadIdx.x; q < d.ncls * 2; q += NT) cp_async4(reinterpret_cast<uint32_t *>(scls) + q, gc + q);
+    const int32_t *gt = a.tnode + pat * a.umaxp;
+    for (int q = threadIdx.x; q < d.nslots; q += NT) cp_async4(stn + q, gt + q);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  if (threadIdx.x < 16) stage[a.zaddr + threadIdx.x] = 0.0;
+  for (int k = threadIdx.x; k < d.ncell; k += NT) {
+    const int64_t c = c0 + k;
+    int32_t cc[DIM + 1], nodes[ND];
+#pragma unroll
+    for (int v = 0; v <= DIM; ++v) cc[v] = a.cell_coord_t[v * a.nc + c];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) nodes[i] = a.cell_node_t[i * a.nc + c];
+    Geom<DIM> g;
+    compute_geometry<DIM>(a.coords, cc, g);
+    double gm[NP];
+    metric<DIM>(g, gm);
+    double u[ND], ud[ND], f[ND];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) {
+      u[i] = __ldg(a.x + nodes[i]);
+      ud[i] = __ldg(a.xdot + nodes[i]);
+    }
+    heat_element_residual<DIM, DEG, VAR, ND, NP>(gm, g.adet, a.p0, u, ud, f);
+    double *st = stage + k * NDP;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) st[i] = f[i];
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  for (int c = 0; c < d.ncls; ++c) {
+    const uint2 ce = scls[c];
+    const int first = (int)(ce.x & 0xffffu), count = (int)(ce.x >> 16), w = (int)((ce.y >> 16) & 0xffu);
+    const bool split = (ce.y >> 24) != 0;
+    const uint32_t pairs = (uint32_t)((w + 1) >> 1);
+    for (int i = first_slice_of<NWARPS>(warp, (uint32_t)first); i < count; i += NWARPS) {
+      const uint32_t *ip = sidx + ((size_t)(ce.y & 0xffffu) + (size_t)i * pairs) * 32 + lane;
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll 4
+      for (uint32_t q = 0; q < pairs; ++q) {
+        const uint32_t pr = ip[q * 32];
+        a0 += stage[pr & 0xffffu];
+        if (2 * q + 1 < (uint32_t)w) a1 += stage[pr >> 16];
+      }
+      double acc = a0 + a1;
+      int gsel = lane;
+      bool wr = true;
+      if (split) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        gsel = lane >> 2;
+        wr = (lane & 3) == 0;
+      }
+      const uint32_t ln = sgd[(size_t)(first + i) * 32 + gsel];
+      if (wr && ln != 0xffffu) {
+        const int32_t rel = stn[ln];
+        if (rel >= 0) red_add_f64(a.out + d.s0 + rel, acc);
+      }
+    }
+  }
+}
+
 template <int DIM, int DEG, int VAR>
 int launch_residual_tiles(RTArgs a, const ResidualPlan &p, int64_t t0, int64_t t1, cudaStream_t s) {
   using T = RefT<DIM, DEG, VAR>;
@@ -471,6 +565,22 @@ int launch_residual_tiles(RTArgs a, const ResidualPlan &p, int64_t t0, int64_t t
   const size_t smem = off;
   if (smem > 227 * 1024) return 4;
   a.t0 = t0;
+  if (a.direct == 2) {
+    size_t o = up16(sizeof(double) * ((size_t)p.zaddr + 16));
+    a.off_sidx = (int)o;
+    o += up16(2 * (size_t)p.max_nidx + 64);
+    a.off_sgd = (int)o;
+    o += up16(64 * (size_t)p.max_nsl + 64);
+    a.off_scls = (int)o;
+    o += up16(8 * (size_t)PLAN2_MAX_CLASSES);
+    a.off_stn = (int)o;
+    o += up16(4 * (size_t)p.umaxp + 16);
+    if (o > 227 * 1024) return 4;
+    auto k3 = heat_residual_tiles_direct3<DIM, DEG, VAR, NT, RT_MINB>;
+    if (o > 48 * 1024 && cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o) != cudaSuccess) return 2;
+    if (t1 > t0) k3<<<(unsigned)(t1 - t0), NT, o, s>>>(a);
+    return cudaGetLastError() == cudaSuccess ? 0 : 2;
+  }
   if (a.direct) {
     const size_t sm2 = up16(sizeof(double) * ((size_t)p.zaddr + 16));
     auto k2 = heat_residual_tiles_direct<DIM, DEG, VAR, NT, RT_MINB>;

@@ -155,6 +155,9 @@ def test_residual_tile_kernel(dim, degree, n, tile):
     assert rel_err(F1.cpu().numpy(), Fo) < TOL
     eng.set_option("residual_tiles", 2)  # variant: cells gather their inputs directly, tile pre-reduction only
     assert rel_err(eng.ifunction(0.0, x, xd).cpu().numpy(), Fo) < TOL
+    eng.set_option("residual_tiles", 3)  # the same with the tile's reduction tables prefetched into shared memory
+    F3 = eng.ifunction(0.0, x, xd).cpu().numpy()
+    assert rel_err(F3, Fo) < TOL
     eng.set_option("residual_tiles", 0)
     F0 = eng.ifunction(0.0, x, xd)
     eng.set_option("residual_tiles", 1)
