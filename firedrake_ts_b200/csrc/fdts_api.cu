@@ -382,6 +382,10 @@ extern "C" int fdts_set_option(fdts_handle e, const char *key, int64_t value) {
     e->opt_overlap = value ? 1 : 0;
     return 0;
   }
+  if (!strcmp(key, "cache_metric")) {
+    e->opt_cache_metric = value ? 1 : 0;
+    return 0;
+  }
   if (!strcmp(key, "threads")) {
     if (value != 512 && value != 1024) {
       fdts_set_error("threads must be 512 or 1024");
@@ -475,6 +479,14 @@ extern "C" int fdts_get_option(fdts_handle e, const char *key, int64_t *value) {
   }
   if (!strcmp(key, "d2h_bytes")) {
     *value = e->d2h_bytes;
+    return 0;
+  }
+  if (!strcmp(key, "cache_metric")) {
+    *value = e->opt_cache_metric;
+    return 0;
+  }
+  if (!strcmp(key, "plan_metric_cached")) {
+    *value = e->plan2.bmetric != nullptr;
     return 0;
   }
   if (!strcmp(key, "plan_sector")) {

@@ -78,6 +78,8 @@ struct GatherPlan2 {
   uint32_t *bcc = nullptr;      // per cell: (dim+1) block-local vertex ids, one byte each
   double *bvcoords = nullptr;   // per block: vmax x dim vertex coordinates
   BlockDesc2 *bdesc = nullptr;
+  double *bmetric = nullptr;    // optional (option "cache_metric"): per block [NP + 1][cmaxp] cell metrics |detJ| G_ab and |detJ|, built on first use
+  int32_t cmaxp = 0;            // cmax padded to 4 (row length of bmetric)
   int64_t total_idx = 0, unique_patterns = 0, shared_idx = 0;
   int32_t optimized = 0;        // unique patterns went through the bank-conflict-aware column ordering
   int32_t compacted = 0;        // only the tables of the unique patterns are kept (the duplicates were freed)
@@ -151,6 +153,7 @@ struct fdts_engine {
   int64_t opt_dmma = 2;          // BBM P2/P3 Jacobian on the fp64 tensor cores: 2 = reference-tensor contraction (default), 1 = quadrature formulation, 0 = generic kernel
   double *bbm_T = nullptr;       // reference tensor of the tensor-contraction BBM Jacobian (built on first use)
   int64_t opt_overlap = 0;       // plan 2: warp-specialised kernel (element matrices of block b+1 overlap the gather of block b; needs two staging buffers in smem; slower than the two-phase kernel on every block shape measured so far)
+  int64_t opt_cache_metric = 1;  // plan 2: phase A reads precomputed cell metrics (one TMA copy per block) instead of forming the geometry from the vertex table (30 % of its fp64 work, 13 conflict-prone loads per cell); costs (NP+1)*8 bytes per block cell of device memory and HBM reads
   int64_t opt_threads = 512;     // plan 2: threads per persistent CTA (512: 128 registers per thread, or 1024)
   int64_t opt_debug = 0;         // development only (timing experiments with phases switched off)
   int variant = -1;              // which baked RefT table matches cfg.R (-1: none, closed-form path off)

@@ -1127,7 +1127,7 @@ static void optimize_pattern(const BlockDesc2 &d, const uint2 *cls, uint16_t *id
 
 void fdts_free_plan2(fdts_engine *e) {
   GatherPlan2 &p = e->plan2;
-  void *ptrs[] = {p.cidx, p.cmeta, p.gdst, p.bcc, p.bvcoords, p.bdesc};
+  void *ptrs[] = {p.cidx, p.cmeta, p.gdst, p.bcc, p.bvcoords, p.bdesc, p.bmetric};
   for (void *q : ptrs)
     if (q) cudaFree(q);
   p = GatherPlan2();
@@ -1312,6 +1312,7 @@ int fdts_build_plan2(fdts_engine *e, const int64_t *starts, int64_t nb) {
       break;
     }
     const int cmaxp = (cmax + 3) & ~3;
+    p.cmaxp = cmaxp;
     P2_ALLOC(p.bvcoords, sizeof(double) * (size_t)nb * vmax * dim + 64, "block vertex tables");
     P2_ALLOC(p.bcc, sizeof(uint32_t) * ((size_t)nb * cmaxp + 16), "block cell vertices");
     P2_ALLOC(p.bdesc, sizeof(BlockDesc2) * (size_t)(nb + 4), "block descriptors");

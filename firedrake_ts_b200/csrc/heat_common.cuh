@@ -14,9 +14,11 @@ struct G2Args {
   const uint2 *cmeta;
   const uint32_t *bcc;
   const double *bvcoords;
+  const double *bmetric;  // cached cell metrics (cache_metric): block b at b * (NP + 1) * cmaxp
   double *out;
   int64_t nblocks;
   double shift;
+  int32_t cmaxp, off_met;
   int32_t off_idx, off_meta, off_gdst, off_vtab, off_lcc, off_bar, off_desc, zaddr, sector, inA_bytes, stage_bytes;
 #ifdef FDTS_DEV_SWITCHES  // timing experiments only (phases switched off, results wrong); never compiled into the shipped library
   int32_t dbg;

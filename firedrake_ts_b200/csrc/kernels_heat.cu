@@ -450,7 +450,42 @@ int launch_gather(int which, GArgs a, const GatherPlan &p, cudaStream_t s) {
 // (addresses, slice table, sector ids) while phase A computes, phase-A tables (vertex coordinates,
 // per-cell local vertex ids) of the next block while phase B sweeps.  With the pattern dictionary the
 // index tables of a structured mesh are a few hundred KB in total and stay L2 resident.
-template <int DIM, int DEG, int VAR, int NT, int G>
+// CM (option cache_metric): phase A reads the cell metrics |detJ| G_ab, |detJ| of the block, precomputed once per
+// plan (block_metrics) and copied in by ONE bulk copy per block into a single buffer (issued right after the
+// phase-A barrier of the previous block, so it lands behind phase B), instead of forming the geometry from
+// the vertex table: 30 % less fp64 work in phase A and 7 conflict-free loads instead of 13 scattered ones.
+template <int DIM>
+__global__ void block_metrics(const BlockDesc2 *__restrict__ bdesc, const uint32_t *__restrict__ bcc,
+                              const double *__restrict__ bvcoords, int cmaxp, double *__restrict__ out) {
+  constexpr int NP = DIM * (DIM + 1) / 2;
+  const int64_t b = blockIdx.x;
+  const BlockDesc2 d = bdesc[b];
+  double *o = out + b * (int64_t)(NP + 1) * cmaxp;
+  for (int k = threadIdx.x; k < cmaxp; k += blockDim.x) {
+    double gm[NP], adet = 0.0;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) gm[p] = 0.0;
+    if (k < d.ncell) {
+      const uint32_t packed = bcc[d.cc_off + k];
+      double X[DIM + 1][DIM];
+#pragma unroll
+      for (int v = 0; v <= DIM; ++v) {
+        const int lv = (packed >> (8 * v)) & 255;
+#pragma unroll
+        for (int q = 0; q < DIM; ++q) X[v][q] = bvcoords[d.vc_off + lv * DIM + q];
+      }
+      Geom<DIM> g;
+      geometry_from_vertices<DIM>(X, g);
+      metric<DIM>(g, gm);
+      adet = g.adet;
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) o[p * cmaxp + k] = gm[p];
+    o[NP * cmaxp + k] = adet;
+  }
+}
+
+template <int DIM, int DEG, int VAR, int NT, int G, bool CM = false>
 __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) heat_jacobian_gather2(const G2Args a) {
   using T = RefT<DIM, DEG, VAR>;
   constexpr int ND = T::ND, NP = T::NP, NEP = (ND * (ND + 1) / 2) | 1;
@@ -470,6 +505,11 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) heat_jacobian_gather2(c
   const uint32_t cls0 = sbase + a.off_meta;
 
   // phase-A inputs (vertex table + local vertex ids), double buffered: issued one block ahead
+  auto issue_M = [&](int64_t blk) {  // CM: all (NP + 1) metric rows of block blk, single buffer
+    const uint32_t mb = (uint32_t)((NP + 1) * a.cmaxp * 8);
+    mbar_expect_tx(&bars[2], mb);
+    bulk_g2s(smraw + a.off_met, a.bmetric + blk * (int64_t)(NP + 1) * a.cmaxp, mb, &bars[2]);
+  };
   auto issue_A = [&](const BlockDesc2 &d, int buf) {
     const uint32_t vb = (uint32_t)(((d.nvert * DIM + 1) & ~1) * 8);
     const uint32_t cb = (uint32_t)(((d.ncell + 3) & ~3) * 4);
@@ -497,7 +537,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) heat_jacobian_gather2(c
     mbar_init(&bars[3], 1);
     sdesc[0] = a.bdesc[b];
     if (b + stride < a.nblocks) sdesc[1] = a.bdesc[b + stride];
-    issue_A(sdesc[0], 0);
+    if constexpr (CM) issue_M(b); else issue_A(sdesc[0], 0);
   }
   if (threadIdx.x < 16) sts_f64(sbase + (a.zaddr + threadIdx.x) * 8, 0.0);  // one staged zero per 8-byte bank
   __syncthreads();
@@ -513,7 +553,8 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) heat_jacobian_gather2(c
     BlockDesc2 dnn;
     if (producer) {
       if (loadB) issue_B(d);
-      if (bn < a.nblocks) issue_A(sdesc[(it + 1) & 3], (it + 1) & 1);
+      if constexpr (!CM)
+        if (bn < a.nblocks) issue_A(sdesc[(it + 1) & 3], (it + 1) & 1);
       if (bnn < a.nblocks) dnn = a.bdesc[bnn];
     }
     if (loadB) {
@@ -521,25 +562,34 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) heat_jacobian_gather2(c
       ++nloadB;
     }
     // ---- phase A
-    mbar_wait(&bars[2 + (it & 1)], (uint32_t)((it >> 1) & 1));
+    if constexpr (CM) mbar_wait(&bars[2], (uint32_t)(it & 1));
+    else mbar_wait(&bars[2 + (it & 1)], (uint32_t)((it >> 1) & 1));
     const int ncell = FDTS_DEV(a, 1) ? 0 : d.ncell;
     const uint32_t lcc0 = sbase + a.off_lcc + (it & 1) * a.inA_bytes, vt0 = sbase + a.off_vtab + (it & 1) * a.inA_bytes;
+    const uint32_t met0 = sbase + a.off_met;
     for (int k = threadIdx.x; k < ncell; k += NT) {
-      const uint32_t packed = lds_u32(lcc0 + k * 4);
-      double X[DIM + 1][DIM];
+      double gm[NP], adet;
+      if constexpr (CM) {
 #pragma unroll
-      for (int v = 0; v <= DIM; ++v) {
-        const uint32_t va = vt0 + ((packed >> (8 * v)) & 255u) * (DIM * 8);
+        for (int p = 0; p < NP; ++p) gm[p] = lds_f64(met0 + (uint32_t)(p * a.cmaxp + k) * 8u);
+        adet = lds_f64(met0 + (uint32_t)(NP * a.cmaxp + k) * 8u);
+      } else {
+        const uint32_t packed = lds_u32(lcc0 + k * 4);
+        double X[DIM + 1][DIM];
 #pragma unroll
-        for (int q = 0; q < DIM; ++q) X[v][q] = lds_f64(va + q * 8);
+        for (int v = 0; v <= DIM; ++v) {
+          const uint32_t va = vt0 + ((packed >> (8 * v)) & 255u) * (DIM * 8);
+#pragma unroll
+          for (int q = 0; q < DIM; ++q) X[v][q] = lds_f64(va + q * 8);
+        }
+        Geom<DIM> g;
+        geometry_from_vertices<DIM>(X, g);
+        metric<DIM>(g, gm);
+        adet = g.adet;
       }
-      Geom<DIM> g;
-      geometry_from_vertices<DIM>(X, g);
-      double gm[NP];
-      metric<DIM>(g, gm);
       const uint32_t st = sbase + k * (NEP * 8);
       if constexpr (T::INT) {
-        const double ms = a.shift * g.adet * (1.0 / T::RDEN);
+        const double ms = a.shift * adet * (1.0 / T::RDEN);
 #pragma unroll
         for (int p = 0; p < NP; ++p) gm[p] *= (1.0 / T::SDEN);
         static_for<ND>([&](auto I) {
@@ -551,7 +601,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) heat_jacobian_gather2(c
           });
         });
       } else {
-        const double m = a.shift * g.adet;
+        const double m = a.shift * adet;
         static_for<ND>([&](auto I) {
           constexpr int i = decltype(I)::value;
           static_for<ND - i>([&](auto JJ) {
@@ -564,6 +614,8 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) heat_jacobian_gather2(c
     }
     if (producer && bnn < a.nblocks) sdesc[(it + 2) & 3] = dnn;
     __syncthreads();
+    if constexpr (CM)  // every thread is done with the metric buffer: fetch the next block's behind phase B
+      if (producer && bn < a.nblocks) issue_M(bn);
     // ---- phase B: class by class, no barrier in between
     if (loadB) mbar_wait(&bars[1], (nloadB - 1u) & 1u);
     const uint32_t lo = (uint32_t)(d.s0 & (G - 1)), span = FDTS_DEV(a, 8) ? 0u : (uint32_t)d.nslots;
@@ -621,7 +673,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) heat_jacobian_gather2(c
   }
 }
 
-template <int DIM, int DEG, int VAR, int NT>
+template <int DIM, int DEG, int VAR, int NT, bool CM = false>
 int launch_gather2_nt(G2Args a, const GatherPlan2 &p, cudaStream_t s) {
   using T = RefT<DIM, DEG, VAR>;
   constexpr int ND = T::ND, NEP = (ND * (ND + 1) / 2) | 1;
@@ -639,7 +691,12 @@ int launch_gather2_nt(G2Args a, const GatherPlan2 &p, cudaStream_t s) {
   a.inA_bytes = (int)(up16(8 * (size_t)p.vmax * DIM + 16) + up16(4 * (size_t)p.cmax + 16));
   a.off_vtab = (int)off;
   a.off_lcc = (int)(off + up16(8 * (size_t)p.vmax * DIM + 16));
-  off += 2 * (size_t)a.inA_bytes;
+  a.off_met = (int)off;
+  a.cmaxp = p.cmaxp;
+  if (CM)
+    off += up16(8 * (size_t)(T::NP + 1) * p.cmaxp);  // one buffer of cached metrics replaces the two vertex-table buffers
+  else
+    off += 2 * (size_t)a.inA_bytes;
   a.off_bar = (int)off;
   off += 32;
   a.off_desc = (int)off;
@@ -659,15 +716,38 @@ int launch_gather2_nt(G2Args a, const GatherPlan2 &p, cudaStream_t s) {
     kern<<<(unsigned)grid, NT, smem, s>>>(a);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
   };
-  if (p.sector == 4) return launch(heat_jacobian_gather2<DIM, DEG, VAR, NT, 4>);
-  if (p.sector == 2) return launch(heat_jacobian_gather2<DIM, DEG, VAR, NT, 2>);
-  return launch(heat_jacobian_gather2<DIM, DEG, VAR, NT, 1>);
+  if (p.sector == 4) return launch(heat_jacobian_gather2<DIM, DEG, VAR, NT, 4, CM>);
+  if (p.sector == 2) return launch(heat_jacobian_gather2<DIM, DEG, VAR, NT, 2, CM>);
+  return launch(heat_jacobian_gather2<DIM, DEG, VAR, NT, 1, CM>);
 }
 
 template <int DIM, int DEG, int VAR>
 int launch_gather2(G2Args a, const GatherPlan2 &p, int threads, cudaStream_t s) {
-  if (threads == 512) return launch_gather2_nt<DIM, DEG, VAR, 512>(a, p, s);
+  if (threads == 512) {
+    if (a.bmetric) {  // cached metrics: falls back to the vertex-table kernel when the metric buffer does not fit
+      const int rc = launch_gather2_nt<DIM, DEG, VAR, 512, true>(a, p, s);
+      if (rc != 4) return rc;
+    }
+    return launch_gather2_nt<DIM, DEG, VAR, 512>(a, p, s);
+  }
   return launch_gather2_nt<DIM, DEG, VAR, 1024>(a, p, s);
+}
+
+// builds the plan's metric cache on first use (option cache_metric); a failed allocation just leaves it off
+template <int DIM>
+void ensure_metrics(fdts_engine *e, cudaStream_t s) {
+  GatherPlan2 &p = e->plan2;
+  if (p.bmetric || !e->opt_cache_metric || p.cmaxp <= 0) return;
+  constexpr int NP = DIM * (DIM + 1) / 2;
+  const size_t bytes = sizeof(double) * (size_t)p.nblocks * (NP + 1) * p.cmaxp + 64;
+  if (cudaMalloc(&p.bmetric, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    p.bmetric = nullptr;
+    e->opt_cache_metric = 0;
+    return;
+  }
+  block_metrics<DIM><<<(unsigned)p.nblocks, 128, 0, s>>>(p.bdesc, p.bcc, p.bvcoords, p.cmaxp, p.bmetric);
+  e->launches++;
 }
 
 __global__ void set_values_k(double *__restrict__ v, const int64_t *__restrict__ slots, int64_t n, double val) {
@@ -724,9 +804,13 @@ static int launch_heat_impl(fdts_engine *e, int which, const double *x, const do
     return 3;
   }
   if (e->opt_scatter == 2 && which == 1 && e->plan2.ready) {
+    if (dim == 1) ensure_metrics<1>(e, s);
+    if (dim == 2) ensure_metrics<2>(e, s);
+    if (dim == 3) ensure_metrics<3>(e, s);
     const GatherPlan2 &p = e->plan2;
     G2Args g;
     g.bdesc = p.bdesc; g.cidx = p.cidx; g.gdst = p.gdst; g.cmeta = p.cmeta; g.bcc = p.bcc; g.bvcoords = p.bvcoords;
+    g.bmetric = e->opt_cache_metric && !e->opt_overlap ? p.bmetric : nullptr;
     g.out = out; g.nblocks = p.nblocks; g.shift = shift;
 #ifdef FDTS_DEV_SWITCHES
     g.dbg = (int32_t)e->opt_debug;

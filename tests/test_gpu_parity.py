@@ -127,9 +127,11 @@ def test_overlapped_kernel_bitwise_equal(dim, degree, n, ftile):
 
     form, bcs, u, udot = make_problem("heat", dim, degree, n, tile=2, ftile=ftile)
     x, xd = u.data.cuda(), udot.data.cuda()
-    e0 = Engine(form, bcs, device="cuda:0", scatter=2, options={"overlap": 0})
+    # cache_metric 0: both kernels form the geometry inline (the cached metrics come out of another kernel)
+    e0 = Engine(form, bcs, device="cuda:0", scatter=2, options={"overlap": 0, "cache_metric": 0})
     e1 = Engine(form, bcs, device="cuda:0", scatter=2, options={"overlap": 1})
     J0 = e0.ijacobian(0.0, x, xd, 3.0)
+    assert e0.get_option("plan_metric_cached") == 0
     for _ in range(3):  # repeated launches: the hand-over barriers must not depend on timing
         assert torch.equal(e1.ijacobian(0.0, x, xd, 3.0), J0)
     assert rel_err(J0.cpu().numpy(), Oracle.from_form(form, bcs).ijacobian(0.0, u.data, udot.data, 3.0)) < TOL
@@ -277,3 +279,25 @@ def test_quadrilateral_engine_matches_oracle(family, warp, tile):
         eng.set_option("scatter", 2)
     with pytest.raises(EngineError):
         eng.set_row_blocks(torch.tensor([0, eng.num_rows]))
+
+
+@pytest.mark.parametrize("dim,degree,n,ftile", [(3, 2, 8, (6, 4, 4)), (3, 2, 7, 6), (2, 2, 12, (8, 4)), (3, 1, 9, 4),
+                                                (2, 3, 6, 4), (1, 2, 30, 6), (2, 1, 20, 14)])
+def test_cached_metric_gather(dim, degree, n, ftile):
+    """plan 2 with the per-block cell metrics precomputed (default) against the kernel that forms the geometry
+    from the vertex table, against the oracle, run-to-run bitwise, and across a change of shift."""
+    from firedrake_ts_b200.engine import Engine
+    from oracle import Oracle
+
+    mt = tuple(max(t // degree, 1) for t in ftile) if isinstance(ftile, tuple) else max(ftile // degree, 1)
+    form, bcs, u, udot = make_problem("heat", dim, degree, n, tile=mt, ftile=ftile)
+    x, xd = u.data.cuda(), udot.data.cuda()
+    orc = Oracle.from_form(form, bcs)
+    e1 = Engine(form, bcs, device="cuda:0", scatter=2)
+    e0 = Engine(form, bcs, device="cuda:0", scatter=2, options={"cache_metric": 0})
+    for shift in (10.0, 0.0, 1234.5):
+        J1 = e1.ijacobian(0.0, x, xd, shift)
+        assert e1.get_option("plan_metric_cached") == 1 and e0.get_option("plan_metric_cached") == 0
+        assert torch.equal(J1, e1.ijacobian(0.0, x, xd, shift))
+        assert rel_err(J1.cpu().numpy(), e0.ijacobian(0.0, x, xd, shift).cpu().numpy()) < TOL
+        assert rel_err(J1.cpu().numpy(), orc.ijacobian(0.0, u.data, udot.data, shift)) < TOL

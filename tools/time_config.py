@@ -29,6 +29,7 @@ ap.add_argument("--threads", type=int, default=512)
 ap.add_argument("--rtiles", type=int, default=0)
 ap.add_argument("--dedup", type=int, default=1)
 ap.add_argument("--foffset", type=int, default=0)
+ap.add_argument("--cache-metric", type=int, default=1)
 ap.add_argument("--dmma", type=int, default=-1)
 a = ap.parse_args()
 
@@ -48,7 +49,8 @@ torch.cuda.synchronize()
 print("mesh+space", time.time() - t0, "s; cells", form.space.mesh.num_cells, "dofs", form.space.num_dofs, flush=True)
 t0 = time.time()
 eng = Engine(form, bcs, scatter=a.scatter, plan_version=a.plan, dedup=a.dedup,
-             options={"sector": a.sector, "optimize": a.optimize, "threads": a.threads, "residual_tiles": a.rtiles})
+             options={"sector": a.sector, "optimize": a.optimize, "threads": a.threads, "residual_tiles": a.rtiles,
+                      "cache_metric": a.cache_metric})
 if a.rtiles:
     eng.set_option("residual_tiles", a.rtiles)
 torch.cuda.synchronize()
