@@ -288,6 +288,13 @@ _TRI_RULES = {
     1: [(1, 1.0)],
     2: [(3, 1 / 3, 1 / 6)],
     4: [(3, 0.223381589678011, 0.445948490915965), (3, 0.109951743655322, 0.091576213509771)],
+    # Radon's 7-point rule (degree 5: vector-P2 Burgers, configuration C2) and the 12- / 16-point rules of
+    # degree 6 / 8 (Dunavant 1985) instead of the 9 / 16 / 25 points of the collapsed Gauss rules
+    5: [(1, 0.225), (3, 0.125939180544827, 0.101286507323456), (3, 0.132394152788506, 0.470142064105115)],
+    6: [(3, 0.116786275726379, 0.249286745170910), (3, 0.050844906370207, 0.063089014491502),
+        (6, 0.082851075618374, 0.053145049844817, 0.310352451033784)],
+    8: [(1, 0.144315607677787), (3, 0.095091634267285, 0.459292588292723), (3, 0.103217370534718, 0.170569307751760),
+        (3, 0.032458497623198, 0.050547228317031), (6, 0.027230314174435, 0.008394777409958, 0.263112829634638)],
 }
 _TET_RULES = {
     1: [(1, 1.0)],
@@ -334,9 +341,10 @@ def _quadrature_simplex(dim: int, degree: int):
             if d >= degree:
                 return _sym_tet(_TET_RULES[d])
     n = degree // 2 + 1
-    if dim == 3 and degree >= 6:
-        # high-order tetrahedra (P3 heat: degree 6, P3 BBM / P2 Cahn-Hilliard: degree 8): 35 / 70 points
-        # instead of the 64 / 125 of the collapsed rule below -- the quadrature kernels are compute bound there
+    if dim == 3 and degree >= 3:
+        # tetrahedra beyond the 4-point rule: Grundmann-Moeller rules with 5 / 15 / 35 / 70 points (degree 3 / 5 /
+        # 7 / 9) instead of the 8 / 27 / 64 / 125 of the collapsed rule below -- the quadrature kernels are
+        # compute bound there (P2 heat and Burgers: degree 4-5, P3 heat: 6, P3 BBM / P2 Cahn-Hilliard: 8)
         return _grundmann_moeller(3, degree // 2)
     if dim == 1:
         x, w = _gauss_jacobi_01(n, 0)
