@@ -12,6 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 IMEX_DT = 2.0e-4
+CH_DT = 5.0e-6
 
 
 def run(rank, world, port, outdir, family, dim, degree, n, grid, solve):
@@ -57,6 +58,17 @@ def run(rank, world, port, outdir, family, dim, degree, n, grid, solve):
                                solver_parameters={"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-13},
                                rhs_projection_parameters={"ksp_rtol": 1e-14})
         solver.ts.setTimeStep(IMEX_DT)
+        solver.solve()
+        out["u_final"] = u.owned().clone()
+        out["steps"] = solver.ts.getStepNumber()
+    elif solve == "ch":
+        # mixed (field-blocked) space on a partition with the default-style Jacobi preconditioner: the diagonal of
+        # dof (m, i) sits at local column m*num_nodes + i, not m*num_owned + i
+        problem = fts.DAEProblem(form, u, udot, (0.0, 2 * CH_DT), bcs=None)
+        solver = fts.DAESolver(problem, assembler=asm, comm=dist.group.WORLD,
+                               solver_parameters={"ksp_type": "gmres", "pc_type": "jacobi", "ksp_rtol": 1e-13,
+                                                  "snes_rtol": 1e-10, "snes_atol": 1e-11, "ksp_max_it": 4000,
+                                                  "ksp_gmres_restart": 200, "ts_dt": CH_DT})
         solver.solve()
         out["u_final"] = u.owned().clone()
         out["steps"] = solver.ts.getStepNumber()
