@@ -1,5 +1,6 @@
 // fdts_common.cuh -- engine state and device helpers shared by all translation units.
 #pragma once
+#include <vector>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
@@ -154,6 +155,7 @@ struct fdts_engine {
   double *bbm_T = nullptr;       // reference tensor of the tensor-contraction BBM Jacobian (built on first use)
   int64_t opt_overlap = 0;       // plan 2: warp-specialised kernel (element matrices of block b+1 overlap the gather of block b; needs two staging buffers in smem; slower than the two-phase kernel on every block shape measured so far)
   int64_t opt_cache_metric = 1;  // plan 2: phase A reads precomputed cell metrics (one TMA copy per block) instead of forming the geometry from the vertex table (30 % of its fp64 work, 13 conflict-prone loads per cell); costs (NP+1)*8 bytes per block cell of device memory and HBM reads
+  int64_t opt_pipelined_readback = 1;  // fdts_ijacobian_host on the gather path: assemble in 8 block ranges, read range i back while range i+1 is assembled (A/B on one box at C4: 202.2 against 207.1 ms)
   int64_t opt_threads = 512;     // plan 2: threads per persistent CTA (512: 128 registers per thread, or 1024)
   int64_t opt_debug = 0;         // development only (timing experiments with phases switched off)
   int variant = -1;              // which baked RefT table matches cfg.R (-1: none, closed-form path off)
@@ -161,6 +163,11 @@ struct fdts_engine {
   double *h2d_x = nullptr, *h2d_xdot = nullptr, *d_f = nullptr, *d_vals = nullptr;  // host-variant staging
   double *scr_x = nullptr, *scr_xdot = nullptr;  // coefficient-scaled states of the diffusion family
   int64_t launches = 0;
+  int64_t gather_b0 = 0, gather_b1 = 0;  // transient: block range of the next plan-2 Jacobian launch (0, 0 = all)
+  cudaStream_t copy_stream = nullptr;    // host-buffer Jacobian: read-back of chunk i overlaps the kernel of chunk i+1
+  cudaEvent_t chunk_event[16] = {};
+  std::vector<int64_t> chunk_slot;       // first CSR slot of every chunk (+ nnz), for plan2.nblocks blocks
+  int64_t chunk_for_blocks = -1;
   int64_t h2d_bytes = 0, d2h_bytes = 0;  // moved by the host-buffer entry points so far (bench.py's e2e record)
   cudaStream_t own_stream = nullptr;
 };

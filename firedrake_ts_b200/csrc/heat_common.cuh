@@ -16,7 +16,8 @@ struct G2Args {
   const double *bvcoords;
   const double *bmetric;  // cached cell metrics (cache_metric): block b at b * (NP + 1) * cmaxp
   double *out;
-  int64_t nblocks;
+  int64_t nblocks;       // end of the block range of this launch (exclusive)
+  int64_t block_first;   // first block of this launch (0 unless the caller pipelines the output in chunks)
   double shift;
   int32_t cmaxp, off_met;
   int32_t off_idx, off_meta, off_gdst, off_vtab, off_lcc, off_bar, off_desc, zaddr, sector, inA_bytes, stage_bytes;

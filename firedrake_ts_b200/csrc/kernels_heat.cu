@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) heat_jacobian_gather2(c
   };
 
   const int64_t stride = gridDim.x;
-  int64_t b = blockIdx.x;
+  int64_t b = a.block_first + blockIdx.x;
   if (b >= a.nblocks) return;
   // descriptors are fetched two blocks ahead (ring of four in shared memory), phase-A inputs one block
   // ahead, so no dependent global access sits on a block's critical path
@@ -711,8 +711,9 @@ int launch_gather2_nt(G2Args a, const GatherPlan2 &p, cudaStream_t s) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
     int occ = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem) != cudaSuccess || occ < 1) occ = 1;
-    const int64_t slots = (int64_t)sms * occ;
-    const int64_t grid = p.nblocks < slots ? p.nblocks : slots;
+    const int64_t slots = (int64_t)sms * occ, nlaunch = a.nblocks - a.block_first;
+    const int64_t grid = nlaunch < slots ? nlaunch : slots;
+    if (grid <= 0) return 0;
     kern<<<(unsigned)grid, NT, smem, s>>>(a);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
   };
@@ -812,6 +813,11 @@ static int launch_heat_impl(fdts_engine *e, int which, const double *x, const do
     g.bdesc = p.bdesc; g.cidx = p.cidx; g.gdst = p.gdst; g.cmeta = p.cmeta; g.bcc = p.bcc; g.bvcoords = p.bvcoords;
     g.bmetric = e->opt_cache_metric && !e->opt_overlap ? p.bmetric : nullptr;
     g.out = out; g.nblocks = p.nblocks; g.shift = shift;
+    g.block_first = 0;
+    if (e->gather_b1 > e->gather_b0 && !e->opt_overlap) {  // block range requested by fdts_ijacobian_host (pipelined read-back)
+      g.block_first = e->gather_b0;
+      g.nblocks = e->gather_b1 < p.nblocks ? e->gather_b1 : p.nblocks;
+    }
 #ifdef FDTS_DEV_SWITCHES
     g.dbg = (int32_t)e->opt_debug;
 #endif

@@ -145,7 +145,9 @@ int fdts_ijacobian_range(fdts_handle h, double t, const double *x, const double 
                          int64_t cell_begin, int64_t cell_end, int32_t flags, void *stream);
 
 /* host-buffer variants: pinned or pageable host pointers; H2D / D2H copies are part of the call (the Jacobian of the
- * linear families does not read the state, so fdts_ijacobian_host uploads nothing for them); the bytes moved so far
+ * linear families does not read the state, so fdts_ijacobian_host uploads nothing for them; on the gather path it
+ * assembles the row blocks in 8 ranges and reads each range back while the next is assembled, option
+ * "pipelined_readback" 1|0); the bytes moved so far
  * are read back with fdts_get_option "h2d_bytes" / "d2h_bytes" */
 int fdts_ifunction_host(fdts_handle h, double t, const double *x_host, const double *xdot_host, double *f_host);
 int fdts_ijacobian_host(fdts_handle h, double t, const double *x_host, const double *xdot_host, double shift,
