@@ -14,6 +14,18 @@ Jh = torch.empty(eng.nnz, dtype=torch.float64).pin_memory()
 for rep in range(2):
     for mode in (0, 1):
         eng.set_option("pipelined_readback", mode)
+        eng.ifunction_host(0.0, xh, xdh, Fh)
+        eng.ijacobian_host(0.0, xh, xdh, 10.0, Jh)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):  # alternating, as bench.py's e2e leg does
+            eng.ifunction_host(0.0, xh, xdh, Fh)
+            eng.ijacobian_host(0.0, xh, xdh, 10.0, Jh)
+        torch.cuda.synchronize()
+        print(f"pipelined {mode}: alternating pair {(time.perf_counter()-t0)/3*1e3:.1f} ms", flush=True)
+for rep in range(2):
+    for mode in (0, 1):
+        eng.set_option("pipelined_readback", mode)
         eng.ijacobian_host(0.0, xh, xdh, 10.0, Jh)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
