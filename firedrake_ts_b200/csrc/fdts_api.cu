@@ -372,7 +372,7 @@ extern "C" int fdts_set_option(fdts_handle e, const char *key, int64_t value) {
     return 0;
   }
   if (!strcmp(key, "optimize")) {
-    e->opt_optimize = value ? 1 : 0;
+    e->opt_optimize = value == 2 ? 2 : (value ? 1 : 0);  // 2: lane orders only, no regrouping of store groups (experiment)
     return 0;
   }
   if (!strcmp(key, "residual_tiles")) {
@@ -447,9 +447,11 @@ extern "C" int fdts_set_row_blocks(fdts_handle e, const int64_t *starts_host, in
   if (e->opt_plan_version == 2) {
     fdts_free_plan(e);
     int rc = fdts_build_plan2(e, starts_host, nblocks);
-    // meshes without repeated blocks stream their index tables from HBM on every call: 16-byte store groups pad
-    // the SELL lists less (4.83 G instead of 6.10 G entries at C4), which outweighs their partial-sector stores
-    if (rc == 0 && e->sector_auto && e->opt_sector == 4 && nblocks >= 64 && e->plan2.unique_patterns * 4 > nblocks) {
+    // meshes without repeated blocks stream their index tables from HBM on every call: with unoptimised lane orders,
+    // 16-byte store groups pad the SELL lists less (4.83 G instead of 6.10 G entries at C4), which outweighs their
+    // partial-sector stores (7.89 -> 7.48 ms); with the GPU lane-order optimiser 32-byte groups win (6.42 vs 6.69 ms)
+    if (rc == 0 && e->sector_auto && !e->opt_optimize && e->opt_sector == 4 && nblocks >= 64 &&
+        e->plan2.unique_patterns * 4 > nblocks) {
       fdts_free_plan2(e);
       e->opt_sector = 2;
       rc = fdts_build_plan2(e, starts_host, nblocks);
@@ -500,6 +502,10 @@ extern "C" int fdts_get_option(fdts_handle e, const char *key, int64_t *value) {
   }
   if (!strcmp(key, "plan_sector")) {
     *value = v2 ? e->plan2.sector : 0;
+    return 0;
+  }
+  if (!strcmp(key, "plan_optimized")) {  // 0 no, 1 host (store groups + lane orders), 2 GPU (lane orders)
+    *value = v2 ? e->plan2.optimized : 0;
     return 0;
   }
   if (!strcmp(key, "plan_cells_max")) {

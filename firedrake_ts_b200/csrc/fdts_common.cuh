@@ -148,7 +148,7 @@ struct fdts_engine {
   int64_t opt_plan_version = 2;  // what fdts_set_row_blocks builds: 1 = windowed SELL (+ residual lists), 2 = sector SELL
   int64_t opt_dedup = 1;         // plan 2: share identical block patterns
   int64_t opt_sector = 4;        // plan 2: slots per store group (4 or 2)
-  bool sector_auto = true;       // "sector" not set by the caller: 16-byte groups when the pattern dictionary does not pay (measured: the streamed index tables shrink by 21 %, 7.89 -> 7.48 ms at C4 without dictionary)
+  bool sector_auto = true;       // "sector" not set by the caller: 16-byte groups when the pattern dictionary does not pay and the lane orders are not optimised (the streamed index tables shrink by 21 %, 7.89 -> 7.48 ms at C4 without dictionary)
   int64_t opt_optimize = 1;      // plan 2: bank-conflict-aware column order for the unique patterns
   int64_t opt_residual_tiles = 1; // residual: tile kernel (pre-reduced atomics) when a cell-tile plan exists (fdts_set_cell_tiles; the Python layer only builds one on request: the kernel is slower than the per-cell one today)
   int64_t opt_dmma = 2;          // BBM P2/P3 Jacobian on the fp64 tensor cores: 2 = reference-tensor contraction (default), 1 = quadrature formulation, 0 = generic kernel

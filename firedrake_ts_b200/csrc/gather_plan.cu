@@ -1000,7 +1000,135 @@ struct LaneOrder {
 };
 }  // namespace
 
-static void optimize_pattern(const BlockDesc2 &d, const uint2 *cls, uint16_t *idx, uint16_t *gdst, int G, int zaddr) {
+// ---- the same lane-order refinement on the GPU, for plans with many unique patterns (meshes without repeated
+// blocks: every block keeps its own tables, and walking them on the host would take minutes).  One warp per slice;
+// the two half-warps are independent (a 64-bit shared-memory load is served half-warp by half-warp).  The 16
+// lanes of a half take turns: for the lane whose turn it is, all 16 lanes evaluate candidate orders of its w
+// addresses (all w! permutations for w <= 5, the 2 w rotations / reversed rotations above) against the bank
+// occupancy of the other 15 lanes, the best one (ties: the current order) is kept.  Padding entries finally
+// take the staged zero of the least occupied bank.  Measured at C4 on the dictionary path: lane orders alone
+// bring the gather from 7.45 to 5.94 ms, regrouping the store groups as well (host only) to 5.87 ms.
+constexpr int OPT_WARPS = 8, OPT_MAXW = 8;
+
+__device__ __forceinline__ void perm_from_index(int p, int w, int (&pm)[OPT_MAXW]) {
+  // p-th permutation of 0..w-1 in the factorial number system (p = 0: identity)
+  int avail[OPT_MAXW];
+#pragma unroll
+  for (int k = 0; k < OPT_MAXW; ++k) avail[k] = k;
+  int f = 1;
+  for (int k = 2; k < w; ++k) f *= k;  // (w-1)!
+  for (int k = 0; k < w; ++k) {
+    const int q = p / f;
+    p -= q * f;
+    pm[k] = avail[q];
+    for (int t = q; t < w - 1 - k; ++t) avail[t] = avail[t + 1];
+    if (w - 1 - k > 0) f /= (w - 1 - k);
+  }
+}
+
+__global__ void __launch_bounds__(OPT_WARPS * 32) optimize_lane_orders(const BlockDesc2 *__restrict__ bdesc,
+                                                                       const uint2 *__restrict__ cmeta,
+                                                                       uint16_t *__restrict__ cidx, int zaddr, int sweeps) {
+  __shared__ uint16_t sA[OPT_WARPS][32][OPT_MAXW];
+  __shared__ uint16_t sC[OPT_WARPS][2][OPT_MAXW][OPT_MAXW];
+  const int64_t b = blockIdx.x;
+  const BlockDesc2 d = bdesc[b];
+  if (d.pattern != (int32_t)b || d.nidx == 0) return;  // shared tables are optimised once, through their owner
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, hl = lane & 15;
+  uint16_t(*A)[OPT_MAXW] = sA[warp];
+  uint16_t(*Cm)[OPT_MAXW] = sC[warp][half];
+  for (int c = 0; c < d.ncls; ++c) {
+    const uint2 ce = cmeta[d.cls_off + c];
+    const int count = (int)(ce.x >> 16), w = (int)((ce.y >> 16) & 0xffu);
+    if (w < 2 || w > OPT_MAXW || count < 1) continue;
+    const int pairs = (w + 1) >> 1;
+    uint16_t *cbase = cidx + d.idx_off + (size_t)(ce.y & 0xffffu) * 64;
+    int nperm = 2 * w;
+    if (w <= 5) {
+      nperm = 1;
+      for (int k = 2; k <= w; ++k) nperm *= k;
+    }
+    for (int sl = warp; sl < count; sl += OPT_WARPS) {
+      auto at = [&](int k) -> uint16_t & { return cbase[((size_t)sl * pairs + (size_t)(k >> 1)) * 64 + 2 * lane + (k & 1)]; };
+      for (int k = 0; k < w; ++k) A[lane][k] = at(k);
+      __syncwarp();
+      for (int sweep = 0; sweep < sweeps; ++sweep) {
+        bool changed = false;
+        for (int j = 0; j < 16; ++j) {
+          const int L = half * 16 + j;  // the lane of my half whose turn it is
+          // conflicts of value m in column k with the other lanes of the half
+          for (int q = hl; q < w * w; q += 16) {
+            const int k = q / w, m = q - k * w;
+            const uint16_t v = A[L][m];
+            int cnt = 0;
+            if (v < zaddr) {
+              for (int l = half * 16; l < half * 16 + 16; ++l) {
+                const uint16_t x = A[l][k];
+                cnt += (l != L && x < zaddr && ((x ^ v) & 15) == 0 && x != v) ? 1 : 0;
+              }
+            }
+            Cm[k][m] = (uint16_t)cnt;
+          }
+          __syncwarp();
+          uint32_t bestkey = 0xffffffffu;
+          for (int pi = hl; pi < nperm; pi += 16) {
+            int pm[OPT_MAXW];
+            if (w <= 5) {
+              perm_from_index(pi, w, pm);
+            } else {
+              const int r = pi >> 1;
+              for (int k = 0; k < w; ++k) pm[k] = (pi & 1) ? (w - 1 - ((k + r) % w)) : ((k + r) % w);
+            }
+            uint32_t cst = 0;
+            for (int k = 0; k < w; ++k) cst += Cm[k][pm[k]];
+            const uint32_t key = (cst << 12) | (uint32_t)pi;  // ties: the lowest index, i.e. the current order first
+            bestkey = key < bestkey ? key : bestkey;
+          }
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) {
+            const uint32_t other = __shfl_xor_sync(0xffffffffu, bestkey, o);
+            bestkey = other < bestkey ? other : bestkey;
+          }
+          const int bp = (int)(bestkey & 0xfffu);
+          if (bp != 0 && hl == 0) {  // one lane of the half rewrites row L
+            int pm[OPT_MAXW];
+            if (w <= 5) {
+              perm_from_index(bp, w, pm);
+            } else {
+              const int r = bp >> 1;
+              for (int k = 0; k < w; ++k) pm[k] = (bp & 1) ? (w - 1 - ((k + r) % w)) : ((k + r) % w);
+            }
+            uint16_t old[OPT_MAXW];
+            for (int k = 0; k < w; ++k) old[k] = A[L][k];
+            for (int k = 0; k < w; ++k) A[L][k] = old[pm[k]];
+          }
+          changed |= bp != 0;
+          __syncwarp();
+        }
+        if (!__any_sync(0xffffffffu, changed)) break;
+      }
+      // padding: the staged zero of the least occupied bank of the column (per half)
+      for (int k = 0; k < w; ++k) {
+        const uint16_t v = A[lane][k];
+        const bool real = v < zaddr;
+        int bestb = 0, bestn = 99;
+        for (int bk = 0; bk < 16; ++bk) {
+          const unsigned m = __ballot_sync(0xffffffffu, real && (v & 15) == bk);
+          const int n = __popc(half ? (m >> 16) : (m & 0xffffu));
+          if (n < bestn) {
+            bestn = n;
+            bestb = bk;
+          }
+        }
+        at(k) = real ? v : (uint16_t)(zaddr + bestb);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+static void optimize_pattern(const BlockDesc2 &d, const uint2 *cls, uint16_t *idx, uint16_t *gdst, int G, int zaddr,
+                             bool regroup = true) {
   const int per_norm = 32 / G;
   LaneOrder lo;
   BankLoad load;
@@ -1014,7 +1142,7 @@ static void optimize_pattern(const BlockDesc2 &d, const uint2 *cls, uint16_t *id
     uint16_t *cbase = idx + (size_t)(cls[c].y & 0xffffu) * 64;
     auto at = [&](int sl, int k, int lane) -> uint16_t & { return cbase[((size_t)sl * pairs + (size_t)(k >> 1)) * 64 + 2 * lane + (k & 1)]; };
     // ---- regroup the store groups of narrow, non-split classes
-    if (!split && w <= 8 && count >= 2) {
+    if (regroup && !split && w <= 8 && count >= 2) {
       struct Unit {
         uint16_t gd;
         std::vector<std::vector<uint16_t>> lanes;  // [G][w]
@@ -1376,6 +1504,15 @@ int fdts_build_plan2(fdts_engine *e, const int64_t *starts, int64_t nb) {
       }
       p.unique_patterns = uniq;
       p.shared_idx = shared;
+      if (e->opt_optimize && uniq > 4096) {  // too many unique patterns for the host walk: lane orders on the GPU
+        optimize_lane_orders<<<(unsigned)nb, OPT_WARPS * 32, 0, s>>>(p.bdesc, p.cmeta, p.cidx, p.zaddr, 3);
+        if (cudaStreamSynchronize(s) != cudaSuccess) {
+          fdts_set_error("gather plan 2: lane-order optimisation failed");
+          rc = 2;
+          break;
+        }
+        p.optimized = 2;
+      }
       if (e->opt_optimize && uniq <= 4096) {
         std::vector<uint2> hm;
         std::vector<uint16_t> hi, hg;
@@ -1389,7 +1526,7 @@ int fdts_build_plan2(fdts_engine *e, const int64_t *starts, int64_t nb) {
                cudaMemcpy(hi.data(), p.cidx + hd[b].idx_off, sizeof(uint16_t) * hi.size(), cudaMemcpyDeviceToHost) == cudaSuccess &&
                cudaMemcpy(hg.data(), p.gdst + hd[b].meta_off * per_norm, sizeof(uint16_t) * hg.size(), cudaMemcpyDeviceToHost) == cudaSuccess;
           if (!ok) break;
-          optimize_pattern(hd[b], hm.data(), hi.data(), hg.data(), G, p.zaddr);
+          optimize_pattern(hd[b], hm.data(), hi.data(), hg.data(), G, p.zaddr, e->opt_optimize != 2);
           ok = cudaMemcpy(p.cidx + hd[b].idx_off, hi.data(), sizeof(uint16_t) * hi.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
                cudaMemcpy(p.gdst + hd[b].meta_off * per_norm, hg.data(), sizeof(uint16_t) * hg.size(), cudaMemcpyHostToDevice) == cudaSuccess;
         }
@@ -1453,6 +1590,14 @@ int fdts_build_plan2(fdts_engine *e, const int64_t *starts, int64_t nb) {
         p.cidx = cidx2; p.gdst = gdst2; p.cmeta = cmeta2; p.bcc = bcc2;
         p.compacted = 1;
       }
+    } else if (e->opt_optimize) {  // no dictionary: every block owns its tables; lane orders on the GPU
+      optimize_lane_orders<<<(unsigned)nb, OPT_WARPS * 32, 0, s>>>(p.bdesc, p.cmeta, p.cidx, p.zaddr, 3);
+      if (cudaStreamSynchronize(s) != cudaSuccess) {
+        fdts_set_error("gather plan 2: lane-order optimisation failed");
+        rc = 2;
+        break;
+      }
+      p.optimized = 2;
     }
     p.ready = true;
   } while (0);

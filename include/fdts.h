@@ -121,9 +121,11 @@ int fdts_set_cell_tiles(fdts_handle h, const int64_t *starts_host, int64_t ntile
  *                    2 = closed-form heat kernels + owner-computes gather (deterministic, write-once);
  * schedule options (set before fdts_set_row_blocks; they never change a value beyond rounding):
  *   "plan_version" 2 (default: sector-grouped SELL + pattern dictionary) | 1 (windowed SELL, residual lists)
- *   "dedup" 1|0 share identical block tables; "optimize" 1|0 bank-conflict-aware ordering of the shared tables
- *   "sector" 4|2|1 CSR slots per store group (not set: 4, or 2 when fewer than 3/4 of the blocks repeat a pattern;
- *   read back as "plan_sector"); "threads" 512|1024 per persistent CTA
+ *   "dedup" 1|0 share identical block tables; "optimize" 1|0 bank-conflict-aware ordering of the tables (at most 4096
+ *   unique patterns: on the host, store groups + lane orders; more, or no dictionary: lane orders on the GPU, one
+ *   warp per slice; read back as "plan_optimized" 0|1|2)
+ *   "sector" 4|2|1 CSR slots per store group (not set: 4, or 2 when fewer than 3/4 of the blocks repeat a pattern
+ *   and "optimize" is off; read back as "plan_sector"); "threads" 512|1024 per persistent CTA
  *   "cache_metric" 1|0 gather Jacobian reads per-block cell metrics precomputed on first use (read back: "plan_metric_cached");
  *   "overlap" 0|1 warp-specialised Jacobian kernel; "residual_tiles" 1|0 use the tile plan when one exists
  *   "gather_residual" 0|1 (plan 1); "persist" 1|0 (plan 1)

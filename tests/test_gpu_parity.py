@@ -100,7 +100,7 @@ def test_pattern_dictionary(n, ftile):
     form, bcs, u, udot = make_problem("heat", 3, 2, n, tile=mt, ftile=ftile)
     x, xd = u.data.cuda(), udot.data.cuda()
     e1 = Engine(form, bcs, device="cuda:0", scatter=2, plan_version=2, dedup=1, options={"optimize": 0, "sector": 4})
-    e0 = Engine(form, bcs, device="cuda:0", scatter=2, plan_version=2, dedup=0, options={"sector": 4})
+    e0 = Engine(form, bcs, device="cuda:0", scatter=2, plan_version=2, dedup=0, options={"sector": 4, "optimize": 0})
     nb = e1.get_option("plan_blocks")
     assert e0.get_option("plan_patterns") == nb
     assert e1.get_option("plan_patterns") < nb
@@ -215,11 +215,14 @@ def test_pattern_dictionary_compaction():
     form, bcs, u, udot = make_problem("heat", 3, 2, 24, tile=3, ftile=6, device="cuda:0")
     x, xd = u.data, udot.data
     e1 = Engine(form, bcs, device="cuda:0", scatter=2, plan_version=2, dedup=1, options={"optimize": 0})
-    e0 = Engine(form, bcs, device="cuda:0", scatter=2, plan_version=2, dedup=0, options={"sector": 4})
+    e0 = Engine(form, bcs, device="cuda:0", scatter=2, plan_version=2, dedup=0, options={"sector": 4, "optimize": 0})
     # store-group width left to the engine: 32-byte groups while the dictionary pays, 16-byte groups for a
     # mesh without repeated blocks (its index tables stream from HBM; less SELL padding)
-    ea = Engine(form, bcs, device="cuda:0", scatter=2, plan_version=2, dedup=0)
+    ea = Engine(form, bcs, device="cuda:0", scatter=2, plan_version=2, dedup=0, options={"optimize": 0})
+    eb = Engine(form, bcs, device="cuda:0", scatter=2, plan_version=2, dedup=0)  # default: GPU lane orders, 32-byte groups
     assert e1.get_option("plan_sector") == 4 and e0.get_option("plan_sector") == 4 and ea.get_option("plan_sector") == 2
+    assert eb.get_option("plan_sector") == 4 and eb.get_option("plan_optimized") == 2
+    assert rel_err(eb.ijacobian(0.0, x, xd, 10.0).cpu().numpy(), e0.ijacobian(0.0, x, xd, 10.0).cpu().numpy()) < TOL
     assert rel_err(ea.ijacobian(0.0, x, xd, 10.0).cpu().numpy(), e0.ijacobian(0.0, x, xd, 10.0).cpu().numpy()) < TOL
     assert e1.get_option("plan_compacted") == 1 and e0.get_option("plan_compacted") == 0
     assert e1.get_option("plan_patterns") * 4 <= e1.get_option("plan_blocks")
@@ -320,3 +323,23 @@ def test_host_jacobian_pipelined_readback():
         assert torch.equal(Jh, eng.ijacobian(0.0, x, xd, shift).cpu())
     moved = eng.get_option("d2h_bytes")
     assert moved == 3 * 8 * eng.nnz and eng.get_option("h2d_bytes") == 0
+
+
+@pytest.mark.parametrize("dim,degree,n,ftile,sector", [(3, 2, 8, (6, 4, 4), 4), (3, 2, 7, 6, 2), (2, 2, 12, (8, 4), 4),
+                                                       (3, 1, 9, 4, 1), (2, 3, 6, 4, 2), (3, 3, 3, 3, 4)])
+def test_gpu_lane_order_optimiser(dim, degree, n, ftile, sector):
+    """plans without a dictionary get their lane orders refined on the GPU (one warp per slice): only the
+    summation order changes -- values against the unoptimised plan and the oracle at 1e-12, run-to-run bitwise."""
+    from firedrake_ts_b200.engine import Engine
+    from oracle import Oracle
+
+    mt = tuple(max(t // degree, 1) for t in ftile) if isinstance(ftile, tuple) else max(ftile // degree, 1)
+    form, bcs, u, udot = make_problem("heat", dim, degree, n, tile=mt, ftile=ftile)
+    x, xd = u.data.cuda(), udot.data.cuda()
+    e1 = Engine(form, bcs, device="cuda:0", scatter=2, dedup=0, options={"sector": sector, "optimize": 1})
+    e0 = Engine(form, bcs, device="cuda:0", scatter=2, dedup=0, options={"sector": sector, "optimize": 0})
+    assert e1.get_option("plan_optimized") == 2 and e0.get_option("plan_optimized") == 0
+    J1 = e1.ijacobian(0.0, x, xd, 10.0)
+    assert torch.equal(J1, e1.ijacobian(0.0, x, xd, 10.0))
+    assert rel_err(J1.cpu().numpy(), e0.ijacobian(0.0, x, xd, 10.0).cpu().numpy()) < TOL
+    assert rel_err(J1.cpu().numpy(), Oracle.from_form(form, bcs).ijacobian(0.0, u.data, udot.data, 10.0)) < TOL
