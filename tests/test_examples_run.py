@@ -11,7 +11,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 ROOT = abspath(join(dirname(__file__), ".."))
-SMALL = {"burgers.py": "10", "bbm.py": "200", "cahn-hilliard.py": "24"}
+SMALL = {"burgers.py": "10", "bbm.py": "500", "cahn-hilliard.py": "24"}
 
 
 @pytest.fixture(params=sorted(glob.glob(join(ROOT, "examples", "*.py"))), ids=lambda x: basename(x))
