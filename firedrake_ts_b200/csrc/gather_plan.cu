@@ -1504,7 +1504,7 @@ int fdts_build_plan2(fdts_engine *e, const int64_t *starts, int64_t nb) {
       }
       p.unique_patterns = uniq;
       p.shared_idx = shared;
-      if (e->opt_optimize && uniq > 4096) {  // too many unique patterns for the host walk: lane orders on the GPU
+      if (e->opt_optimize && uniq > 256) {  // too many unique patterns for the host walk (~50 ms each): lane orders on the GPU
         optimize_lane_orders<<<(unsigned)nb, OPT_WARPS * 32, 0, s>>>(p.bdesc, p.cmeta, p.cidx, p.zaddr, 3);
         if (cudaStreamSynchronize(s) != cudaSuccess) {
           fdts_set_error("gather plan 2: lane-order optimisation failed");
@@ -1513,7 +1513,7 @@ int fdts_build_plan2(fdts_engine *e, const int64_t *starts, int64_t nb) {
         }
         p.optimized = 2;
       }
-      if (e->opt_optimize && uniq <= 4096) {
+      if (e->opt_optimize && uniq <= 256) {
         std::vector<uint2> hm;
         std::vector<uint16_t> hi, hg;
         bool ok = true;

@@ -113,6 +113,41 @@ def _tiled_index(p, dims, tile, offset=0):
     return off + loc
 
 
+_MORTON_CACHE = {}
+
+
+def _morton_rank(dims, device):
+    """rank of every point of the integer box prod(range(dims[a])) (lexicographic index, first coordinate
+    fastest) along the Morton (Z-order) curve: a numbering without any tile structure -- consecutive ids are
+    spatially compact but no two row blocks look alike, which is what a mesh numbered by a generic
+    cache-friendly traversal (DMPlex / RCM) gives the engine.  Single rank only."""
+    key = (tuple(int(d) for d in dims), str(device))
+    if key not in _MORTON_CACHE:
+        dim = len(dims)
+        n = int(np.prod(dims))
+        lex = torch.arange(n, device=device, dtype=torch.int64)
+        coords, rem = [], lex
+        for a in range(dim):
+            coords.append(rem % dims[a])
+            rem = torch.div(rem, dims[a], rounding_mode="floor")
+        code = torch.zeros(n, dtype=torch.int64, device=device)
+        for b in range(max(int(d - 1).bit_length() for d in dims)):
+            for a in range(dim):
+                code |= ((coords[a] >> b) & 1) << (b * dim + a)
+        order = torch.argsort(code)
+        rank = torch.empty(n, dtype=torch.int64, device=device)
+        rank[order] = torch.arange(n, device=device, dtype=torch.int64)
+        _MORTON_CACHE[key] = rank
+    return _MORTON_CACHE[key]
+
+
+def _numbering_index(p, dims, tile, offset=0, numbering=None):
+    """_tiled_index, or the Morton rank when numbering == "morton" """
+    if numbering == "morton":
+        return _morton_rank(dims, p.device)[_tiled_index(p, dims, 0)]
+    return _tiled_index(p, dims, tile, offset)
+
+
 @dataclass
 class Partition:
     """Box partition of the cube lattice: ``grid`` ranks per dimension."""
@@ -167,7 +202,7 @@ class SimplexMesh:
     """
 
     def __init__(self, shape, lengths=None, periodic=False, partition: Partition | None = None,
-                 tile=0, device="cpu", quadrilateral=False):
+                 tile=0, device="cpu", quadrilateral=False, numbering=None):
         self.shape = tuple(int(s) for s in shape)
         self.dim = len(self.shape)
         # quadrilateral=True: one Q1 cell per lattice square (reference examples/cahn-hilliard.py:14,
@@ -180,6 +215,8 @@ class SimplexMesh:
         self.partition = partition or Partition((1,) * self.dim, 0)
         assert not (self.periodic and self.partition.size > 1)
         self.tile = _tile_tuple(tile, len(self.shape))
+        self.numbering = numbering  # None (tiled / lexicographic) or "morton" (no tile structure; single rank)
+        assert numbering in (None, "morton")
         self.device = torch.device(device)
         dim = self.dim
         pc = self.partition.coords_of(self.partition.rank)
@@ -201,7 +238,7 @@ class SimplexMesh:
         axes = [torch.arange(dims[a], device=dev, dtype=torch.int64) for a in range(dim)]
         grids = torch.meshgrid(*axes, indexing="ij")
         p = torch.stack([g.reshape(-1) for g in grids], dim=-1)  # local cube coords
-        key = _tiled_index(p, dims, self.tile)
+        key = _numbering_index(p, dims, self.tile, 0, self.numbering)
         p = p[torch.argsort(key)]
         cube = p + torch.tensor(self.box_lo, device=dev, dtype=torch.int64)
         # a cube touches ghost nodes iff it lies in the halo layer or at the
@@ -232,7 +269,8 @@ class SimplexMesh:
         lo = torch.tensor(self.box_lo, device=dev, dtype=torch.int64)
         vdims = [self.box_hi[a] - self.box_lo[a] + 1 for a in range(dim)]
         self._vdims = vdims
-        self.cell_coord_map = _tiled_index(self.cell_vlat - lo, vdims, self.tile).to(torch.int32).contiguous()
+        self.cell_coord_map = _numbering_index(self.cell_vlat - lo, vdims, self.tile, 0,
+                                               self.numbering).to(torch.int32).contiguous()
         nv = int(np.prod(vdims))
         self.num_coord_nodes = nv
         coords = torch.zeros((nv, dim), dtype=torch.float64, device=dev)
@@ -288,13 +326,16 @@ class FunctionSpace:
     """
 
     def __init__(self, mesh: SimplexMesh, degree: int, ncomp: int = 1, layout: str = "interleaved",
-                 variant: str = "gll", tile=None, tile_offset=0):
+                 variant: str = "gll", tile=None, tile_offset=0, block_rows=192):
         assert degree in (1, 2, 3)
         assert layout in ("interleaved", "blocked")
         self.mesh, self.degree, self.ncomp, self.layout, self.variant = mesh, degree, ncomp, layout, variant
         self.dim = mesh.dim
         self.tile = (tuple(t * degree for t in mesh.tile) if tile is None else _tile_tuple(tile, mesh.dim))
         self.tile_offset = int(tile_offset)
+        self.numbering = getattr(mesh, "numbering", None)
+        self.block_rows = int(block_rows)  # rows per gather block for numberings without tiles
+        assert self.numbering is None or mesh.partition.size == 1, "Morton numbering: single rank only"
         self.nd = fem.num_nodes(self.dim, degree, mesh.cell)
         self._build()
 
@@ -341,7 +382,7 @@ class FunctionSpace:
         owned = ((q >= 0) & (q < dims_t)).all(dim=-1)
         ids = torch.full(p.shape[:-1], -1, dtype=torch.int64, device=dev)
         qo = torch.where(owned[..., None], q, torch.zeros_like(q))
-        ids_owned = _tiled_index(qo, dims, self.tile, self.tile_offset)
+        ids_owned = _numbering_index(qo, dims, self.tile, self.tile_offset, self.numbering)
         ids = torch.where(owned, ids_owned, ids)
         if part.size > 1:
             gl = self._ghost_table(rank)
@@ -515,6 +556,9 @@ class FunctionSpace:
         in the numbering): int64 tensor of nblocks+1 offsets.  The gather kernels
         use them as row blocks (one CTA per tile)."""
         dims = [self.owned_hi[a] - self.owned_lo[a] for a in range(self.dim)]
+        if self.numbering == "morton":  # no tiles: uniform chunks of consecutive (spatially compact) rows
+            starts = torch.arange(0, self.num_owned_nodes + self.block_rows, self.block_rows, dtype=torch.int64)
+            return torch.unique(starts.clamp(max=self.num_owned_nodes))
         if self.tile[0] <= 0:
             return None
         per_dim = [_tile_sizes(dims[a], self.tile[a], self.tile_offset) for a in range(self.dim)]

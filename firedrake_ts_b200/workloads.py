@@ -21,14 +21,15 @@ CONFIGS = {
 
 
 def make_problem(family, dim, degree, n, *, tile=0, partition=None, device="cpu", variant="gll", seed=0,
-                 ftile=None, foffset=0, quadrilateral=False, warp=0.0):
+                 ftile=None, foffset=0, quadrilateral=False, warp=0.0, numbering=None, block_rows=192):
     """returns (form, bcs, u, udot) with the seeded states of SURVEY.md 8(d).
 
     quadrilateral: Q1 cells (examples/cahn-hilliard.py:14); warp > 0 displaces the vertices smoothly
     (x += warp sin(2 pi x) sin(2 pi y) ...) so that quadrilaterals are no longer parallelograms and the
     non-affine geometry path is exercised; boundary vertices stay on the boundary."""
     shape = (n,) * dim
-    msh = M.SimplexMesh(shape, partition=partition, tile=tile, device=device, quadrilateral=quadrilateral)
+    msh = M.SimplexMesh(shape, partition=partition, tile=tile, device=device, quadrilateral=quadrilateral,
+                        numbering=numbering)
     if warp:
         X = msh.coords.clone()
         bump = torch.ones(X.shape[0], dtype=X.dtype, device=X.device)
@@ -37,7 +38,7 @@ def make_problem(family, dim, degree, n, *, tile=0, partition=None, device="cpu"
         for a in range(dim):
             msh.coords[:, a] = X[:, a] + warp * (1.0 + 0.5 * a) * bump
     if family in ("heat", "bbm", "diffusion"):
-        V = M.FunctionSpace(msh, degree, variant=variant, tile=ftile, tile_offset=foffset)
+        V = M.FunctionSpace(msh, degree, variant=variant, tile=ftile, tile_offset=foffset, block_rows=block_rows)
     elif family == "burgers":
         V = M.FunctionSpace(msh, degree, ncomp=dim, layout="interleaved", variant=variant)
     elif family == "cahn_hilliard":

@@ -121,7 +121,7 @@ int fdts_set_cell_tiles(fdts_handle h, const int64_t *starts_host, int64_t ntile
  *                    2 = closed-form heat kernels + owner-computes gather (deterministic, write-once);
  * schedule options (set before fdts_set_row_blocks; they never change a value beyond rounding):
  *   "plan_version" 2 (default: sector-grouped SELL + pattern dictionary) | 1 (windowed SELL, residual lists)
- *   "dedup" 1|0 share identical block tables; "optimize" 1|0 bank-conflict-aware ordering of the tables (at most 4096
+ *   "dedup" 1|0 share identical block tables; "optimize" 1|0 bank-conflict-aware ordering of the tables (at most 256
  *   unique patterns: on the host, store groups + lane orders; more, or no dictionary: lane orders on the GPU, one
  *   warp per slice; read back as "plan_optimized" 0|1|2)
  *   "sector" 4|2|1 CSR slots per store group (not set: 4, or 2 when fewer than 3/4 of the blocks repeat a pattern

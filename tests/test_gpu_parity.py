@@ -343,3 +343,24 @@ def test_gpu_lane_order_optimiser(dim, degree, n, ftile, sector):
     assert torch.equal(J1, e1.ijacobian(0.0, x, xd, 10.0))
     assert rel_err(J1.cpu().numpy(), e0.ijacobian(0.0, x, xd, 10.0).cpu().numpy()) < TOL
     assert rel_err(J1.cpu().numpy(), Oracle.from_form(form, bcs).ijacobian(0.0, u.data, udot.data, 10.0)) < TOL
+
+
+@pytest.mark.parametrize("dim,degree,n,block_rows", [(3, 2, 7, 120), (3, 2, 6, 60), (2, 2, 14, 90), (3, 1, 10, 40), (2, 1, 24, 150)])
+def test_gather_on_morton_numbering(dim, degree, n, block_rows):
+    """a numbering without any tile structure (Morton order: compact but irregular row blocks, hardly any
+    repeated pattern): gather path with uniform row blocks against the oracle; the dictionary finds (almost)
+    nothing, so the tables are per block and their lane orders come from the GPU optimiser when there are many."""
+    from firedrake_ts_b200.engine import Engine
+    from oracle import Oracle
+
+    form, bcs, u, udot = make_problem("heat", dim, degree, n, numbering="morton", block_rows=block_rows)
+    orc = Oracle.from_form(form, bcs)
+    eng = Engine(form, bcs, device="cuda:0", scatter=2)
+    rp, ci = orc.pattern()
+    grp, gci = eng.csr()
+    assert np.array_equal(grp.cpu().numpy(), rp) and np.array_equal(gci.cpu().numpy(), ci)
+    x, xd = u.data.cuda(), udot.data.cuda()
+    J = eng.ijacobian(0.0, x, xd, 10.0)
+    assert torch.equal(J, eng.ijacobian(0.0, x, xd, 10.0))
+    assert rel_err(J.cpu().numpy(), orc.ijacobian(0.0, u.data, udot.data, 10.0)) < TOL
+    assert rel_err(eng.ifunction(0.0, x, xd).cpu().numpy(), orc.ifunction(0.0, u.data, udot.data)) < TOL

@@ -30,6 +30,8 @@ ap.add_argument("--rtiles", type=int, default=0)
 ap.add_argument("--dedup", type=int, default=1)
 ap.add_argument("--foffset", type=int, default=0)
 ap.add_argument("--cache-metric", type=int, default=1)
+ap.add_argument("--numbering", default=None)
+ap.add_argument("--block-rows", type=int, default=192)
 ap.add_argument("--dmma", type=int, default=-1)
 a = ap.parse_args()
 
@@ -44,7 +46,7 @@ def _tile(v):
 
 
 form, bcs, u, udot = make_problem(a.family, a.dim, a.degree, a.n, tile=_tile(a.tile), device="cuda:0",
-                                  ftile=_tile(a.ftile), foffset=a.foffset)
+                                  ftile=_tile(a.ftile), foffset=a.foffset, numbering=a.numbering, block_rows=a.block_rows)
 torch.cuda.synchronize()
 print("mesh+space", time.time() - t0, "s; cells", form.space.mesh.num_cells, "dofs", form.space.num_dofs, flush=True)
 t0 = time.time()
