@@ -457,6 +457,21 @@ extern "C" int fdts_set_row_blocks(fdts_handle e, const int64_t *starts_host, in
       rc = fdts_build_plan2(e, starts_host, nblocks);
       e->opt_sector = 4;
     }
+    if (rc == 0) {  // the kernel's shared-memory footprint (vertex-table variant, kernels_heat.cu: launch_gather2_nt)
+      const GatherPlan2 &p = e->plan2;
+      auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+      const int dim = e->cfg.dim;
+      const size_t inA = up16(8 * (size_t)p.vmax * dim + 16) + up16(4 * (size_t)p.cmax + 16);
+      const size_t need = up16(sizeof(double) * ((size_t)p.zaddr + 16)) + up16(2 * (size_t)p.max_nidx + 64) +
+                          up16(8 * (size_t)PLAN2_MAX_CLASSES + 16) + up16(2 * (size_t)(32 / p.sector) * (size_t)p.max_nsl + 16) +
+                          2 * inA + 32 + 4 * sizeof(BlockDesc2);
+      if (need > 227 * 1024) {
+        fdts_free_plan2(e);
+        fdts_set_error("gather plan: a row block needs " + std::to_string(need / 1024) +
+                       " KB of shared memory (limit 227 KB): use smaller row blocks");
+        return 4;
+      }
+    }
     return rc;
   }
   fdts_free_plan2(e);

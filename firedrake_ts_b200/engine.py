@@ -207,10 +207,22 @@ class Engine:
         if scatter is not None:
             if int(scatter) == 2:
                 starts = V.row_block_starts()
-                if starts is None:  # untiled numbering: uniform blocks
-                    starts = torch.arange(0, V.num_owned_nodes + 128, 128).clamp(max=V.num_owned_nodes)
-                    starts = torch.unique(starts)
-                self.set_row_blocks(starts)
+                if starts is None:
+                    # untiled numbering (e.g. a live Firedrake space): uniform chunks of consecutive rows; how many
+                    # cells / vertices a chunk touches depends on the numbering, so shrink until the plan fits
+                    err = None
+                    for rows in (160, 128, 96, 64, 32):
+                        starts = torch.unique(torch.arange(0, V.num_owned_nodes + rows, rows).clamp(max=V.num_owned_nodes))
+                        try:
+                            self.set_row_blocks(starts)
+                            err = None
+                            break
+                        except EngineError as exc:
+                            err = exc
+                    if err is not None:
+                        raise err
+                else:
+                    self.set_row_blocks(starts)
                 if form.family == 0 and V.ncomp == 1 and (options or {}).get("residual_tiles", 0):
                     self.set_cell_tiles(m.cell_tile_starts(max_pairs=4096 // V.nd))
             self.set_option("scatter", scatter)

@@ -364,3 +364,25 @@ def test_gather_on_morton_numbering(dim, degree, n, block_rows):
     assert torch.equal(J, eng.ijacobian(0.0, x, xd, 10.0))
     assert rel_err(J.cpu().numpy(), orc.ijacobian(0.0, u.data, udot.data, 10.0)) < TOL
     assert rel_err(eng.ifunction(0.0, x, xd).cpu().numpy(), orc.ifunction(0.0, u.data, udot.data)) < TOL
+
+
+def test_untiled_numbering_shrinks_row_blocks():
+    """a numbering the engine knows nothing about (row_block_starts() is None, as for a live Firedrake space): uniform
+    chunks of rows are tried from 160 downwards until the plan fits; values against the oracle."""
+    from firedrake_ts_b200.engine import Engine
+    from oracle import Oracle
+
+    form, bcs, u, udot = make_problem("heat", 3, 2, 10, numbering="morton")
+    form.space.row_block_starts = lambda: None
+    eng = Engine(form, bcs, device="cuda:0", scatter=2)
+    nb = eng.get_option("plan_blocks")
+    assert nb >= form.space.num_owned_nodes // 160
+    x, xd = u.data.cuda(), udot.data.cuda()
+    J = eng.ijacobian(0.0, x, xd, 10.0)
+    assert rel_err(J.cpu().numpy(), Oracle.from_form(form, bcs).ijacobian(0.0, u.data, udot.data, 10.0)) < TOL
+    # lexicographic numbering of a 3-D mesh: 160 consecutive rows form a pencil that touches far too many cells
+    form, bcs, u, udot = make_problem("heat", 3, 2, 24, tile=0)
+    eng = Engine(form, bcs, device="cuda:0", scatter=2)
+    assert eng.get_option("plan_blocks") > form.space.num_owned_nodes // 160
+    J = eng.ijacobian(0.0, u.data.cuda(), udot.data.cuda(), 10.0)
+    assert rel_err(J.cpu().numpy(), Oracle.from_form(form, bcs).ijacobian(0.0, u.data, udot.data, 10.0)) < TOL
